@@ -1,0 +1,141 @@
+// hm_common.cuh -- shared device/host helpers of libhalob200 (sm_100a, fp64 throughout).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/halob200.h"
+
+// ---- error plumbing (never throw across the C ABI) -------------------------------------------------------------
+void hm_set_error(const char* fmt, ...);
+int hm_check_device();   // HM_OK or HM_ERR_NODEVICE (cached)
+
+#define HM_CUDA_TRY(expr)                                                                            \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess) {                                                                         \
+      hm_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(_e));     \
+      return HM_ERR_CUDA;                                                                            \
+    }                                                                                                \
+  } while (0)
+
+#define HM_REQUIRE(cond, msg)                                  \
+  do {                                                         \
+    if (!(cond)) {                                             \
+      hm_set_error("%s: %s", __func__, msg);                   \
+      return HM_ERR_INVALID;                                   \
+    }                                                          \
+  } while (0)
+
+#define HM_LAUNCH_CHECK()                                                                    \
+  do {                                                                                       \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess) {                                                                 \
+      hm_set_error("kernel launch failed at %s:%d: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+      return HM_ERR_CUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+static inline int hm_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// ---- streaming loads: (k,M) grids are read exactly once, keep them out of L1 ---------------------------------
+__device__ __forceinline__ double2 hm_ldg_stream2(const double* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double hm_ldg_stream1(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
+// ---- mass function g(nu) and linear bias b(nu) ---------------------------------------------------------------
+// Operation order follows pyhalomodel.py:217-284 so that the only differences are libm-vs-CUDA ulps.
+__device__ __forceinline__ double hm_g_nu(const hm_model_desc& d, double nu) {
+  const double* P = d.par;
+  switch (d.family) {
+    case HM_PS74:
+      return sqrt(2. / M_PI) * exp(-(nu * nu) / 2.);                              // :223
+    case HM_ST99:
+    case HM_SMT01:
+    case HM_DESPALI16: {
+      const double A = P[0], q = P[1], p = P[2];
+      const double nu2 = nu * nu;
+      return A * (1. + pow(q * nu2, -p)) * exp(-q * nu2 / 2.);                     // :228
+    }
+    case HM_TINKER10:
+    case HM_TINKER10_PBS: {
+      const double f1 = 1. + pow(P[1] * nu, -2. * P[3]);                           // :235
+      const double f2 = pow(nu, 2. * P[4]);                                        // :236
+      const double f3 = exp(-P[2] * (nu * nu) / 2.);                               // :237
+      return P[0] * f1 * f2 * f3;
+    }
+  }
+  return nan("");
+}
+
+__device__ __forceinline__ double hm_b_nu(const hm_model_desc& d, double nu) {
+  const double* P = d.par;
+  const double dc = d.dc;
+  switch (d.family) {
+    case HM_PS74:
+      return 1. + (nu * nu - 1.) / dc;                                            // :248
+    case HM_ST99:
+    case HM_DESPALI16: {
+      const double q = P[1], p = P[2];
+      const double qn2 = q * (nu * nu);
+      return 1. + (qn2 - 1. + 2. * p / (1. + pow(qn2, p))) / dc;                   // :252
+    }
+    case HM_SMT01: {
+      const double a = P[3], b = P[4], c = P[5];
+      const double sa = sqrt(a);
+      const double anu2 = a * (nu * nu);
+      const double f1 = sa * anu2;
+      const double f2 = sa * b * pow(anu2, 1. - c);
+      const double f3 = pow(anu2, c);
+      const double f4 = f3 + b * (1. - c) * (1. - c / 2.);
+      return 1. + (f1 + f2 - f3 / f4) / (dc * sa);                                 // :254-262
+    }
+    case HM_TINKER10: {
+      const double nua = pow(nu, P[6]);
+      const double fA = P[5] * nua / (nua + pow(dc, P[6]));                        // :279
+      const double fB = P[7] * pow(nu, P[8]);
+      const double fC = P[9] * pow(nu, P[10]);
+      return 1. - fA + fB + fC;                                                    // :282
+    }
+    case HM_TINKER10_PBS: {
+      const double f1 = (P[2] * (nu * nu) - (1. + 2. * P[4])) / dc;                // :269
+      const double f2 = (2. * P[3] / dc) / (1. + pow(P[1] * nu, 2. * P[3]));       // :270
+      return 1. + f1 + f2;
+    }
+  }
+  return nan("");
+}
+
+// ---- warp / block reductions (fixed order => bitwise reproducible run to run) --------------------------------
+__device__ __forceinline__ double hm_warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// Sum `v` over the whole CTA; every thread gets the result.  `scratch` holds >= 32 doubles.
+__device__ __forceinline__ double hm_block_sum(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  v = hm_warp_sum(v);
+  __syncthreads();                      // protect scratch against the previous use
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double t = (lane < nwarps) ? scratch[lane] : 0.;
+  return hm_warp_sum(t);
+}

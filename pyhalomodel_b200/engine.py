@@ -1,0 +1,245 @@
+"""
+Device-side engine: thin, batch-capable wrappers over the C ABI (include/halob200.h) working on torch float64
+CUDA tensors.  The reference-shaped API in `halomodel.py` and the sweep driver in `sweep.py` both sit on this.
+
+PyTorch is plumbing here (device memory, streams); all arithmetic happens in libhalob200.so.  Nothing in this
+module can run without a CUDA device and there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import HaloB200Error, ModelDesc, Problem, check, lib
+
+F64 = torch.float64
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise HaloB200Error('no CUDA device visible: pyhalomodel_b200 runs on B200 only and has no CPU fallback')
+    return torch.device('cuda', torch.cuda.current_device())
+
+
+def is_host(x):
+    """True if `x` lives on the host (numpy array, scalar, list, CPU tensor)."""
+    return not (isinstance(x, torch.Tensor) and x.is_cuda)
+
+
+def to_dev(x, shape=None):
+    """numpy / list / scalar / torch tensor  ->  contiguous float64 CUDA tensor (a copy only when needed)."""
+    dev = device()
+    if isinstance(x, torch.Tensor):
+        t = x.to(device=dev, dtype=F64, non_blocking=True)
+    else:
+        a = np.asarray(x, dtype=np.float64)
+        if a.ndim and not a.flags.c_contiguous:      # (np.ascontiguousarray would promote scalars to 1-d)
+            a = np.ascontiguousarray(a)
+        t = torch.from_numpy(a).to(dev, non_blocking=True)
+    t = t.contiguous()
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise ValueError('expected shape %s, got %s' % (tuple(shape), tuple(t.shape)))
+    return t
+
+
+def to_host(t):
+    return t.detach().cpu().numpy()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def pack_models(descs):
+    """list of ModelDesc -> uint8 CUDA tensor holding the packed hm_model_desc array."""
+    arr = (ModelDesc*len(descs))(*descs)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def massfn_nu(desc: ModelDesc, nu, want_g=True, want_b=True):
+    nu = to_dev(nu)
+    g = torch.empty_like(nu) if want_g else None
+    b = torch.empty_like(nu) if want_b else None
+    check(lib().hm_massfn_nu(C.byref(desc), _ptr(nu), nu.numel(), _ptr(g), _ptr(b), _stream()))
+    return g, b
+
+
+def low_mass_correction(descs, nu0):
+    nu0 = to_dev(nu0).reshape(-1)
+    models = pack_models(descs)
+    A = torch.empty_like(nu0)
+    check(lib().hm_low_mass_correction(_ptr(models), _ptr(nu0), nu0.numel(), _ptr(A), _stream()))
+    return A
+
+
+def average(desc: ModelDesc, M, sigma, funcs):
+    """funcs: [nf, nM] -> [nf] halo averages (model.average, pyhalomodel.py:335-359)."""
+    M, sigma, funcs = to_dev(M), to_dev(sigma), to_dev(funcs)
+    if funcs.dim() == 1:
+        funcs = funcs[None, :]
+    nf, nM = funcs.shape
+    out = torch.empty(nf, dtype=F64, device=M.device)
+    check(lib().hm_average(C.byref(desc), _ptr(M), _ptr(sigma), nM, _ptr(funcs), nf, _ptr(out), _stream()))
+    return out
+
+
+def sici(x):
+    x = to_dev(x)
+    si, ci = torch.empty_like(x), torch.empty_like(x)
+    check(lib().hm_sici(_ptr(x), x.numel(), _ptr(si), _ptr(ci), _stream()))
+    return si, ci
+
+
+def window_nfw(k, rv, c):
+    """k [nk]; rv, c [nM] or [G, nM]  ->  U [nk, nM] or [G, nk, nM] (pyhalomodel.py:1040-1055)."""
+    k, rv, c = to_dev(k), to_dev(rv), to_dev(c)
+    batched = rv.dim() == 2
+    G, nM = (rv.shape if batched else (1, rv.shape[0]))
+    out = torch.empty((G, k.shape[0], nM), dtype=F64, device=k.device)
+    check(lib().hm_window_nfw(_ptr(k), _ptr(rv), _ptr(c), k.shape[0], nM, G, _ptr(out), _stream()))
+    return out if batched else out[0]
+
+
+def window_isothermal(k, rv):
+    k, rv = to_dev(k), to_dev(rv)
+    batched = rv.dim() == 2
+    G, nM = (rv.shape if batched else (1, rv.shape[0]))
+    out = torch.empty((G, k.shape[0], nM), dtype=F64, device=k.device)
+    check(lib().hm_window_isothermal(_ptr(k), _ptr(rv), k.shape[0], nM, G, _ptr(out), _stream()))
+    return out if batched else out[0]
+
+
+def sigma_tophat(kgrid, Pk, dlnk, R):
+    """kgrid [nkg]; Pk [nkg] or [G, nkg]; R [nR] or [G, nR] -> sigma with R's shape (cosmology.py:89-106)."""
+    kgrid, Pk, R = to_dev(kgrid), to_dev(Pk), to_dev(R)
+    batched = R.dim() == 2
+    R2 = R if batched else R[None, :]
+    P2 = Pk if Pk.dim() == 2 else Pk[None, :].expand(R2.shape[0], -1).contiguous()
+    G, nR = R2.shape
+    out = torch.empty_like(R2)
+    for g0 in range(0, G, 65535):
+        g1 = min(G, g0+65535)
+        check(lib().hm_sigma_tophat(_ptr(kgrid), _ptr(P2[g0:g1]), float(dlnk), kgrid.shape[0], _ptr(R2[g0:g1]), nR,
+                                    g1-g0, _ptr(out[g0:g1]), _stream()))
+    return out if batched else out[0]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class Tracer:
+    """Device-side description of one halo profile for a batch (mirrors hm_tracer)."""
+    __slots__ = ('grid', 'wk', 'amplitude', 'variance', 'normalisation', 'mode', 'mass_tracer', 'discrete_tracer')
+
+    def __init__(self, grid, amplitude, normalisation, variance=None, wk=None, mode=_lib.GRID_UK,
+                 mass_tracer=False, discrete_tracer=False):
+        self.grid, self.wk, self.amplitude, self.variance = grid, wk, amplitude, variance
+        self.normalisation, self.mode = normalisation, mode
+        self.mass_tracer, self.discrete_tracer = bool(mass_tracer), bool(discrete_tracer)
+
+
+class PowerSpectrumPlan:
+    """A validated hm_problem plus its workspace and output buffers, reusable across calls (no allocation and
+    no host work in the steady state; CUDA-graph friendly)."""
+
+    def __init__(self, k, Pk_lin, M, sigma, tracers, models, models_per_sample=1, simple_twohalo=False,
+                 subtract_shotnoise=True, correct_discrete=True, k_trunc=None):
+        self.k, self.M = to_dev(k), to_dev(M)
+        nk, nM = self.k.shape[0], self.M.shape[0]
+        self.Pk_lin, self.sigma = to_dev(Pk_lin), to_dev(sigma)
+        if self.Pk_lin.dim() == 1:
+            self.Pk_lin = self.Pk_lin[None, :]
+        if self.sigma.dim() == 1:
+            self.sigma = self.sigma[None, :]
+        G = self.sigma.shape[0]
+        if tuple(self.Pk_lin.shape) != (G, nk) or self.sigma.shape[1] != nM:
+            raise ValueError('Pk_lin must be [G, nk] and sigma [G, nM]')
+        P = len(tracers)
+        if not 1 <= P <= _lib.HM_MAX_TRACERS:
+            raise ValueError('between 1 and %d tracers are supported by the quadrature path' % _lib.HM_MAX_TRACERS)
+        B = G*models_per_sample
+        self.tracers = tracers
+        self.G, self.B, self.P, self.S, self.nk, self.nM = G, B, P, P*(P+1)//2, nk, nM
+        self.keep = []          # tensors the C struct borrows
+        pr = Problem()
+        pr.nk, pr.nM, pr.n_tracers, pr.n_samples, pr.models_per_sample = nk, nM, P, G, models_per_sample
+        pr.simple_twohalo, pr.subtract_shotnoise = int(bool(simple_twohalo)), int(bool(subtract_shotnoise))
+        pr.correct_discrete = int(bool(correct_discrete))
+        pr.k_trunc = float(k_trunc) if k_trunc is not None else 0.
+        pr.k_dev, pr.M_dev = self.k.data_ptr(), self.M.data_ptr()
+        pr.sigma_dev, pr.Pk_lin_dev = self.sigma.data_ptr(), self.Pk_lin.data_ptr()
+        if isinstance(models, torch.Tensor):
+            self.models_dev = models
+            pr.models_dev = models.data_ptr()
+        elif len(models) == 1 and B == 1:
+            self.models_dev = None
+            pr.models_dev = None
+            pr.model_host = models[0]
+        else:
+            if len(models) != B:
+                raise ValueError('need one model descriptor per model (%d), got %d' % (B, len(models)))
+            self.models_dev = pack_models(models)
+            pr.models_dev = self.models_dev.data_ptr()
+        for p, t in enumerate(tracers):
+            grid = to_dev(t.grid)
+            grid = grid if grid.dim() == 3 else grid[None]
+            if tuple(grid.shape) != (G, nk, nM):
+                raise ValueError('tracer %d: grid must be [G, nk, nM]' % p)
+            ct = pr.tracers[p]
+            ct.grid_dev = grid.data_ptr()
+            self.keep.append(grid)
+            if t.mode == _lib.GRID_SEPARATE:
+                wk = to_dev(t.wk)
+                wk = wk if wk.dim() == 3 else wk[None]
+                ct.wk_dev = wk.data_ptr()
+                self.keep.append(wk)
+            if t.amplitude is not None:
+                amp = to_dev(t.amplitude).reshape(G, nM)
+                ct.amplitude_dev = amp.data_ptr()
+                self.keep.append(amp)
+            elif t.mode != _lib.GRID_WK:
+                raise ValueError('tracer %d: amplitude is required' % p)
+            if t.variance is not None:
+                var = to_dev(t.variance).reshape(G, nM)
+                ct.variance_dev = var.data_ptr()
+                self.keep.append(var)
+            norm = t.normalisation
+            norm = to_dev(np.full(B, float(norm))) if np.isscalar(norm) else to_dev(norm).reshape(B)
+            ct.normalisation_dev = norm.data_ptr()
+            self.keep.append(norm)
+            ct.grid_mode, ct.mass_tracer, ct.discrete_tracer = int(t.mode), int(t.mass_tracer), int(t.discrete_tracer)
+        self.problem = pr
+        nbytes = lib().hm_power_spectrum_workspace(C.byref(pr))
+        dev = self.k.device
+        self.workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        self.workspace_bytes = nbytes
+        self.out = torch.empty((B, self.S, 3, nk), dtype=F64, device=dev)
+        self.lowmass = torch.empty(B, dtype=F64, device=dev)
+
+    def weights(self):
+        check(lib().hm_halo_weights(C.byref(self.problem), _ptr(self.lowmass), _ptr(self.workspace),
+                                    self.workspace_bytes, _stream()))
+
+    def quadrature(self):
+        check(lib().hm_mass_quadrature(C.byref(self.problem), _ptr(self.out), _ptr(self.workspace),
+                                       self.workspace_bytes, _stream()))
+
+    def run(self):
+        """Enqueue both stages on the current stream; returns (out [B,S,3,nk], A [B]) device tensors."""
+        check(lib().hm_power_spectrum(C.byref(self.problem), _ptr(self.out), _ptr(self.lowmass), _ptr(self.workspace),
+                                      self.workspace_bytes, _stream()))
+        return self.out, self.lowmass
+
+    def algorithmic_bytes(self):
+        """Bytes the quadrature kernel must move per launch: every distinct grid once, the weight vectors once
+        per model, P_lin once per sample, three output vectors per unique pair."""
+        ngrids = sum(2 if t.mode == _lib.GRID_SEPARATE else 1 for t in self.tracers)
+        return 8*(self.G*ngrids*self.nk*self.nM + self.B*(self.P+self.S)*self.nM + self.G*self.nk
+                  + self.B*3*self.S*self.nk)

@@ -1,0 +1,512 @@
+"""
+Reference-shaped API of the B200 halo-model engine: `model`, `profile` and the module functions of
+pyhalomodel/pyhalomodel.py, with the same names, arguments, dictionary conventions, exceptions and warnings, and
+the arithmetic done by libhalob200.so (hand-written sm_100a CUDA, fp64) on torch CUDA tensors.
+
+    import pyhalomodel_b200 as halo
+    hmod = halo.model(z, Om_m, name='Tinker et al. (2010)', Dv=330., dc=1.686)
+    Pk_2h, Pk_1h, Pk_hm = hmod.power_spectrum(k, Pk_lin, M, sigmaM, {'m': matter, 'g': galaxies})
+
+Array arguments may be numpy arrays or torch tensors.  Results come back as numpy arrays unless an input of the
+call was a CUDA tensor, in which case they stay on the device.  There is no CPU fallback.
+
+Module-level switches are read at call time, as in the reference (pyhalomodel.py:16-46).
+"""
+from __future__ import annotations
+
+import warnings
+from time import time
+
+import numpy as np
+import torch
+
+from . import _lib, constants, cosmology, engine
+from . import utility as util
+from ._lib import ModelDesc
+
+# Parameters (same names as pyhalomodel.py:16-46)
+dc_rel_tol = 1e-3
+Dv_rel_tol = 1e-3
+Tinker_z_dep = False    # redshift-dependent Tinker et al. (2010) parameters (pyhalomodel.py:20, :163-167)
+Tinker_PBS = False      # peak-background-split bias for Tinker et al. (2010) (pyhalomodel.py:22, :264-271)
+halo_integration = 'trapezoid'    # the only mass integrator with a parity oracle (pyhalomodel.py:27)
+
+_FAMILY = {'Press & Schecter (1974)': _lib.PS74, 'Sheth & Tormen (1999)': _lib.ST99,
+           'Sheth, Mo & Tormen (2001)': _lib.SMT01, 'Tinker et al. (2010)': _lib.TINKER10,
+           'Despali et al. (2016)': _lib.DESPALI16}
+
+_TINKER_DV = np.array([200., 300., 400., 600., 800., 1200., 1600, 2400., 3200.])
+_TINKER_TABLE4 = dict(   # Tinker et al. (2010) table 4, as tabulated at pyhalomodel.py:142-151
+    alpha=[0.368, 0.363, 0.385, 0.389, 0.393, 0.365, 0.379, 0.355, 0.327],
+    beta=[0.589, 0.585, 0.544, 0.543, 0.564, 0.623, 0.637, 0.673, 0.702],
+    gamma=[0.864, 0.922, 0.987, 1.09, 1.20, 1.34, 1.50, 1.68, 1.81],
+    phi=[-0.729, -0.789, -0.910, -1.05, -1.20, -1.26, -1.45, -1.50, -1.49],
+    eta=[-0.243, -0.261, -0.261, -0.273, -0.278, -0.301, -0.301, -0.319, -0.336])
+
+
+def _lin_interp_extrap(x, xs, ys):
+    """Piecewise-linear interpolation with linear extrapolation from the end segments, in the two-weight form
+    the installed scipy interp1d(fill_value='extrapolate') evaluates (so the Tinker parameters of
+    pyhalomodel.py:152-161 are reproduced to the bit): w_hi*y_hi + w_lo*y_lo on the bracketing/end segment."""
+    xs, ys = np.asarray(xs, dtype=float), np.asarray(ys, dtype=float)
+    hi = int(np.clip(np.searchsorted(xs, x), 1, len(xs)-1))
+    lo = hi-1
+    return ((x-xs[lo])/(xs[hi]-xs[lo]))*ys[hi]+((xs[hi]-x)/(xs[hi]-xs[lo]))*ys[lo]
+
+
+def _wants_device(*arrays):
+    return any(isinstance(a, torch.Tensor) and a.is_cuda for a in arrays)
+
+
+def _give_back(t, on_device):
+    return t if on_device else engine.to_host(t)
+
+
+class model():
+    '''
+    Halo model: mass function g(nu), linear bias b(nu) and halo-model power spectra (pyhalomodel.py:51-719)
+    '''
+
+    def __init__(self, z: float, Om_m: float, name='Tinker et al. (2010)', Dv=200., dc=1.686, verbose=False):
+        '''
+        Args (identical to the reference, pyhalomodel.py:56-71):
+            z: Redshift
+            Om_m: Cosmological matter density
+            name: 'Press & Schecter (1974)' | 'Sheth & Tormen (1999)' | 'Sheth, Mo & Tormen (2001)' |
+                  'Tinker et al. (2010)' | 'Despali et al. (2016)'
+            Dv: Halo overdensity definition
+            dc: Halo linear collapse threshold
+        '''
+        self.z = z
+        self.a = cosmology.scalefactor_from_redshift(z)
+        self.Om_m = Om_m
+        self.name = name
+        self.dc = dc
+        self.Dv = Dv
+        self.rhom = cosmology.comoving_matter_density(Om_m)
+        if verbose:
+            print('Initialising halo model')
+            print('Halo model:', self.name)
+            print('Redshift: %1.3f' % (self.z))
+            print('Scale factor: %1.3f' % (self.a))
+            print('Omega_m(z=0): %1.3f' % (self.Om_m))
+            print('delta_c: %1.4f' % (self.dc))
+            print('Delta_v: %4.1f' % (self.Dv))
+        if name not in _FAMILY:
+            raise ValueError('Halo model not recognised')
+        if name in ('Sheth & Tormen (1999)', 'Sheth, Mo & Tormen (2001)'):
+            from scipy.special import gamma as Gamma
+            self.p_ST, self.q_ST = 0.3, 0.707
+            self.A_ST = np.sqrt(2.*self.q_ST)/(np.sqrt(np.pi)+Gamma(0.5-self.p_ST)/2**self.p_ST)   # ~0.2161
+            if name == 'Sheth, Mo & Tormen (2001)':
+                self.a_SMT, self.b_SMT, self.c_SMT = 0.707, 0.5, 0.6
+        elif name == 'Despali et al. (2016)':
+            self.p_ST, self.q_ST = 0.2536, 0.7689
+            self.A_ST = 0.3295*np.sqrt(2.*self.q_ST/np.pi)
+        elif name == 'Tinker et al. (2010)':
+            lnDv, lnDv_tab = np.log(self.Dv), np.log(_TINKER_DV)
+            par = {key: _lin_interp_extrap(lnDv, lnDv_tab, tab) for key, tab in _TINKER_TABLE4.items()}
+            if Tinker_z_dep:    # equations (9-12) of Tinker et al. (2010); only calibrated for M200
+                par['beta'] *= (1.+z)**0.20
+                par['gamma'] *= (1.+z)**-0.01
+                par['phi'] *= (1.+z)**-0.08
+                par['eta'] *= (1.+z)**0.27
+            self.alpha_Tinker, self.beta_Tinker, self.gamma_Tinker = par['alpha'], par['beta'], par['gamma']
+            self.phi_Tinker, self.eta_Tinker = par['phi'], par['eta']
+            y = np.log10(self.Dv)       # calibrated bias, table 2
+            e = np.exp(-(4./y)**4)
+            self.A_Tinker, self.a_Tinker = 1.+0.24*y*e, 0.44*y-0.88
+            self.B_Tinker, self.b_Tinker = 0.183, 1.5
+            self.C_Tinker, self.c_Tinker = 0.019+0.107*y+0.19*e, 2.4
+        if verbose:
+            self._print_parameters()
+            print()
+
+    def _print_parameters(self):
+        if self.name in ['Sheth & Tormen (1999)', 'Sheth, Mo & Tormen (2001)', 'Despali et al. (2016)']:
+            print('p: %1.3f; q: %1.3f; A: %1.4f' % (self.p_ST, self.q_ST, self.A_ST))
+            if self.name in ['Sheth, Mo & Tormen (2001)']:
+                print('a: %1.3f; b: %1.3f; c: %1.3f' % (self.a_SMT, self.b_SMT, self.c_SMT))
+        elif self.name in ['Tinker et al. (2010)']:
+            print('alpha: %1.3f; beta: %1.3f; gamma: %1.3f; phi: %1.3f; eta: %1.3f'
+                  % (self.alpha_Tinker, self.beta_Tinker, self.gamma_Tinker, self.phi_Tinker, self.eta_Tinker))
+            print('A: %1.3f; a: %1.3f' % (self.A_Tinker, self.a_Tinker))
+            print('B: %1.3f; b: %1.3f' % (self.B_Tinker, self.b_Tinker))
+            print('C: %1.3f; c: %1.3f' % (self.C_Tinker, self.c_Tinker))
+
+    def __str__(self):
+        print('Halo model:', self.name)
+        print('Scale factor: %1.3f' % (self.a))
+        print('Redshift: %1.3f' % (self.z))
+        print('Omega_m(z=0): %1.3f' % (self.Om_m))
+        print('delta_c: %1.4f' % (self.dc))
+        print('Delta_v: %4.1f' % (self.Dv))
+        if self.name != 'Press & Schecter (1974)':
+            print('Parameters:')
+        self._print_parameters()
+        return ''
+
+    # -- C-ABI descriptor -----------------------------------------------------------------------------------
+    def descriptor(self) -> ModelDesc:
+        '''hm_model_desc of this model (include/halob200.h); Tinker_PBS is read now, as the reference does.'''
+        d = ModelDesc()
+        d.family, d.dc, d.rhom = _FAMILY[self.name], float(self.dc), float(self.rhom)
+        if d.family in (_lib.ST99, _lib.SMT01, _lib.DESPALI16):
+            d.par[0], d.par[1], d.par[2] = self.A_ST, self.q_ST, self.p_ST
+            if d.family == _lib.SMT01:
+                d.par[3], d.par[4], d.par[5] = self.a_SMT, self.b_SMT, self.c_SMT
+        elif d.family == _lib.TINKER10:
+            vals = (self.alpha_Tinker, self.beta_Tinker, self.gamma_Tinker, self.phi_Tinker, self.eta_Tinker,
+                    self.A_Tinker, self.a_Tinker, self.B_Tinker, self.b_Tinker, self.C_Tinker, self.c_Tinker)
+            for i, v in enumerate(vals):
+                d.par[i] = float(v)
+            if Tinker_PBS:
+                d.family = _lib.TINKER10_PBS
+        return d
+
+    # -- functions of nu ------------------------------------------------------------------------------------
+    def _mass_function_nu(self, nu):
+        '''g(nu) with nu=delta_c/sigma(M); integrates to unity (pyhalomodel.py:217-240)'''
+        g, _ = engine.massfn_nu(self.descriptor(), nu, want_b=False)
+        return _give_back(g, _wants_device(nu))
+
+    def _linear_bias_nu(self, nu):
+        '''b(nu) (pyhalomodel.py:242-284)'''
+        _, b = engine.massfn_nu(self.descriptor(), nu, want_g=False)
+        return _give_back(b, _wants_device(nu))
+
+    def _peak_height(self, M, sigmaM):
+        '''nu = delta_c/sigma(M) (pyhalomodel.py:706-711)'''
+        return self.dc/sigmaM
+
+    def linear_bias(self, M, sigmaM):
+        '''Linear halo bias as a function of halo mass (pyhalomodel.py:317-325)'''
+        return self._linear_bias_nu(self._peak_height(M, sigmaM))
+
+    def multiplicity_function(self, M, sigmaM):
+        '''M^2 n(M)/rhobar (pyhalomodel.py:298-315): g(nu) dnu/dlnM with the reference's three-point Lagrange
+        derivative of ln sigma against ln R (utility.py:15-35), vectorised on the device.'''
+        on_dev = _wants_device(M, sigmaM)
+        Md, sd = engine.to_dev(M), engine.to_dev(sigmaM)
+        nu = self.dc/sd
+        x = torch.log(torch.as_tensor(self.Lagrangian_radius(engine.to_host(Md)), device=Md.device))
+        f = torch.log(sd)
+        n = x.shape[0]
+        i1 = torch.arange(n, device=Md.device).clamp(1, n-2)      # stencil centre: (0,1,2) and (n-3,n-2,n-1) at the ends
+        x0, x1, x2 = x[i1-1], x[i1], x[i1+1]
+        f0, f1, f2 = f[i1-1], f[i1], f[i1+1]
+        d = (f0*(2.*x-x1-x2)/((x0-x1)*(x0-x2))+f1*(2.*x-x0-x2)/((x1-x0)*(x1-x2))+f2*(2.*x-x0-x1)/((x2-x0)*(x2-x1)))
+        g, _ = engine.massfn_nu(self.descriptor(), nu, want_b=False)
+        return _give_back(g*(-(nu/6.)*(2.*d)), on_dev)
+
+    def mass_function(self, M, sigmaM):
+        '''n(M) = F rhom/M^2 (pyhalomodel.py:286-296)'''
+        F = self.multiplicity_function(M, sigmaM)
+        return F*self.rhom/M**2
+
+    def Lagrangian_radius(self, M):
+        '''Radius [Mpc/h] of a sphere containing mass M in a homogeneous universe (pyhalomodel.py:327-333)'''
+        return cosmology.Lagrangian_radius(M, self.Om_m)
+
+    def virial_radius(self, M):
+        '''Halo virial radius from the halo mass and overdensity (pyhalomodel.py:713-719)'''
+        R = self.Lagrangian_radius(M)
+        return R/np.cbrt(self.Dv)
+
+    def average(self, M, sigmaM, func):
+        '''<f> = int f(M) n(M) dM = rhom trapz((f/M) g(nu), nu) (pyhalomodel.py:335-359)'''
+        Mh = engine.to_host(M) if isinstance(M, torch.Tensor) else np.asarray(M)
+        if not util.is_array_monotonic(Mh):
+            raise ValueError('Halo mass array must be increasing monotonically')
+        out = engine.average(self.descriptor(), M, sigmaM, func)
+        return out[0] if _wants_device(M, sigmaM, func) else float(out[0].item())
+
+    # -- the hot path ---------------------------------------------------------------------------------------
+    def power_spectrum(self, k, Pk_lin, M, sigmaM, profiles: dict, beta=None, simple_twohalo=False,
+                       subtract_shotnoise=True, correct_discrete=True, k_trunc=None, verbose=False) -> tuple:
+        '''
+        Halo-model power spectra; returns the two-halo, one-halo and total dictionaries keyed 'u-v' for every
+        ordered pair of profiles (pyhalomodel.py:361-513).  Arguments as in the reference.  `beta`
+        (non-linear halo bias) is not on the B200 path yet and raises NotImplementedError.
+        '''
+        if verbose:
+            t_start = time()
+        if simple_twohalo and (beta is not None):
+            raise ValueError('A simple two-halo term is not compatible with non-linear halo bias')
+        Mh = engine.to_host(M) if isinstance(M, torch.Tensor) else np.asarray(M, dtype=float)
+        kh = engine.to_host(k) if isinstance(k, torch.Tensor) else np.asarray(k, dtype=float)
+        if not util.is_array_monotonic(Mh):
+            raise ValueError('Halo mass array must be increasing monotonically')
+        if not isinstance(profiles, dict):
+            raise TypeError('profiles must be a dictionary')
+        for prof in profiles.values():
+            if np.shape(kh) != np.shape(prof.k) or (kh != prof.k).all():
+                raise ValueError('k arrays must all be identical to those in profiles')
+            if np.shape(Mh) != np.shape(prof.M) or (Mh != prof.M).all():
+                raise ValueError('Mass arrays must be identical to those in profiles')
+        if beta is not None:
+            raise NotImplementedError('beta_NL (pyhalomodel.py:546-571) is a "next" row of the B200 build')
+        on_dev = _wants_device(k, Pk_lin, M, sigmaM)
+        names = list(profiles.keys())
+        if len(names) > _lib.HM_MAX_TRACERS:
+            from . import manytracer
+            return manytracer.power_spectrum(self, k, Pk_lin, M, sigmaM, profiles, simple_twohalo=simple_twohalo,
+                                             subtract_shotnoise=subtract_shotnoise, correct_discrete=correct_discrete,
+                                             k_trunc=k_trunc, on_device=on_dev)
+        tracers = [prof._tracer() for prof in profiles.values()]
+        plan = engine.PowerSpectrumPlan(k, Pk_lin, M, sigmaM, tracers, [self.descriptor()],
+                                        simple_twohalo=simple_twohalo, subtract_shotnoise=subtract_shotnoise,
+                                        correct_discrete=correct_discrete, k_trunc=k_trunc)
+        out, lowmass = plan.run()
+        if on_dev:
+            res, A = out[0], float(lowmass[0].item())
+        else:   # one device->host copy for everything the caller sees
+            packed = torch.cat([out.reshape(-1), lowmass]).cpu().numpy()
+            res, A = packed[:-1].reshape(plan.S, 3, plan.nk), float(packed[-1])
+        if verbose:
+            sig = engine.to_host(engine.to_dev(sigmaM))
+            print('Redshift:', self.z)
+            print('Halo mass range [log10(Msun/h)]:', np.log10(Mh[0]), np.log10(Mh[-1]))
+            print('Peak height range:', self.dc/sig[0], self.dc/sig[-1])
+            print('Number of integration points:', len(Mh))
+            print('Missing halo-bias-mass from the low-mass end of the two-halo integrand:', A)
+        if A < 0.:
+            warnings.warn('Warning: Mass function/bias correction is negative!', RuntimeWarning)
+        if (not correct_discrete) and subtract_shotnoise and any(p.discrete_tracer for p in profiles.values()):
+            warnings.warn('Warning: Subtracting shot noise while not treating discreteness properly is bad',
+                          RuntimeWarning)
+        Pk_2h_dict, Pk_1h_dict, Pk_hm_dict = {}, {}, {}
+        s = 0
+        for iu, name_u in enumerate(names):     # unique pairs first, in the kernel's (u<=v) order ...
+            for iv in range(iu, len(names)):
+                key = name_u+'-'+names[iv]
+                Pk_2h_dict[key], Pk_1h_dict[key], Pk_hm_dict[key] = _split3(res[s], on_dev)
+                s += 1
+        ordered = ({}, {}, {})
+        for name_u in names:                    # ... then every ordered pair in dict insertion order, with the
+            for name_v in names:                # lower triangle aliasing the upper one (pyhalomodel.py:503-507)
+                key, rkey = name_u+'-'+name_v, name_v+'-'+name_u
+                for dst, src in zip(ordered, (Pk_2h_dict, Pk_1h_dict, Pk_hm_dict)):
+                    dst[key] = src[key] if key in src else src[rkey]
+        if verbose:
+            print('Halomodel calculation time [s]:', time()-t_start, '\n')
+        return ordered
+
+
+def _split3(block, on_dev):
+    if on_dev:
+        return block[0].clone(), block[1].clone(), block[2].clone()
+    return block[0].copy(), block[1].copy(), block[2].copy()
+
+
+class profile():
+    '''
+    Halo profile container with the data semantics of the reference (pyhalomodel.py:807-884).  The (k,M) grids
+    live in HBM; `Uk` and `Wk` are materialised lazily (as numpy arrays for host-constructed profiles).
+    '''
+
+    def __init__(self, k, M, Uk, Wk, amplitude=None, normalisation=1., variance=None,
+                 mass_tracer=False, discrete_tracer=False):
+        self._init_common(k, M, amplitude, normalisation, variance, mass_tracer, discrete_tracer,
+                          _wants_device(Uk, Wk))
+        self._mode = _lib.GRID_SEPARATE
+        self._grid = engine.to_dev(Uk).clone()
+        self._wk = engine.to_dev(Wk).clone()
+
+    def _init_common(self, k, M, amplitude, normalisation, variance, mass_tracer, discrete_tracer, on_dev):
+        self.k = np.array(engine.to_host(k) if isinstance(k, torch.Tensor) else k, dtype=float)
+        self.M = np.array(engine.to_host(M) if isinstance(M, torch.Tensor) else M, dtype=float)
+        self._on_dev = on_dev
+        self._amplitude = engine.to_dev(amplitude).clone() if amplitude is not None else None
+        self.normalisation = normalisation
+        self._variance = engine.to_dev(variance).clone() if variance is not None else None
+        self.mass_tracer, self.discrete_tracer = mass_tracer, discrete_tracer
+        self._wk = None
+
+    @classmethod
+    def Fourier(cls, k, M, Uk, amplitude=None, normalisation=1., variance=None, mass_tracer=False,
+                discrete_tracer=False):
+        '''
+        Fourier-space profile (pyhalomodel.py:853-884).  If amplitude is None, Uk is taken to be dimensionful:
+        amplitude := Uk[0,:], Wk := Uk, Uk := Uk/amplitude; otherwise Wk := (amplitude*Uk)/normalisation.
+        Only ONE grid is kept in HBM; the quadrature kernel derives the other on the fly.
+        '''
+        if tuple(Uk.shape) != (k.shape[0], M.shape[0]):
+            raise ValueError('k, M, array shapes do not match')
+        self = cls.__new__(cls)
+        grid = engine.to_dev(Uk).clone()
+        if amplitude is None:
+            self._init_common(k, M, grid[0, :], normalisation, variance, mass_tracer, discrete_tracer,
+                              _wants_device(Uk))
+            self._mode = _lib.GRID_WK
+        else:
+            self._init_common(k, M, amplitude, normalisation, variance, mass_tracer, discrete_tracer,
+                              _wants_device(Uk, amplitude))
+            self._mode = _lib.GRID_UK
+        self._grid = grid
+        return self
+
+    # lazily materialised views with the reference's field names
+    @property
+    def Uk(self):
+        if self._mode == _lib.GRID_WK:
+            return _give_back(self._grid/self._amplitude, self._on_dev)
+        return _give_back(self._grid, self._on_dev)
+
+    @property
+    def Wk(self):
+        if self._mode == _lib.GRID_UK:
+            return _give_back((self._amplitude*self._grid)/self.normalisation, self._on_dev)
+        if self._mode == _lib.GRID_WK:
+            return _give_back(self._grid, self._on_dev)
+        return _give_back(self._wk, self._on_dev)
+
+    @property
+    def amplitude(self):
+        return None if self._amplitude is None else _give_back(self._amplitude, self._on_dev)
+
+    @property
+    def variance(self):
+        return None if self._variance is None else _give_back(self._variance, self._on_dev)
+
+    def _tracer(self) -> engine.Tracer:
+        norm = self.normalisation
+        if isinstance(norm, torch.Tensor):
+            norm = float(norm.item())
+        return engine.Tracer(self._grid, self._amplitude, float(norm), variance=self._variance, wk=self._wk,
+                             mode=self._mode, mass_tracer=self.mass_tracer, discrete_tracer=self.discrete_tracer)
+
+    def __str__(self):
+        log_limit = 1e5
+        amp = engine.to_host(self._amplitude)
+        print('Mass tracer:', self.mass_tracer)
+        print('Discrete tracer:', self.discrete_tracer)
+        if self.normalisation != 1.:
+            print('Field normalisation:', self.normalisation)
+        print('Number of wavenumber bins:', len(self.k))
+        print('Number of mass bins:', len(self.M))
+        print('Wavenumber range [log10(h/Mpc)]: %1.3f %1.3f' % (np.log10(self.k[0]), np.log10(self.k[-1])))
+        print('Halo mass range [log10(Msun/h)]: %1.3f %1.3f' % (np.log10(self.M[0]), np.log10(self.M[-1])))
+        print('The following are at the low and high halo mass ends')
+        if amp[0] > log_limit:
+            print('Profile amplitude mean [log10]:', np.log10(amp[0]), np.log10(amp[-1]))
+        else:
+            print('Profile amplitude mean:', amp[0], amp[-1])
+        if self._variance is not None:
+            var = engine.to_host(self._variance)
+            if var[0] > log_limit:
+                print('Profile amplitude variance [log10]:', np.log10(var[0]), np.log10(var[-1]))
+            else:
+                print('Profile amplitude variance:', var[0], var[-1])
+        U, W = engine.to_host(engine.to_dev(self.Uk)), engine.to_host(engine.to_dev(self.Wk))
+        print('Dimensionless profiles at low k (should be ~1):', U[0, 0], U[0, -1])
+        print('Dimensionful profiles at low k (should be amplitudes):', W[0, 0], W[0, -1])
+        return ''
+
+
+### Halo profiles in Fourier space ###
+
+def window_function(k, rv, *args, profile=None):
+    '''
+    Fourier transforms of halo profiles: 'delta', 'isothermal', 'NFW' (pyhalomodel.py:1006-1026).
+    Scalar rv / c are accepted for 'isothermal' and 'NFW' (shape (nk, 1)), as np.outer does in the reference.
+    '''
+    on_dev = _wants_device(k, rv, *args)
+    if profile == 'delta':
+        Wk = torch.ones((len(k), len(rv)), dtype=torch.float64, device=engine.device())
+    elif profile == 'isothermal':
+        Wk = engine.window_isothermal(k, _vector(rv))
+    elif profile == 'NFW':
+        (c,) = args
+        rvv = _vector(rv)
+        cv = _vector(c)
+        if cv.shape[0] != rvv.shape[0]:
+            cv = cv.expand(rvv.shape[0]).contiguous() if cv.shape[0] == 1 else cv
+            rvv = rvv.expand(cv.shape[0]).contiguous() if rvv.shape[0] == 1 else rvv
+        Wk = engine.window_nfw(k, rvv, cv)
+    else:
+        raise ValueError('Halo profile not recognised')
+    return _give_back(Wk, on_dev)
+
+
+def _vector(x):
+    t = engine.to_dev(x)
+    return t.reshape(-1)
+
+
+def matter_profile(k, M, rv, c, Om_m: float) -> profile:
+    '''Pre-configured matter NFW profile (pyhalomodel.py:1065-1077); the grid never leaves the device.'''
+    rhom = cosmology.comoving_matter_density(Om_m)
+    Uk = engine.window_nfw(k, _vector(rv), _vector(c))
+    prof = profile.Fourier(engine.to_dev(k), engine.to_dev(M), Uk, amplitude=engine.to_dev(M), normalisation=rhom,
+                           mass_tracer=True)
+    prof._on_dev = _wants_device(k, M, rv, c)
+    return prof
+
+
+### Halo concentration ###
+
+_DUFFY = ((('M200', '200', '200b'), (10.14, -0.081, -1.01)),       # Duffy et al. (2008) table 1, full samples
+          (('vir', 'virial', 'Mvir'), (7.85, -0.081, -0.71)),
+          (('M200c', '200c'), (5.71, -0.084, -0.47)))
+
+
+def concentration(M, z: float, method='Duffy et al. (2008)', halo_definition='M200'):
+    '''Halo concentration c(M, z) (pyhalomodel.py:1084-1124)'''
+    if method != 'Duffy et al. (2008)':
+        raise ValueError('Halo concentration not recognised')
+    for names, (A, B, C) in _DUFFY:
+        if halo_definition in names:
+            return A*(M/2e12)**B*(1.+z)**C
+    raise ValueError('Halo definition not recognised')
+
+
+### Halo-occupation distribution (HOD) ###
+
+def _xp(M):
+    return torch if isinstance(M, torch.Tensor) else np
+
+
+def _step(x):
+    '''np.heaviside(x, 1.)'''
+    if isinstance(x, torch.Tensor):
+        return (x >= 0.).to(x.dtype)
+    return np.heaviside(x, 1.)
+
+
+def _erf(x):
+    if isinstance(x, torch.Tensor):
+        return torch.erf(x)
+    from scipy.special import erf
+    return erf(x)
+
+
+def HOD_mean(M, method='Zheng et al. (2005)', **kwargs) -> tuple:
+    '''Mean numbers of central and satellite galaxies (pyhalomodel.py:1131-1201); same methods and keywords.'''
+    xp = _xp(M)
+    if method == 'simple':
+        Mmin, Msat, alpha = kwargs.get('Mmin', 1e12), kwargs.get('Msat', 1e13), kwargs.get('alpha', 1.)
+        Nc = _step(M-Mmin)
+        return Nc, Nc*(M/Msat)**alpha
+    if method == 'Zehavi et al. (2004)':
+        Mmin, M1, alpha = kwargs.get('Mmin', 1e12), kwargs.get('M1', 1e13), kwargs.get('alpha', 1.)
+        return _step(M-Mmin), (M/M1)**alpha
+    if method == 'Zheng et al. (2005)':
+        Mmin, sigma, M0 = kwargs.get('Mmin', 1e12), kwargs.get('sigma', 0.15), kwargs.get('M0', 1e12)
+        M1, alpha = kwargs.get('M1', 1e13), kwargs.get('alpha', 1.)
+        Nc = _step(M-Mmin) if sigma == 0. else 0.5*(1.+_erf(xp.log10(M/Mmin)/sigma))
+        return Nc, (_step(M-M0)*(M-M0)/M1)**alpha
+    if method == 'Zhai et al. (2017)':
+        Mmin, sigma = kwargs.get('Mmin', 10**13.68), kwargs.get('sigma', 0.82)
+        Msat, alpha, Mcut = kwargs.get('Msat', 10**14.87), kwargs.get('alpha', 0.41), kwargs.get('Mcut', 10**12.32)
+        Nc = _step(M-Mmin) if sigma == 0. else 0.5*(1.+_erf(xp.log10(M/Mmin)/sigma))
+        return Nc, ((M/Msat)**alpha)*xp.exp(-Mcut/M)
+    raise ValueError('HOD method not recognised')
+
+
+def HOD_variance(p, lam, central_condition=False) -> tuple:
+    '''Bernoulli centrals, Poisson satellites (pyhalomodel.py:1204-1221)'''
+    vcc = p*(1.-p)
+    if central_condition:
+        return vcc, p*lam*(1.+lam*(1.-p)), lam*(1.-p)
+    return vcc, lam, 0.

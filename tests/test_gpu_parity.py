@@ -1,0 +1,384 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the reference-shaped Python API and hence the C ABI,
+against (i) the golden vectors generated from the live reference and (ii) the oracle on seeded inputs.
+Tolerance: rtol 1e-10 in fp64 on every spectrum (BASELINE.json north_star), with an absolute floor only where
+the reference is identically zero.  Ingredient kernels are held to tighter, stated tolerances."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_spectra_close, load_golden
+from oracle import halo_oracle as orc
+from pyhalomodel_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+SHORT = dict(zip(['PS74', 'ST99', 'SMT01', 'Tinker2010', 'Despali2016'], orc.FAMILIES))
+
+
+@pytest.fixture(scope='module')
+def halo():
+    assert torch.cuda.is_available()
+    import pyhalomodel_b200.pyhalomodel as h
+    from pyhalomodel_b200 import _lib
+    _lib.lib()      # fail loudly if the extension is missing
+    return h
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def test_massfn_bias_lowmass(halo):
+    from pyhalomodel_b200 import engine
+    g = load_golden('massfn.npz')
+    nu, nu0 = g['nu'], g['nu0']
+    for short, name in SHORT.items():
+        for i, (Dv, dc) in enumerate(g['DvDc']):
+            m = halo.model(0.5, 0.3, name=name, Dv=Dv, dc=dc)
+            np.testing.assert_allclose(m._mass_function_nu(nu), g['g_%s_%d' % (short, i)], rtol=2e-14)
+            np.testing.assert_allclose(m._linear_bias_nu(nu), g['b_%s_%d' % (short, i)], rtol=2e-14, atol=1e-15)
+            A = engine.low_mass_correction([m.descriptor()]*len(nu0), nu0).cpu().numpy()
+            np.testing.assert_allclose(A, g['A_%s_%d' % (short, i)], rtol=0, atol=3e-14)
+    halo.Tinker_z_dep = True
+    try:
+        m = halo.model(1.3, 0.3, Dv=200., dc=1.686)
+    finally:
+        halo.Tinker_z_dep = False
+    np.testing.assert_allclose(m._mass_function_nu(nu), g['g_Tinker2010_zdep'], rtol=2e-14)
+    np.testing.assert_allclose(m._linear_bias_nu(nu), g['b_Tinker2010_zdep'], rtol=2e-14)
+    halo.Tinker_PBS = True
+    try:
+        m = halo.model(0.5, 0.3, Dv=330., dc=1.686)
+        np.testing.assert_allclose(m._linear_bias_nu(nu), g['b_Tinker2010_pbs'], rtol=2e-14)
+        A = engine.low_mass_correction([m.descriptor()]*len(nu0), nu0).cpu().numpy()
+        np.testing.assert_allclose(A, g['A_Tinker2010_pbs'], rtol=0, atol=3e-14)
+    finally:
+        halo.Tinker_PBS = False
+
+
+def test_sici_and_windows(halo):
+    from pyhalomodel_b200 import engine
+    g = load_golden('windows.npz')
+    x = g['sici_x']
+    si, ci = (t.cpu().numpy() for t in engine.sici(x))
+    fin = np.isfinite(g['sici_ci'])
+    np.testing.assert_allclose(si, g["sici_si"], rtol=2e-15, atol=0)                    # Si: relative
+    np.testing.assert_allclose(ci[fin], g['sici_ci'][fin], rtol=2e-16, atol=2e-15)       # Ci: absolute (zero crossings)
+    si0, ci0 = (t.cpu().numpy() for t in engine.sici(np.array([0., -2.5, np.inf])))
+    assert si0[0] == 0. and ci0[0] == -np.inf and si0[2] == np.pi/2 and ci0[2] == 0.
+    ref_si, ref_ci = g['sici_si'], g['sici_ci']
+    k, rv, c = g['k'], g['rv'], g['c_Mvir']
+    np.testing.assert_allclose(halo.window_function(k, rv, c, profile='NFW'), g['U_nfw'], rtol=1e-12)
+    np.testing.assert_allclose(halo.window_function(k, rv, profile='isothermal'), g['U_iso'], rtol=1e-14)
+    assert np.array_equal(halo.window_function(k, rv, profile='delta'), np.ones((len(k), len(rv))))
+    # scalar rv / c as in notebooks/NFW-profile.ipynb (np.outer flattens scalars)
+    U1 = halo.window_function(k, rv[3], c[3], profile='NFW')
+    assert U1.shape == (len(k), 1)
+    np.testing.assert_allclose(U1[:, 0], g['U_nfw'][:, 3], rtol=1e-12)
+    with pytest.raises(ValueError):
+        halo.window_function(k, rv, profile='bogus')
+
+
+def test_sigmaR(halo):
+    from pyhalomodel_b200 import cosmology
+    g = load_golden('sigma.npz')
+    grid = g['Pk_grid']
+    sig = cosmology.sigmaR(g['R'], lambda k: grid)
+    np.testing.assert_allclose(sig[:-1], g['sigma'][:-1], rtol=1e-12)
+    # R = 1e-9: every k R lies in [1e-14, 1e-4], where the reference's own 3(sin x - x cos x)/x^3 loses up to
+    # ~1e-6 to cancellation just above its Taylor switch (cosmology.py:47); only libm-vs-CUDA sincos ulps differ
+    np.testing.assert_allclose(sig[-1], g['sigma'][-1], rtol=1e-7)
+    assert isinstance(cosmology.sigmaR(8., lambda k: grid), float)
+    with pytest.raises(NotImplementedError):
+        cosmology.sigmaR(g['R'], lambda k: grid, integration_type='quad')
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _profiles(halo, hmod, g, hod=None, pressure=False, split=False):
+    """tests/test_consistency.py:68-85 with this package's API."""
+    k, M, sig = g['k'], g['M'], g['sigmaM']
+    rv = hmod.virial_radius(M)
+    c = halo.concentration(M, hmod.z, halo_definition='Mvir')
+    profs = {'m': halo.matter_profile(k, M, rv, c, hmod.Om_m)}
+    if hod is not None:
+        Nc, Ns = halo.HOD_mean(M, method='Zheng et al. (2005)', **hod)
+        Vc, Vs, _ = halo.HOD_variance(Nc, Ns)
+        Uiso = halo.window_function(k, rv, profile='isothermal')
+        rho_g = hmod.average(M, sig, Nc+Ns)
+        if 'rho_g' in g:
+            np.testing.assert_allclose(rho_g, g['rho_g'], rtol=1e-13)
+        if split:
+            profs['c'] = halo.profile.Fourier(k, M, halo.window_function(k, rv, profile='delta'), amplitude=Nc,
+                                              normalisation=rho_g, variance=Vc, discrete_tracer=True)
+            profs['s'] = halo.profile.Fourier(k, M, Uiso, amplitude=Ns, normalisation=rho_g, variance=Vs,
+                                              discrete_tracer=True)
+        else:
+            profs['g'] = halo.profile.Fourier(k, M, Uiso, amplitude=Nc+Ns, normalisation=rho_g, variance=Vc+Vs,
+                                              discrete_tracer=True)
+    if pressure:
+        profs['p'] = halo.profile.Fourier(k, M, syn.pressure_profile(k, M, rv))
+    return profs
+
+
+def _check(out, g, prefix, names, rtol=RTOL):
+    for u in names:
+        for v in names:
+            want = g['%s_%s-%s' % (prefix, u, v)]
+            for t in range(3):
+                assert_spectra_close(out[t][u+'-'+v], want[t], rtol=rtol, what='%s %s-%s term %d' % (prefix, u, v, t),
+                                     zero_scale=np.max(np.abs(want)))
+
+
+def test_power_c1_golden(halo):
+    g = load_golden('power_c1.npz')
+    hmod = halo.model(float(g['z']), float(g['Om_m']), name=orc.ST99, Dv=g['dcDv'][1], dc=g['dcDv'][0])
+    out = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], _profiles(halo, hmod, g))
+    _check(out, g, 'P', ['m'])
+
+
+def test_power_families_golden(halo):
+    g = load_golden('power_families.npz')
+    for z in g['zs']:
+        dc, Dv = g['dcDv_z%g' % z]
+        gg = dict(k=g['k'], M=g['M'], sigmaM=g['sigmaM_z%g' % z])
+        for short, name in SHORT.items():
+            hmod = halo.model(z, float(g['Om_m']), name=name, Dv=Dv, dc=dc)
+            gg['rho_g'] = g['rho_g_%s_z%g' % (short, z)]
+            out = hmod.power_spectrum(g['k'], g['Pk_lin_z%g' % z], g['M'], gg['sigmaM'],
+                                      _profiles(halo, hmod, gg, hod=syn.zheng_defaults()))
+            _check(out, g, '%s_z%g' % (short, z), ['m', 'g'])
+
+
+VARIANTS = {
+    'default': {},
+    'noshot': dict(subtract_shotnoise=False),
+    'nocorr': dict(correct_discrete=False, subtract_shotnoise=False),
+    'nocorr_sub': dict(correct_discrete=False, subtract_shotnoise=True),
+    'ktrunc': dict(k_trunc=0.1),
+    'simple': dict(simple_twohalo=True),
+    'simple_ktrunc_noshot': dict(simple_twohalo=True, k_trunc=0.05, subtract_shotnoise=False),
+}
+
+
+def test_power_flags_golden_and_aliasing(halo):
+    g = load_golden('power_flags.npz')
+    dc, Dv = g['dcDv']
+    hmod = halo.model(float(g['z']), float(g['Om_m']), name=orc.TINKER10, Dv=Dv, dc=dc)
+    hod = dict(zip(('Mmin', 'sigma', 'M0', 'M1', 'alpha'), g['hod']))
+    profs = _profiles(halo, hmod, g, hod=hod, pressure=True, split=True)
+    for tag, kw in VARIANTS.items():
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            out = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs, **kw)
+        _check(out, g, tag, ['m', 'c', 's', 'p'])
+        assert out[2]['c-m'] is out[2]['m-c'] and out[1]['p-s'] is out[1]['s-p']       # pyhalomodel.py:503-507
+        assert list(out[0].keys()) == [u+'-'+v for u in 'mcsp' for v in 'mcsp']          # insertion order
+    # exact zero of the central-central one-halo term
+    out = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs)
+    assert np.all(out[1]['c-c'] == 0.)
+    with pytest.warns(RuntimeWarning):
+        hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs, correct_discrete=False)
+
+
+def test_power_c2_small_golden_and_average(halo):
+    g = load_golden('power_c2_small.npz')
+    dc, Dv = g['dcDv']
+    hmod = halo.model(float(g['z']), float(g['Om_m']), name=orc.TINKER10, Dv=Dv, dc=dc)
+    out = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'],
+                              _profiles(halo, hmod, g, hod=syn.zheng_defaults(), pressure=True))
+    _check(out, g, 'P', ['m', 'g', 'p'])
+    M, sig = g['M'], g['sigmaM']
+    np.testing.assert_allclose(hmod.average(M, sig, M), g['avg_M'], rtol=1e-13)
+    np.testing.assert_allclose(hmod.average(M, sig, np.ones_like(M)), g['avg_one'], rtol=1e-13)
+    np.testing.assert_allclose(hmod.linear_bias(M, sig), g['bias'], rtol=2e-14)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def _synthetic_case(nk, nM, z=0.3, Om_m=0.3, seed=0):
+    k, M = syn.k_grid(nk), syn.M_grid(nM)
+    Plin0 = syn.LinearSpectrum(Om_m, 0.7, 0.96, 0.8)
+    kg, dlnk = syn.sigma_k_grid()
+    Omz = syn.Om_m_of_z(z, Om_m)
+    dc, Dv = orc.dc_nakamura_suto(Omz), orc.Dv_bryan_norman(Omz)
+    sig = syn.sigmaR_numpy(orc.lagrangian_radius(M, Om_m), Plin0(kg, z), kg, dlnk)
+    return dict(k=k, M=M, sigmaM=sig, Pk_lin=Plin0(k, z), z=z, Om_m=Om_m, dc=dc, Dv=Dv)
+
+
+def _oracle_profiles(om, g, hods, pressure):
+    k, M, sig = g['k'], g['M'], g['sigmaM']
+    rv, c = orc.virial_radius(M, om.Om_m, om.Dv), orc.concentration(M, om.z, halo_definition='Mvir')
+    profs = {'m': orc.matter_profile(k, M, rv, c, om.Om_m)}
+    Uiso = orc.window_isothermal(k, rv)
+    for i, hod in enumerate(hods):
+        Nc, Ns = orc.hod_mean(M, **hod)
+        Vc, Vs, _ = orc.hod_variance(Nc, Ns)
+        profs['g%d' % i] = orc.Profile.Fourier(k, M, Uiso, amplitude=Nc+Ns, normalisation=orc.average(om, M, sig, Nc+Ns),
+                                               variance=Vc+Vs, discrete_tracer=True)
+    if pressure:
+        profs['p'] = orc.Profile.Fourier(k, M, syn.pressure_profile(k, M, rv))
+    return profs
+
+
+def _gpu_profiles(halo, hmod, g, hods, pressure):
+    k, M, sig = g['k'], g['M'], g['sigmaM']
+    rv, c = hmod.virial_radius(M), halo.concentration(M, hmod.z, halo_definition='Mvir')
+    profs = {'m': halo.matter_profile(k, M, rv, c, hmod.Om_m)}
+    Uiso = halo.window_function(k, rv, profile='isothermal')
+    for i, hod in enumerate(hods):
+        Nc, Ns = halo.HOD_mean(M, **hod)
+        Vc, Vs, _ = halo.HOD_variance(Nc, Ns)
+        profs['g%d' % i] = halo.profile.Fourier(k, M, Uiso, amplitude=Nc+Ns, normalisation=hmod.average(M, sig, Nc+Ns),
+                                                variance=Vc+Vs, discrete_tracer=True)
+    if pressure:
+        profs['p'] = halo.profile.Fourier(k, M, syn.pressure_profile(k, M, rv))
+    return profs
+
+
+@pytest.mark.parametrize('ntr,nk,nM', [(1, 37, 130), (2, 33, 257), (3, 50, 96), (4, 21, 64), (5, 10, 77), (6, 9, 40),
+                                       (7, 8, 34), (8, 7, 32)])
+def test_tracer_counts_and_ragged_shapes_vs_oracle(halo, ntr, nk, nM):
+    """P = 1..8 tracers, nk not a multiple of the row tile, odd nM (scalar-load kernel variant)."""
+    g = _synthetic_case(nk, nM, seed=ntr)
+    rng = np.random.default_rng(100+ntr)
+    pressure = ntr >= 3
+    hods = [syn.draw_hod(rng) for _ in range(ntr-1-int(pressure))]
+    for name in (orc.TINKER10, orc.SMT01):
+        om = orc.make_model(g['z'], g['Om_m'], name=name, Dv=g['Dv'], dc=g['dc'])
+        hmod = halo.model(g['z'], g['Om_m'], name=name, Dv=g['Dv'], dc=g['dc'])
+        want = orc.power_spectrum(om, g['k'], g['Pk_lin'], g['M'], g['sigmaM'], _oracle_profiles(om, g, hods, pressure))
+        got = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], _gpu_profiles(halo, hmod, g, hods, pressure))
+        assert list(got[0].keys()) == list(want[0].keys())
+        for t in range(3):
+            for key in want[t]:
+                assert_spectra_close(got[t][key], want[t][key], rtol=RTOL, what='%s %s term %d' % (name, key, t))
+
+
+def test_direct_profile_constructor_separate_grids(halo):
+    """profile(k, M, Uk, Wk, ...) with independent Uk and Wk grids (pyhalomodel.py:812-819)."""
+    g = _synthetic_case(24, 48)
+    rng = np.random.default_rng(7)
+    k, M = g['k'], g['M']
+    Uk = 1./(1.+np.outer(k, np.linspace(0.1, 2., len(M))))
+    Wk = Uk*rng.uniform(0.5, 1.5, size=Uk.shape)
+    amp, var = rng.uniform(0.5, 2., len(M)), rng.uniform(0., 1., len(M))
+    om = orc.make_model(g['z'], g['Om_m'], Dv=g['Dv'], dc=g['dc'])
+    hmod = halo.model(g['z'], g['Om_m'], Dv=g['Dv'], dc=g['dc'])
+    rv, c = orc.virial_radius(M, om.Om_m, om.Dv), orc.concentration(M, om.z)
+    oprofs = {'x': orc.Profile(k, M, Uk, Wk, amplitude=amp, normalisation=3.3, variance=var, discrete_tracer=True),
+              'm': orc.matter_profile(k, M, rv, c, om.Om_m)}
+    gprofs = {'x': halo.profile(k, M, Uk, Wk, amplitude=amp, normalisation=3.3, variance=var, discrete_tracer=True),
+              'm': halo.matter_profile(k, M, rv, c, hmod.Om_m)}
+    np.testing.assert_array_equal(gprofs['x'].Uk, Uk)
+    np.testing.assert_array_equal(gprofs['x'].Wk, Wk)
+    np.testing.assert_allclose(gprofs['m'].Wk, oprofs['m'].Wk, rtol=1e-12)
+    for kw in ({}, dict(subtract_shotnoise=False), dict(k_trunc=0.2)):
+        want = orc.power_spectrum(om, k, g['Pk_lin'], M, g['sigmaM'], oprofs, **kw)
+        got = hmod.power_spectrum(k, g['Pk_lin'], M, g['sigmaM'], gprofs, **kw)
+        for t in range(3):
+            for key in want[t]:
+                assert_spectra_close(got[t][key], want[t][key], rtol=RTOL, what='%s term %d' % (key, t))
+
+
+def test_full_size_c2_vs_oracle_and_properties(halo):
+    """BASELINE config 2 at full size (512 k x 2048 M, Tinker10, m+g+p): parity against the oracle, then the
+    size-independent properties: bitwise determinism, linearity in P_lin, and torch-in/torch-out equality."""
+    g = _synthetic_case(512, 2048, z=0.)
+    hods = [syn.zheng_defaults()]
+    om = orc.make_model(g['z'], g['Om_m'], Dv=g['Dv'], dc=g['dc'])
+    hmod = halo.model(g['z'], g['Om_m'], Dv=g['Dv'], dc=g['dc'])
+    gprofs = _gpu_profiles(halo, hmod, g, hods, True)
+    want = orc.power_spectrum(om, g['k'], g['Pk_lin'], g['M'], g['sigmaM'], _oracle_profiles(om, g, hods, True))
+    got = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], gprofs)
+    for t in range(3):
+        for key in want[t]:
+            assert_spectra_close(got[t][key], want[t][key], rtol=RTOL, what='C2 %s term %d' % (key, t))
+    again = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], gprofs)
+    twice = hmod.power_spectrum(g['k'], 2.*g['Pk_lin'], g['M'], g['sigmaM'], gprofs)
+    dev = hmod.power_spectrum(torch.as_tensor(g['k']).cuda(), torch.as_tensor(g['Pk_lin']).cuda(),
+                              torch.as_tensor(g['M']).cuda(), torch.as_tensor(g['sigmaM']).cuda(), gprofs)
+    for key in got[0]:
+        for t in range(3):
+            assert np.array_equal(got[t][key], again[t][key])                    # fixed reduction order
+            assert dev[t][key].is_cuda and np.array_equal(dev[t][key].cpu().numpy(), got[t][key])
+        assert np.array_equal(twice[0][key], 2.*got[0][key])                      # two-halo is linear in P_lin
+        assert np.array_equal(twice[1][key], got[1][key])                         # one-halo does not see P_lin
+
+
+def test_batched_plan_equals_single_models(halo):
+    """The batch entry (G samples x F models per sample sharing grids) reproduces per-model calls bit for bit."""
+    from pyhalomodel_b200 import engine, _lib
+    nk, nM, G = 40, 128, 3
+    rng = np.random.default_rng(3)
+    cases = [_synthetic_case(nk, nM, z=z, Om_m=Om) for z, Om in [(0., 0.3), (0.7, 0.27), (1.5, 0.33)]]
+    k, M = cases[0]['k'], cases[0]['M']
+    names = [orc.PS74, orc.ST99, orc.TINKER10]
+    models, grids_m, grids_g, amp_g, var_g, norm_g, norm_m, singles = [], [], [], [], [], [], [], []
+    for cs in cases:
+        hod = syn.draw_hod(rng)
+        for name in names:
+            hmod = halo.model(cs['z'], cs['Om_m'], name=name, Dv=cs['Dv'], dc=cs['dc'])
+            profs = _gpu_profiles(halo, hmod, cs, [hod], False)
+            singles.append(hmod.power_spectrum(k, cs['Pk_lin'], M, cs['sigmaM'], profs))
+            models.append(hmod.descriptor())
+            norm_g.append(profs['g0'].normalisation)
+            norm_m.append(profs['m'].normalisation)
+        grids_m.append(profs['m']._grid)
+        grids_g.append(profs['g0']._grid)
+        amp_g.append(profs['g0']._amplitude)
+        var_g.append(profs['g0']._variance)
+    Mdev = engine.to_dev(M)
+    tr = [engine.Tracer(torch.stack(grids_m), Mdev[None, :].expand(G, -1).contiguous(), np.array(norm_m),
+                        mode=_lib.GRID_UK, mass_tracer=True),
+          engine.Tracer(torch.stack(grids_g), torch.stack(amp_g), np.array(norm_g), variance=torch.stack(var_g),
+                        mode=_lib.GRID_UK, discrete_tracer=True)]
+    plan = engine.PowerSpectrumPlan(k, np.stack([c['Pk_lin'] for c in cases]), M, np.stack([c['sigmaM'] for c in cases]),
+                                    tr, models, models_per_sample=len(names))
+    out, A = plan.run()
+    out = out.cpu().numpy()
+    for b, single in enumerate(singles):
+        for s, key in enumerate(['m-m', 'm-g0', 'g0-g0']):
+            for t in range(3):
+                assert np.array_equal(out[b, s, t], single[t][key]), (b, key, t)
+
+
+def test_error_behaviour(halo):
+    g = load_golden('power_c1.npz')
+    hmod = halo.model(0., 0.3, name=orc.ST99, Dv=330.)
+    profs = _profiles(halo, hmod, g)
+    k, Pk, M, sig = g['k'], g['Pk_lin'], g['M'], g['sigmaM']
+    with pytest.raises(ValueError):
+        hmod.power_spectrum(k, Pk, M[::-1], sig, profs)                     # pyhalomodel.py:387-389
+    with pytest.raises(TypeError):
+        hmod.power_spectrum(k, Pk, M, sig, list(profs.values()))            # :390-391
+    with pytest.raises(ValueError):
+        hmod.power_spectrum(k*2., Pk, M, sig, profs)                        # :393-395
+    with pytest.raises(ValueError):
+        hmod.power_spectrum(k, Pk, M*2., sig, profs)                        # :396-398
+    with pytest.raises(ValueError):
+        hmod.power_spectrum(k, Pk, M, sig, profs, simple_twohalo=True, beta=np.zeros((2, 2, 2)))   # :384-386
+    with pytest.raises(ValueError):
+        halo.profile.Fourier(k, M, np.ones((3, 3)))                         # :872-873
+    with pytest.raises(ValueError):
+        hmod.average(M[::-1], sig, M)                                       # :353-355
+    k2 = k.copy()
+    k2[1:] *= 1.5                                                           # partially different grid passes
+    hmod.power_spectrum(k2, Pk, M, sig, profs)
+
+
+def test_multiplicity_and_mass_function(halo):
+    g = load_golden('power_c2_small.npz')
+    dc, Dv = g['dcDv']
+    hmod = halo.model(float(g['z']), float(g['Om_m']), Dv=Dv, dc=dc)
+    M, sig = g['M'], g['sigmaM']
+    F = hmod.multiplicity_function(M, sig)
+    # independent restatement of pyhalomodel.py:298-315 / utility.py:15-35 with numpy's polynomial derivative
+    R = orc.lagrangian_radius(M, hmod.Om_m)
+    x, f = np.log(R), np.log(sig)
+    d = np.empty_like(x)
+    for i in range(len(x)):
+        j = min(max(i, 1), len(x)-2)
+        d[i] = np.polyval(np.polyder(np.polyfit(x[j-1:j+2], f[j-1:j+2], 2)), x[i])
+    om = orc.make_model(hmod.z, hmod.Om_m, Dv=Dv, dc=dc)
+    nu = dc/sig
+    want = orc.mass_function_nu(om, nu)*(-(nu/6.)*2.*d)
+    np.testing.assert_allclose(F, want, rtol=1e-8)
+    np.testing.assert_allclose(hmod.mass_function(M, sig), want*hmod.rhom/M**2, rtol=1e-8)
