@@ -1,19 +1,24 @@
-// hm_quad.cu -- the hot path of model.power_spectrum (pyhalomodel.py:361-513, beta=None) as two kernels:
+// hm_quad.cu -- the hot path of model.power_spectrum (pyhalomodel.py:361-513, beta=None) as three kernels:
 //
-//   hm_weights_kernel   one CTA per model: nu = dc/sigma, g(nu), b(nu), trapezoid-in-nu weights, the low-mass
-//                       correction A, and from those the P+S per-mass weight vectors that turn every integral of
-//                       the reference into a plain weighted row sum over M:
-//                         I_u(k)   = rhom * sum_m  e_u[m]  * G_u[k,m]                      (:535-544, incl. A W(k,M0)/M0)
-//                         P1h_uu   = rhom * sum_m  d_u[m]  * G_u[k,m]^2                    (:465-477, :526-533)
-//                         P1h_uv   = rhom * sum_m  q_uv[m] * G_u[k,m] * G_v[k,m]           (:479)
-//                       where G_u is the single grid a Fourier profile was built from (Uk, or Wk when
-//                       amplitude=None; :874-881), so each (k,M) grid is read from HBM exactly once.
-//   hm_quad_kernel      streams the grids: a CTA takes a tile of R wavenumber rows, its threads split the mass
-//                       axis with 16-byte coalesced loads, keep R*(P+S) partial sums in registers, reduce them
-//                       with a transposing warp-shuffle network plus one shared-memory pass across warps, and the
-//                       epilogue forms P_2h = I_u I_v P_lin, the discrete/shot-noise/k_trunc fix-ups and P_hm.
+//   hm_weights_kernel      (mass-chunk, model) CTAs: nu = dc/sigma, g(nu), b(nu), trapezoid-in-nu weights, the
+//                          low-mass correction A, and from those the P+S per-mass weight vectors that turn every
+//                          integral of the reference into a plain weighted row sum over M:
+//                            I_u(k)  = rhom * sum_m  e_u[m]  * G_u[k,m]                  (:535-544, incl. A W(k,M0)/M0)
+//                            P1h_uu  = rhom * sum_m  d_u[m]  * G_u[k,m]^2                (:465-477, :526-533)
+//                            P1h_uv  = rhom * sum_m  q_uv[m] * G_u[k,m] * G_v[k,m]       (:479)
+//                          where G_u is the single grid a Fourier profile was built from (Uk, or Wk when
+//                          amplitude=None; :874-881), so each (k,M) grid is read from HBM exactly once.
+//   hm_quad_stream_kernel  the HBM-bound kernel.  Persistent CTAs (one per SM); a producer warp feeds a shared-memory
+//                          ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of R-row x 512-mass
+//                          tiles of every tracer grid; 8 consumer warps keep the weights of their two mass columns
+//                          in registers, accumulate R*(P+S) partial sums, reduce them with a transposing
+//                          warp-shuffle network and one shared-memory pass, and write per-mass-slice row sums.
+//   hm_quad_kernel         fallback of the same arithmetic with plain (scalar or 16-byte) loads for odd nM,
+//                          unaligned grids or profiles with separate Uk/Wk grids.
+//   hm_epilogue_kernel     sums the mass slices in fixed order and forms P_2h = I_u I_v P_lin, the
+//                          discrete/shot-noise/k_trunc fix-ups and P_hm (:456-501).
 //
-// HBM-bound: algorithmic bytes per model = 8*(P*nk*nM + (P+S)*nM + nk + 3*S*nk).
+// Algorithmic bytes per launch of the streaming kernel: 8*(G*P*nk*nM + B*(P+S)*nM + B*nslices*(P+S)*nk).
 #include "hm_common.cuh"
 #include "hm_tables.h"
 
@@ -53,14 +58,32 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Workspace layout (doubles): weights [B][NW][nMp] then scalars [B][HM_NSCAL]
+// Workspace layout (doubles):
+//   weights [B][NW][nMp]            per-mass weight vectors
+//   scal    [B][HM_NSCAL]           A, rhom
+//   cpart   [B][nchunks][2*HM_MAXP] per-mass-chunk partial sums of the shot-noise and simple-two-halo integrals
+//   partial [B][nslices][NW][nk]    per-mass-slice row sums written by the quadrature kernel
 // ---------------------------------------------------------------------------------------------------------------
-#define HM_NSCAL (2 + 2 * HM_MAXP)   // A, rhom, SN_p[8], Isimple_p[8]
+#define HM_NSCAL 4
+#define HM_WCHUNK 256        // masses per CTA of the weights kernel
+#define HM_MC 512            // masses per slice of the streaming kernel (256 consumer threads x double2)
+#define HM_CONSUMER_WARPS 8
+#define HM_STREAM_THREADS (32 * (HM_CONSUMER_WARPS + 1))
 
 struct hm_layout {
-  int P, S, NW, nMp;
-  size_t weights_doubles, scal_offset, total_bytes;
+  int P, S, NW, nMp, nchunks, nslices;
+  bool stream;
+  size_t B, scal_offset, cpart_offset, partial_offset, total_bytes;
 };
+
+static bool hm_can_stream(const hm_problem* pr) {
+  if (pr->nM % 2) return false;
+  for (int p = 0; p < pr->n_tracers; ++p) {
+    if (pr->tracers[p].grid_mode == HM_GRID_SEPARATE) return false;
+    if ((uintptr_t)pr->tracers[p].grid_dev & 15) return false;
+  }
+  return true;
+}
 
 static hm_layout hm_make_layout(const hm_problem* pr) {
   hm_layout L;
@@ -68,16 +91,21 @@ static hm_layout hm_make_layout(const hm_problem* pr) {
   L.S = L.P * (L.P + 1) / 2;
   L.NW = L.P + L.S;
   L.nMp = (pr->nM + 1) & ~1;
-  const size_t B = (size_t)pr->n_samples * (size_t)pr->models_per_sample;
-  L.weights_doubles = B * (size_t)L.NW * (size_t)L.nMp;
-  L.scal_offset = (L.weights_doubles + 31) & ~(size_t)31;
-  L.total_bytes = (L.scal_offset + B * HM_NSCAL) * sizeof(double);
+  L.nchunks = (L.nMp + HM_WCHUNK - 1) / HM_WCHUNK;
+  L.stream = hm_can_stream(pr);
+  L.nslices = L.stream ? (pr->nM + HM_MC - 1) / HM_MC : 1;
+  L.B = (size_t)pr->n_samples * (size_t)pr->models_per_sample;
+  auto align = [](size_t x) { return (x + 31) & ~(size_t)31; };
+  L.scal_offset = align(L.B * (size_t)L.NW * (size_t)L.nMp);
+  L.cpart_offset = align(L.scal_offset + L.B * HM_NSCAL);
+  L.partial_offset = align(L.cpart_offset + L.B * (size_t)L.nchunks * 2 * HM_MAXP);
+  L.total_bytes = (L.partial_offset + L.B * (size_t)L.nslices * L.NW * (size_t)pr->nk) * sizeof(double);
   return L;
 }
 
 struct hm_weights_args {
-  int nM, nMp, P, NW, F, B;
-  int simple_twohalo, correct_discrete;
+  int nM, nMp, P, NW, F, nchunks;
+  int correct_discrete;
   const double* M;
   const double* sigma;             // [G][nM]
   const hm_model_desc* models;     // [B] or NULL
@@ -89,18 +117,19 @@ struct hm_weights_args {
   int mode[HM_MAXP], mass[HM_MAXP], discrete[HM_MAXP];
   double* weights;
   double* scal;
+  double* cpart;
   double* lowmass;                   // optional [B]
 };
 
-__global__ void __launch_bounds__(256) hm_weights_kernel(const hm_weights_args a) {
+__global__ void __launch_bounds__(HM_WCHUNK) hm_weights_kernel(const hm_weights_args a) {
   __shared__ double scratch[32];
-  const int b = blockIdx.x;
+  const int b = blockIdx.y, chunk = blockIdx.x;
   const int s = b / a.F;
   const hm_model_desc d = a.models ? a.models[b] : a.single;
   const double* sig = a.sigma + (size_t)s * a.nM;
   const double M0 = a.M[0];
 
-  // A = 1 - int g b dnu from nu[0] (pyhalomodel.py:413-414)
+  // A = 1 - int g b dnu from nu[0] (pyhalomodel.py:413-414); every chunk CTA recomputes the same value
   const double nu_first = d.dc / sig[0];
   const double A = 1. - hm_block_sum(hm_lowmass_node(d, nu_first, threadIdx.x), scratch);
   const double Aterm = A / M0;   // multiplies W(k, M[0]) for mass tracers (:541-542)
@@ -110,11 +139,10 @@ __global__ void __launch_bounds__(256) hm_weights_kernel(const hm_weights_args a
   for (int p = 0; p < HM_MAXP; ++p) sn[p] = simp[p] = 0.;
 
   double* wout = a.weights + (size_t)b * a.NW * a.nMp;
-  for (int m = threadIdx.x; m < a.nMp; m += blockDim.x) {
-    if (m >= a.nM) {   // padding column
-      for (int i = 0; i < a.NW; ++i) wout[(size_t)i * a.nMp + m] = 0.;
-      continue;
-    }
+  const int m = chunk * HM_WCHUNK + threadIdx.x;
+  if (m < a.nMp && m >= a.nM) {   // padding column
+    for (int i = 0; i < a.NW; ++i) wout[(size_t)i * a.nMp + m] = 0.;
+  } else if (m < a.nM) {
     const double nu = d.dc / sig[m];
     const double nu_hi = (m + 1 < a.nM) ? d.dc / sig[m + 1] : nu;
     const double nu_lo = (m > 0) ? d.dc / sig[m - 1] : nu;
@@ -123,12 +151,13 @@ __global__ void __launch_bounds__(256) hm_weights_kernel(const hm_weights_args a
     const double bg = hm_b_nu(d, nu) * g;
     const double Mm = a.M[m];
     const double w1 = tw * (g / Mm);           // one-halo weight  (:530)
-    const double w2 = tw * (bg / Mm) + ((m == 0) ? Aterm : 0.);   // two-halo weight; low-mass term only if mass tracer
-    const double w2_plain = tw * (bg / Mm);
+    const double w2_plain = tw * (bg / Mm);    // two-halo weight  (:539)
+    const double w2_mass = w2_plain + ((m == 0) ? Aterm : 0.);   // + low-mass term for mass tracers
 
     double cW[HM_MAXP];
 #pragma unroll
     for (int p = 0; p < HM_MAXP; ++p) {
+      cW[p] = 0.;
       if (p < a.P) {
         const double amp = a.amplitude[p][(size_t)s * a.amp_stride[p] + m];
         const double norm = a.norm[p][b];
@@ -140,11 +169,11 @@ __global__ void __launch_bounds__(256) hm_weights_kernel(const hm_weights_args a
         if (a.mode[p] == HM_GRID_UK) { cW[p] = an; uS = 1. / norm; }
         else if (a.mode[p] == HM_GRID_WK) { cW[p] = 1.; uS = 1. / (amp * norm); }
         else { cW[p] = 1.; uS = 1. / norm; }
-        const double w2p = a.mass[p] ? w2 : w2_plain;
-        wout[(size_t)p * a.nMp + m] = w2p * cW[p];                       // e_p
-        wout[(size_t)(a.P + p) * a.nMp + m] = __dmul_rn(__dmul_rn(w1, fac), uS * uS);   // d_p
-        sn[p] += w1 * (amp / (norm * norm));                             // shot noise integrand (:425)
-        simp[p] += w2p * an;                                             // simple two-halo (:442-446)
+        const double w2p = a.mass[p] ? w2_mass : w2_plain;
+        wout[(size_t)p * a.nMp + m] = w2p * cW[p];                                       // e_p
+        wout[(size_t)(a.P + p) * a.nMp + m] = __dmul_rn(__dmul_rn(w1, fac), uS * uS);     // d_p
+        sn[p] = w1 * (amp / (norm * norm));                                              // shot noise integrand (:425)
+        simp[p] = w2p * an;                                                              // simple two-halo (:442-446)
       }
     }
     int idx = 2 * a.P;
@@ -152,16 +181,17 @@ __global__ void __launch_bounds__(256) hm_weights_kernel(const hm_weights_args a
       for (int v = u + 1; v < a.P; ++v) wout[(size_t)(idx++) * a.nMp + m] = w1 * cW[u] * cW[v];   // q_uv
   }
 
-  double* sc = a.scal + (size_t)b * HM_NSCAL;
+  double* cp = a.cpart + ((size_t)b * a.nchunks + chunk) * 2 * HM_MAXP;
   for (int p = 0; p < a.P; ++p) {
     const double t1 = hm_block_sum(sn[p], scratch);
     const double t2 = hm_block_sum(simp[p], scratch);
     if (threadIdx.x == 0) {
-      sc[2 + p] = a.discrete[p] ? t1 * d.rhom : 0.;
-      sc[2 + HM_MAXP + p] = t2 * d.rhom;
+      cp[p] = a.discrete[p] ? t1 : 0.;
+      cp[HM_MAXP + p] = t2;
     }
   }
-  if (threadIdx.x == 0) {
+  if (chunk == 0 && threadIdx.x == 0) {
+    double* sc = a.scal + (size_t)b * HM_NSCAL;
     sc[0] = A;
     sc[1] = d.rhom;
     if (a.lowmass) a.lowmass[b] = A;
@@ -169,24 +199,18 @@ __global__ void __launch_bounds__(256) hm_weights_kernel(const hm_weights_args a
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The streaming quadrature kernel
+// Shared pieces of the two quadrature kernels
 // ---------------------------------------------------------------------------------------------------------------
 struct hm_quad_args {
-  int nk, nM, nMp, F, B, ntiles;
+  int nk, nM, nMp, F, B, ntiles, nslices;
   long long nitems;
-  int simple_twohalo, subtract_shotnoise, correct_discrete;
-  double k_trunc;
-  const double* k;
-  const double* Pk_lin;              // [G][nk]
   const double* gridW[HM_MAXP];      // two-halo / cross source
   const double* gridU[HM_MAXP];      // auto one-halo source (== gridW unless HM_GRID_SEPARATE)
-  int discrete[HM_MAXP];
   const double* weights;
-  const double* scal;
-  double* out;                       // [B][S][3][nk]
+  double* partial;                   // [B][nslices][NW][nk]
 };
 
-// v[0..32) per lane  ->  lane l holds sum over the warp of v[l]  (31 shuffles instead of 160).
+// v[0..32) per lane  ->  lane l holds the warp-wide sum of v[l]  (31 shuffles instead of 160).
 __device__ __forceinline__ double hm_warp_transpose_sum32(double (&v)[32], int lane) {
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
@@ -201,6 +225,33 @@ __device__ __forceinline__ double hm_warp_transpose_sum32(double (&v)[32], int l
   return v[0];
 }
 
+// acc[r*NW + i] += w_i * (grid values the weight vector i multiplies), for one mass column.
+template <int P, int R, bool SEP>
+__device__ __forceinline__ void hm_accumulate(double* __restrict__ acc, const double* __restrict__ wv,
+                                              const double (&x)[R][P], const double (&xu)[SEP ? R : 1][SEP ? P : 1]) {
+  constexpr int NW = P + P * (P + 1) / 2;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      acc[r * NW + p] = fma(wv[p], x[r][p], acc[r * NW + p]);                                 // two-halo sums
+      const double xa = SEP ? xu[SEP ? r : 0][SEP ? p : 0] : x[r][p];
+      acc[r * NW + P + p] = fma(wv[P + p] * xa, xa, acc[r * NW + P + p]);                     // auto one-halo
+    }
+    int idx = 2 * P;
+#pragma unroll
+    for (int u = 0; u < P; ++u)
+#pragma unroll
+      for (int v = u + 1; v < P; ++v) {
+        acc[r * NW + idx] = fma(wv[idx] * x[r][u], x[r][v], acc[r * NW + idx]);               // cross one-halo
+        ++idx;
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fallback quadrature kernel: plain loads, one CTA per (model, R-row tile), whole mass axis (nslices == 1)
+// ---------------------------------------------------------------------------------------------------------------
 template <int P, int R, int VEC, bool SEP>
 __global__ void __launch_bounds__(256) hm_quad_kernel(const hm_quad_args a) {
   constexpr int S = P * (P + 1) / 2;
@@ -208,13 +259,11 @@ __global__ void __launch_bounds__(256) hm_quad_kernel(const hm_quad_args a) {
   constexpr int NV = R * NW;
   constexpr int NG = (NV + 31) / 32;   // groups of 32 values for the transposing reduction
   __shared__ double red[8][NG * 32];
-  __shared__ double fin[NG * 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int ncol = (VEC == 2) ? (a.nM >> 1) : a.nM;
   const size_t rowstride = (size_t)a.nM;
 
-  // contiguous chunk of (model, row-tile) items per CTA keeps the weight vectors of one model hot in L1
   const long long per = (a.nitems + gridDim.x - 1) / gridDim.x;
   long long item = (long long)blockIdx.x * per;
   const long long item_end = (item + per < a.nitems) ? item + per : a.nitems;
@@ -239,60 +288,38 @@ __global__ void __launch_bounds__(256) hm_quad_kernel(const hm_quad_args a) {
 
     for (int c = tid; c < ncol; c += blockDim.x) {
       const int m = c * VEC;
-      double x[R][P][VEC], xu[SEP ? R : 1][SEP ? P : 1][VEC];
+      double x[VEC][R][P], xu[VEC][SEP ? R : 1][SEP ? P : 1];
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int p = 0; p < P; ++p) {
           if (VEC == 2) {
             const double2 t = hm_ldg_stream2(a.gridW[p] + rowoff[r] + m);
-            x[r][p][0] = t.x; x[r][p][VEC - 1] = t.y;
+            x[0][r][p] = t.x; x[VEC - 1][r][p] = t.y;
             if (SEP) {
               const double2 tu = hm_ldg_stream2(a.gridU[p] + rowoff[r] + m);
-              xu[SEP ? r : 0][SEP ? p : 0][0] = tu.x; xu[SEP ? r : 0][SEP ? p : 0][VEC - 1] = tu.y;
+              xu[0][SEP ? r : 0][SEP ? p : 0] = tu.x; xu[VEC - 1][SEP ? r : 0][SEP ? p : 0] = tu.y;
             }
           } else {
-            x[r][p][0] = hm_ldg_stream1(a.gridW[p] + rowoff[r] + m);
-            if (SEP) xu[SEP ? r : 0][SEP ? p : 0][0] = hm_ldg_stream1(a.gridU[p] + rowoff[r] + m);
+            x[0][r][p] = hm_ldg_stream1(a.gridW[p] + rowoff[r] + m);
+            if (SEP) xu[0][SEP ? r : 0][SEP ? p : 0] = hm_ldg_stream1(a.gridU[p] + rowoff[r] + m);
           }
         }
+      double wv[VEC][NW];
 #pragma unroll
       for (int i = 0; i < NW; ++i) {
-        double wv[VEC];
         if (VEC == 2) {
           const double2 t = *reinterpret_cast<const double2*>(w + (size_t)i * a.nMp + m);
-          wv[0] = t.x; wv[VEC - 1] = t.y;
+          wv[0][i] = t.x; wv[VEC - 1][i] = t.y;
         } else {
-          wv[0] = w[(size_t)i * a.nMp + m];
+          wv[0][i] = w[(size_t)i * a.nMp + m];
         }
-        // which grids does weight vector i multiply?
-        int u = 0, v = 0;
-        if (i < P) { u = i; }
-        else if (i < 2 * P) { u = v = i - P; }
-        else {
-          int idx = 2 * P;
-#pragma unroll
-          for (int uu = 0; uu < P; ++uu)
-#pragma unroll
-            for (int vv = uu + 1; vv < P; ++vv) {
-              if (idx == i) { u = uu; v = vv; }
-              ++idx;
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) {
-            if (i < P) acc[r * NW + i] += wv[e] * x[r][u][e];
-            else if (i < 2 * P) {
-              const double xa = SEP ? xu[SEP ? r : 0][SEP ? u : 0][e] : x[r][u][e];
-              acc[r * NW + i] += (wv[e] * xa) * xa;
-            } else acc[r * NW + i] += (wv[e] * x[r][u][e]) * x[r][v][e];
-          }
       }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) hm_accumulate<P, R, SEP>(acc, wv[e], x[e], xu[e]);
     }
 
-    // ---- reduce over the mass axis: lanes (transposing shuffle network), then warps (shared memory) ----
+    // reduce over the mass axis: lanes (transposing shuffle network), then warps (shared memory)
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       double v[32];
@@ -301,56 +328,251 @@ __global__ void __launch_bounds__(256) hm_quad_kernel(const hm_quad_args a) {
       red[warp][g * 32 + lane] = hm_warp_transpose_sum32(v, lane);
     }
     __syncthreads();
-    if (tid < NG * 32) {
+    if (tid < NV) {
       double t = 0.;
       for (int wi = 0; wi < nwarps; ++wi) t += red[wi][tid];
-      fin[tid] = t;
+      const int r = tid / NW, i = tid - r * NW;
+      if (row0 + r < a.nk) a.partial[((size_t)b * NW + i) * a.nk + row0 + r] = t;
     }
     __syncthreads();
+  }
+}
 
-    // ---- epilogue: one thread per (row, pair)  (pyhalomodel.py:456-501) ----
-    if (tid < R * S) {
-      const int r = tid / S, s = tid - r * S;
-      const int row = row0 + r;
-      if (row < a.nk) {
-        int u = 0, v = 0, cnt = 0;
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming quadrature kernel: TMA bulk copies -> shared-memory ring -> register accumulation
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t hm_smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void hm_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void hm_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void hm_mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hm_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  }
+}
+// 1-D TMA: global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void hm_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void hm_consumer_barrier() {   // named barrier 1: the 256 consumer threads only
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * HM_CONSUMER_WARPS) : "memory");
+}
+
+template <int P, int R>
+struct hm_stream_cfg {
+  static constexpr int S = P * (P + 1) / 2;
+  static constexpr int NW = P + S;
+  static constexpr int NV = R * NW;
+  static constexpr int NG = (NV + 31) / 32;
+  static constexpr int STAGE_DOUBLES = R * P * HM_MC;
+  static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
+  static constexpr int RED_DOUBLES = 2 * HM_CONSUMER_WARPS * NG * 32;
+  static constexpr int BUDGET = 226 * 1024 - RED_DOUBLES * 8 - 256;
+  static constexpr int NS = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = NS * STAGE_BYTES + RED_DOUBLES * 8 + 256;
+};
+
+template <int P, int R>
+__global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(const hm_quad_args a) {
+  using C = hm_stream_cfg<P, R>;
+  constexpr int NW = C::NW, NV = C::NV, NG = C::NG, NS = C::NS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* ring = reinterpret_cast<double*>(smem_raw);
+  double* red = ring + (size_t)NS * C::STAGE_DOUBLES;                    // [2][warps][NG*32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + C::RED_DOUBLES);    // full[NS], empty[NS]
+  const uint32_t bar_full = hm_smem_addr(bars), bar_empty = hm_smem_addr(bars + NS);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      hm_mbar_init(bar_full + 8 * s, 1);
+      hm_mbar_init(bar_empty + 8 * s, HM_CONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // contiguous range of (model, mass slice, row tile) items for this CTA
+  const long long per = (a.nitems + gridDim.x - 1) / gridDim.x;
+  const long long it0 = (long long)blockIdx.x * per;
+  const long long it1 = (it0 + per < a.nitems) ? it0 + per : a.nitems;
+  const long long per_model = (long long)a.nslices * a.ntiles;
+
+  if (warp == HM_CONSUMER_WARPS) {
+    // ------------------------------ producer: one lane drives the TMA engine ------------------------------
+    if (lane == 0) {
+      long long n = 0;
+      for (long long item = it0; item < it1; ++item, ++n) {
+        const int b = (int)(item / per_model);
+        const int rem = (int)(item - (long long)b * per_model);
+        const int slice = rem / a.ntiles, tile = rem - slice * a.ntiles;
+        const int smp = b / a.F, m0 = slice * HM_MC, row0 = tile * R;
+        const int cols = (a.nM - m0 < HM_MC) ? a.nM - m0 : HM_MC;
+        const uint32_t bytes = (uint32_t)cols * 8u;
+        const int s = (int)(n % NS);
+        const uint32_t parity = (uint32_t)((n / NS) & 1);
+        hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);        // slot drained by all consumer warps
+        hm_mbar_arrive_expect_tx(bar_full + 8 * s, bytes * (uint32_t)(R * P));
+        const uint32_t dst0 = hm_smem_addr(ring + (size_t)s * C::STAGE_DOUBLES);
 #pragma unroll
-        for (int uu = 0; uu < P; ++uu)
+        for (int r = 0; r < R; ++r) {
+          const int row = (row0 + r < a.nk) ? row0 + r : a.nk - 1;   // clamp: duplicates are never written
+          const size_t off = ((size_t)smp * a.nk + row) * (size_t)a.nM + m0;
 #pragma unroll
-          for (int vv = uu; vv < P; ++vv) {
-            if (cnt == s) { u = uu; v = vv; }
-            ++cnt;
-          }
-        const double* sc = a.scal + (size_t)b * HM_NSCAL;
-        const double rhom = sc[1];
-        const double* f = fin + r * NW;
-        const double Iu = a.simple_twohalo ? sc[2 + HM_MAXP + u] : f[u] * rhom;
-        const double Iv = a.simple_twohalo ? sc[2 + HM_MAXP + v] : f[v] * rhom;
-        const double p2h = __dmul_rn(__dadd_rn(__dmul_rn(Iu, Iv), 0.), a.Pk_lin[(size_t)smp * a.nk + row]);   // :524
-        int i1 = P + u;
-        if (u != v) {
-          i1 = 2 * P;
-          for (int uu = 0; uu < u; ++uu) i1 += P - 1 - uu;
-          i1 += v - u - 1;
+          for (int p = 0; p < P; ++p)
+            hm_bulk_g2s(dst0 + (uint32_t)((r * P + p) * HM_MC * 8), a.gridW[p] + off, bytes, bar_full + 8 * s);
         }
-        double p1h = f[i1] * rhom;                                                                           // :532
-        if (u == v && a.discrete[u]) {                                                                       // :484-491
-          if (a.correct_discrete && !a.subtract_shotnoise) p1h += sc[2 + u];
-          else if (!a.correct_discrete && a.subtract_shotnoise) p1h -= sc[2 + u];
-        }
-        if (a.k_trunc > 0.) {                                                                                // :494-495
-          const double q = a.k[row] / a.k_trunc;
-          p1h *= 1. - exp(-(q * q));
-        }
-        double* o = a.out + ((size_t)b * S + s) * 3 * a.nk + row;
-        o[0] = p2h;
-        o[a.nk] = p1h;
-        o[2 * (size_t)a.nk] = __dadd_rn(p2h, p1h);                                                           // :500-501
       }
     }
-    // the next item's writes to red/fin happen after its own __syncthreads, which every thread reaches only
-    // after finishing this epilogue
+    return;
   }
+
+  // ------------------------------------ consumers: 8 warps, 2 mass columns per thread ------------------------
+  double wv[2][NW];
+  int cur_b = -1, cur_slice = -1;
+  long long n = 0;
+  for (long long item = it0; item < it1; ++item, ++n) {
+    const int b = (int)(item / per_model);
+    const int rem = (int)(item - (long long)b * per_model);
+    const int slice = rem / a.ntiles, tile = rem - slice * a.ntiles;
+    const int m = slice * HM_MC + 2 * tid, row0 = tile * R;
+    const bool active = m < a.nM;
+    if (b != cur_b || slice != cur_slice) {   // weights of my two columns live in registers for the whole slice
+      cur_b = b; cur_slice = slice;
+      const double* __restrict__ w = a.weights + (size_t)b * NW * a.nMp + m;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) {
+        const double2 t = active ? *reinterpret_cast<const double2*>(w + (size_t)i * a.nMp) : make_double2(0., 0.);
+        wv[0][i] = t.x; wv[1][i] = t.y;
+      }
+    }
+    const int s = (int)(n % NS);
+    const uint32_t parity = (uint32_t)((n / NS) & 1);
+    hm_mbar_wait(bar_full + 8 * s, parity);                  // TMA bytes have landed
+    const double* st = ring + (size_t)s * C::STAGE_DOUBLES + 2 * tid;
+    double x[2][R][P];
+    const double xu[1][1] = {{0.}};
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const double2 t = active ? *reinterpret_cast<const double2*>(st + (r * P + p) * HM_MC) : make_double2(0., 0.);
+        x[0][r][p] = t.x; x[1][r][p] = t.y;
+      }
+    __syncwarp();
+    if (lane == 0) hm_mbar_arrive(bar_empty + 8 * s);        // values are in registers: release the slot early
+
+    double acc[NG * 32];
+#pragma unroll
+    for (int i = 0; i < NG * 32; ++i) acc[i] = 0.;
+    hm_accumulate<P, R, false>(acc, wv[0], x[0], xu);
+    hm_accumulate<P, R, false>(acc, wv[1], x[1], xu);
+
+    double* rbuf = red + (size_t)(n & 1) * (HM_CONSUMER_WARPS * NG * 32);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      double v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = acc[g * 32 + i];
+      rbuf[warp * (NG * 32) + g * 32 + lane] = hm_warp_transpose_sum32(v, lane);
+    }
+    hm_consumer_barrier();   // red is double buffered by item parity: one barrier per item suffices
+    if (tid < NV) {
+      double t = 0.;
+#pragma unroll
+      for (int wi = 0; wi < HM_CONSUMER_WARPS; ++wi) t += rbuf[wi * (NG * 32) + tid];
+      const int r = tid / NW, i = tid - r * NW;
+      if (row0 + r < a.nk) a.partial[(((size_t)b * a.nslices + slice) * NW + i) * a.nk + row0 + r] = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Epilogue: one thread per (model, wavenumber)                                          pyhalomodel.py:456-501
+// ---------------------------------------------------------------------------------------------------------------
+struct hm_epi_args {
+  int nk, B, F, P, NW, S, nslices, nchunks;
+  int simple_twohalo, subtract_shotnoise, correct_discrete;
+  double k_trunc;
+  const double* k;
+  const double* Pk_lin;      // [G][nk]
+  const double* partial;
+  const double* scal;
+  const double* cpart;
+  int discrete[HM_MAXP];
+  double* out;               // [B][S][3][nk]
+};
+
+template <int P>
+__global__ void __launch_bounds__(128) hm_epilogue_kernel(const hm_epi_args a) {
+  constexpr int S = P * (P + 1) / 2, NW = P + S;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)a.B * a.nk) return;
+  const int b = (int)(gid / a.nk), row = (int)(gid - (long long)b * a.nk);
+  const int smp = b / a.F;
+  const double rhom = a.scal[(size_t)b * HM_NSCAL + 1];
+
+  double f[NW];
+#pragma unroll
+  for (int i = 0; i < NW; ++i) {
+    double t = 0.;
+    for (int j = 0; j < a.nslices; ++j) t += a.partial[(((size_t)b * a.nslices + j) * NW + i) * a.nk + row];
+    f[i] = t;
+  }
+  double sn[P], simp[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    double t1 = 0., t2 = 0.;
+    const double* cp = a.cpart + (size_t)b * a.nchunks * 2 * HM_MAXP;
+    for (int c = 0; c < a.nchunks; ++c) {
+      t1 += cp[(size_t)c * 2 * HM_MAXP + p];
+      t2 += cp[(size_t)c * 2 * HM_MAXP + HM_MAXP + p];
+    }
+    sn[p] = t1 * rhom;       // P_SN = rhom trapz((amplitude/norm^2) g/M)   (:423-426)
+    simp[p] = t2 * rhom;     // k-independent two-halo integral             (:442-446)
+  }
+  const double plin = a.Pk_lin[(size_t)smp * a.nk + row];
+  double damp = 1.;
+  if (a.k_trunc > 0.) {                                                                      // :494-495
+    const double q = a.k[row] / a.k_trunc;
+    damp = 1. - exp(-(q * q));
+  }
+  int s = 0, icross = 2 * P;
+#pragma unroll
+  for (int u = 0; u < P; ++u)
+#pragma unroll
+    for (int v = u; v < P; ++v) {
+      const double Iu = a.simple_twohalo ? simp[u] : f[u] * rhom;                             // :540-543
+      const double Iv = a.simple_twohalo ? simp[v] : f[v] * rhom;
+      const double p2h = __dmul_rn(__dadd_rn(__dmul_rn(Iu, Iv), 0.), plin);                  // :524
+      double p1h = ((u == v) ? f[P + u] : f[icross]) * rhom;                                 // :532
+      if (u != v) ++icross;
+      if (u == v && a.discrete[u]) {                                                         // :484-491
+        if (a.correct_discrete && !a.subtract_shotnoise) p1h += sn[u];
+        else if (!a.correct_discrete && a.subtract_shotnoise) p1h -= sn[u];
+      }
+      if (a.k_trunc > 0.) p1h *= damp;
+      double* o = a.out + ((size_t)b * S + s) * 3 * a.nk + row;
+      o[0] = p2h;
+      o[a.nk] = p1h;
+      o[2 * (size_t)a.nk] = __dadd_rn(p2h, p1h);                                             // :500-501
+      ++s;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -364,6 +586,7 @@ static int hm_validate(const hm_problem* pr) {
   HM_REQUIRE(pr->M_dev && pr->sigma_dev && pr->Pk_lin_dev, "M, sigma and Pk_lin are required");
   HM_REQUIRE(pr->k_trunc <= 0. || pr->k_dev, "k is required when k_trunc is set");
   const long long B = (long long)pr->n_samples * pr->models_per_sample;
+  HM_REQUIRE(B <= 65535, "at most 65535 models per call");
   HM_REQUIRE(pr->models_dev || B == 1, "models_dev is required for more than one model");
   for (int p = 0; p < pr->n_tracers; ++p) {
     const hm_tracer& t = pr->tracers[p];
@@ -372,6 +595,14 @@ static int hm_validate(const hm_problem* pr) {
     HM_REQUIRE(t.grid_mode != HM_GRID_SEPARATE || t.wk_dev, "HM_GRID_SEPARATE needs wk_dev");
     HM_REQUIRE(t.amplitude_dev || t.grid_mode == HM_GRID_WK, "amplitude is required unless grid_mode is HM_GRID_WK");
     HM_REQUIRE(t.normalisation_dev, "normalisation is required");
+  }
+  return HM_OK;
+}
+
+static int hm_check_workspace(const char* who, const hm_layout& L, const void* ws, size_t ws_bytes) {
+  if (!ws || ws_bytes < L.total_bytes || ((uintptr_t)ws & 15)) {
+    hm_set_error("%s: workspace needs %zu bytes, 16-byte aligned (got %zu)", who, L.total_bytes, ws_bytes);
+    return HM_ERR_WORKSPACE;
   }
   return HM_OK;
 }
@@ -386,14 +617,10 @@ extern "C" int hm_halo_weights(const hm_problem* pr, double* lowmass_dev, void* 
   if (rc) return rc;
   if ((rc = hm_validate(pr))) return rc;
   const hm_layout L = hm_make_layout(pr);
-  if (!ws || ws_bytes < L.total_bytes || ((uintptr_t)ws & 15)) {
-    hm_set_error("hm_halo_weights: workspace needs %zu bytes, 16-byte aligned (got %zu)", L.total_bytes, ws_bytes);
-    return HM_ERR_WORKSPACE;
-  }
+  if ((rc = hm_check_workspace("hm_halo_weights", L, ws, ws_bytes))) return rc;
   hm_weights_args a;
-  a.nM = pr->nM; a.nMp = L.nMp; a.P = L.P; a.NW = L.NW; a.F = pr->models_per_sample;
-  a.B = pr->n_samples * pr->models_per_sample;
-  a.simple_twohalo = pr->simple_twohalo; a.correct_discrete = pr->correct_discrete;
+  a.nM = pr->nM; a.nMp = L.nMp; a.P = L.P; a.NW = L.NW; a.F = pr->models_per_sample; a.nchunks = L.nchunks;
+  a.correct_discrete = pr->correct_discrete;
   a.M = pr->M_dev; a.sigma = pr->sigma_dev; a.models = pr->models_dev; a.single = pr->model_host;
   for (int p = 0; p < HM_MAXP; ++p) {
     const bool on = p < L.P;
@@ -406,20 +633,23 @@ extern "C" int hm_halo_weights(const hm_problem* pr, double* lowmass_dev, void* 
   }
   a.weights = (double*)ws;
   a.scal = (double*)ws + L.scal_offset;
+  a.cpart = (double*)ws + L.cpart_offset;
   a.lowmass = lowmass_dev;
-  hm_weights_kernel<<<a.B, 256, 0, (cudaStream_t)stream>>>(a);
+  dim3 grid(L.nchunks, (unsigned)L.B);
+  hm_weights_kernel<<<grid, HM_WCHUNK, 0, (cudaStream_t)stream>>>(a);
   HM_LAUNCH_CHECK();
   return HM_OK;
 }
 
 template <int P, int R>
-static int hm_launch_quad(const hm_quad_args& a, bool vec2, bool sep, cudaStream_t st) {
+static int hm_launch_fallback(hm_quad_args& a, bool vec2, bool sep, cudaStream_t st) {
+  a.ntiles = (a.nk + R - 1) / R;
+  a.nitems = (long long)a.B * a.ntiles;
   const int ncol = vec2 ? a.nM / 2 : a.nM;
   int threads = ((ncol + 31) / 32) * 32;
   if (threads > 256) threads = 256;
   if (threads < 64) threads = 64;
-  const int ctas_per_sm = 2048 / threads > 8 ? 8 : 2048 / threads;
-  long long grid = (long long)hm_num_sms() * ctas_per_sm;
+  long long grid = (long long)hm_num_sms() * (512 / threads);
   if (grid > a.nitems) grid = a.nitems;
   if (vec2) {
     if (sep) hm_quad_kernel<P, R, 2, true><<<(int)grid, threads, 0, st>>>(a);
@@ -432,6 +662,32 @@ static int hm_launch_quad(const hm_quad_args& a, bool vec2, bool sep, cudaStream
   return HM_OK;
 }
 
+template <int P, int R>
+static int hm_launch_stream(hm_quad_args& a, cudaStream_t st) {
+  using C = hm_stream_cfg<P, R>;
+  static bool configured = false;
+  if (!configured) {
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_quad_stream_kernel<P, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::SMEM_BYTES));
+    configured = true;
+  }
+  a.ntiles = (a.nk + R - 1) / R;
+  a.nitems = (long long)a.B * a.nslices * a.ntiles;
+  long long grid = hm_num_sms();
+  if (grid > a.nitems) grid = a.nitems;
+  hm_quad_stream_kernel<P, R><<<(int)grid, HM_STREAM_THREADS, C::SMEM_BYTES, st>>>(a);
+  HM_LAUNCH_CHECK();
+  return HM_OK;
+}
+
+template <int P>
+static int hm_launch_epilogue(const hm_epi_args& e, cudaStream_t st) {
+  const long long n = (long long)e.B * e.nk;
+  hm_epilogue_kernel<P><<<(int)((n + 127) / 128), 128, 0, st>>>(e);
+  HM_LAUNCH_CHECK();
+  return HM_OK;
+}
+
 extern "C" int hm_mass_quadrature(const hm_problem* pr, double* out_dev, const void* ws, size_t ws_bytes,
                                   void* stream) {
   int rc = hm_check_device();
@@ -439,34 +695,34 @@ extern "C" int hm_mass_quadrature(const hm_problem* pr, double* out_dev, const v
   if ((rc = hm_validate(pr))) return rc;
   HM_REQUIRE(out_dev, "out_dev is NULL");
   const hm_layout L = hm_make_layout(pr);
-  if (!ws || ws_bytes < L.total_bytes || ((uintptr_t)ws & 15)) {
-    hm_set_error("hm_mass_quadrature: workspace needs %zu bytes, 16-byte aligned (got %zu)", L.total_bytes, ws_bytes);
-    return HM_ERR_WORKSPACE;
-  }
+  if ((rc = hm_check_workspace("hm_mass_quadrature", L, ws, ws_bytes))) return rc;
   hm_quad_args a;
-  a.nk = pr->nk; a.nM = pr->nM; a.nMp = L.nMp; a.F = pr->models_per_sample;
-  a.B = pr->n_samples * pr->models_per_sample;
-  a.simple_twohalo = pr->simple_twohalo; a.subtract_shotnoise = pr->subtract_shotnoise;
-  a.correct_discrete = pr->correct_discrete; a.k_trunc = pr->k_trunc; a.k = pr->k_dev; a.Pk_lin = pr->Pk_lin_dev;
+  a.nk = pr->nk; a.nM = pr->nM; a.nMp = L.nMp; a.F = pr->models_per_sample; a.B = (int)L.B; a.nslices = L.nslices;
   bool sep = false, aligned = (pr->nM % 2 == 0);
   for (int p = 0; p < HM_MAXP; ++p) {
     const bool on = p < L.P;
     const hm_tracer& t = pr->tracers[p];
     a.gridU[p] = on ? t.grid_dev : nullptr;
     a.gridW[p] = on ? (t.grid_mode == HM_GRID_SEPARATE ? t.wk_dev : t.grid_dev) : nullptr;
-    a.discrete[p] = on ? t.discrete_tracer : 0;
     if (on && t.grid_mode == HM_GRID_SEPARATE) sep = true;
     if (on && (((uintptr_t)a.gridU[p] | (uintptr_t)a.gridW[p]) & 15)) aligned = false;
   }
   a.weights = (const double*)ws;
-  a.scal = (const double*)ws + L.scal_offset;
-  a.out = out_dev;
+  a.partial = (double*)ws + L.partial_offset;
+  hm_epi_args e;
+  e.nk = pr->nk; e.B = (int)L.B; e.F = pr->models_per_sample; e.P = L.P; e.NW = L.NW; e.S = L.S;
+  e.nslices = L.nslices; e.nchunks = L.nchunks;
+  e.simple_twohalo = pr->simple_twohalo; e.subtract_shotnoise = pr->subtract_shotnoise;
+  e.correct_discrete = pr->correct_discrete; e.k_trunc = pr->k_trunc; e.k = pr->k_dev; e.Pk_lin = pr->Pk_lin_dev;
+  e.partial = a.partial; e.scal = (const double*)ws + L.scal_offset; e.cpart = (const double*)ws + L.cpart_offset;
+  for (int p = 0; p < HM_MAXP; ++p) e.discrete[p] = (p < L.P) ? pr->tracers[p].discrete_tracer : 0;
+  e.out = out_dev;
   cudaStream_t st = (cudaStream_t)stream;
-#define HM_CASE(PP, RR)                                   \
-  case PP:                                                \
-    a.ntiles = (pr->nk + RR - 1) / RR;                    \
-    a.nitems = (long long)a.B * a.ntiles;                 \
-    return hm_launch_quad<PP, RR>(a, aligned, sep, st);
+#define HM_CASE(PP, RR)                                                            \
+  case PP:                                                                         \
+    rc = L.stream ? hm_launch_stream<PP, RR>(a, st) : hm_launch_fallback<PP, RR>(a, aligned, sep, st); \
+    if (rc) return rc;                                                             \
+    return hm_launch_epilogue<PP>(e, st);
   switch (L.P) {
     HM_CASE(1, 8)
     HM_CASE(2, 4)
