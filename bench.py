@@ -256,7 +256,7 @@ def main():
         tj = json.load(open(tpath))
         if tj.get('batch') == B:
             traffic = tj.get('dram_bytes_per_launch')
-    roofline = dict(bound='hbm', kernel='hm_quad_kernel<3,3,2,false>', achieved=achieved, peak=peak, unit='GB/s',
+    roofline = dict(bound='hbm', kernel='hm_quad_stream_kernel<3,3> (+ hm_epilogue_kernel<3>, timed together)', achieved=achieved, peak=peak, unit='GB/s',
                     frac=achieved/peak, traffic=traffic, algorithmic_bytes_per_launch=alg_bytes,
                     kernel_ms=quad_ms, weights_kernel_ms=weights_ms, peak_source=peak_src)
 
@@ -325,7 +325,7 @@ def main():
                     config=dict(workload=WORKLOAD % B, nk=NK, nM=NM, tracers=list(TRACERS), family='Tinker et al. (2010)',
                                 models_per_gpu_per_step=B, l2='inputs larger than L2: %.0f MB of grids per step per GPU'
                                 % (B*len(TRACERS)*NK*NM*8/1e6), collective='all_gather of spectra (NCCL)' if world > 1 else 'none'),
-                    clocks=clocks, e2e=e2e, gpu_launches=2*K, roofline=roofline, cpu_baseline=cpu)
+                    clocks=clocks, e2e=e2e, gpu_launches=3*K, roofline=roofline, cpu_baseline=cpu)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

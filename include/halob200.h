@@ -135,6 +135,10 @@ int hm_halo_weights(const hm_problem* prob, double* lowmass_dev, void* workspace
                     void* stream);
 int hm_mass_quadrature(const hm_problem* prob, double* out_dev, const void* workspace_dev, size_t workspace_bytes,
                        void* stream);
+/* Same, launching only part of stage 2 (for timing the dominant kernel alone): bit 0 = the streaming kernel that
+ * reduces the (k,M) grids to partial row sums, bit 1 = the epilogue kernel that forms the spectra. */
+int hm_mass_quadrature_stages(const hm_problem* prob, double* out_dev, const void* workspace_dev,
+                              size_t workspace_bytes, void* stream, int stages);
 
 /* ---- Fourier profiles ------------------------------------------------------------------------------------
  * Si(x), Ci(x) element-wise (scipy.special.sici as used at pyhalomodel.py:1033-1035,1044-1049). */

@@ -50,6 +50,8 @@ _SIGNATURES = {
     'hm_power_spectrum': (C.c_int, [C.POINTER(Problem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'hm_halo_weights': (C.c_int, [C.POINTER(Problem), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'hm_mass_quadrature': (C.c_int, [C.POINTER(Problem), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    'hm_mass_quadrature_stages': (C.c_int, [C.POINTER(Problem), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                            C.c_int]),
     'hm_sici': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     'hm_window_nfw': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_void_p]),

@@ -62,7 +62,8 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
 //   weights [B][NW][nMp]            per-mass weight vectors
 //   scal    [B][HM_NSCAL]           A, rhom
 //   cpart   [B][nchunks][2*HM_MAXP] per-mass-chunk partial sums of the shot-noise and simple-two-halo integrals
-//   partial [B][nslices][NW][nk]    per-mass-slice row sums written by the quadrature kernel
+//   partial [B][nparts][nk][NW]     partial row sums over mass sub-ranges written by the quadrature kernel
+//                                   (streaming kernel: one part per consumer warp per 512-mass slice)
 // ---------------------------------------------------------------------------------------------------------------
 #define HM_NSCAL 4
 #define HM_WCHUNK 256        // masses per CTA of the weights kernel
@@ -71,7 +72,7 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
 #define HM_STREAM_THREADS (32 * (HM_CONSUMER_WARPS + 1))
 
 struct hm_layout {
-  int P, S, NW, nMp, nchunks, nslices;
+  int P, S, NW, nMp, nchunks, nslices, nparts;
   bool stream;
   size_t B, scal_offset, cpart_offset, partial_offset, total_bytes;
 };
@@ -94,12 +95,13 @@ static hm_layout hm_make_layout(const hm_problem* pr) {
   L.nchunks = (L.nMp + HM_WCHUNK - 1) / HM_WCHUNK;
   L.stream = hm_can_stream(pr);
   L.nslices = L.stream ? (pr->nM + HM_MC - 1) / HM_MC : 1;
+  L.nparts = L.stream ? L.nslices * HM_CONSUMER_WARPS : 1;
   L.B = (size_t)pr->n_samples * (size_t)pr->models_per_sample;
   auto align = [](size_t x) { return (x + 31) & ~(size_t)31; };
   L.scal_offset = align(L.B * (size_t)L.NW * (size_t)L.nMp);
   L.cpart_offset = align(L.scal_offset + L.B * HM_NSCAL);
   L.partial_offset = align(L.cpart_offset + L.B * (size_t)L.nchunks * 2 * HM_MAXP);
-  L.total_bytes = (L.partial_offset + L.B * (size_t)L.nslices * L.NW * (size_t)pr->nk) * sizeof(double);
+  L.total_bytes = (L.partial_offset + L.B * (size_t)L.nparts * L.NW * (size_t)pr->nk) * sizeof(double);
   return L;
 }
 
@@ -122,24 +124,28 @@ struct hm_weights_args {
 };
 
 __global__ void __launch_bounds__(HM_WCHUNK) hm_weights_kernel(const hm_weights_args a) {
-  __shared__ double scratch[32];
+  constexpr int NRED = 2 * HM_MAXP + 1;                 // shot noise [8], simple two-halo [8], low-mass integral
+  __shared__ double sred[HM_WCHUNK / 32][NRED];
+  __shared__ double stot[NRED];
+  __shared__ double s_an0[HM_MAXP];
   const int b = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int s = b / a.F;
   const hm_model_desc d = a.models ? a.models[b] : a.single;
   const double* sig = a.sigma + (size_t)s * a.nM;
   const double M0 = a.M[0];
 
-  // A = 1 - int g b dnu from nu[0] (pyhalomodel.py:413-414); every chunk CTA recomputes the same value
-  const double nu_first = d.dc / sig[0];
-  const double A = 1. - hm_block_sum(hm_lowmass_node(d, nu_first, threadIdx.x), scratch);
-  const double Aterm = A / M0;   // multiplies W(k, M[0]) for mass tracers (:541-542)
-
-  double sn[HM_MAXP], simp[HM_MAXP];
+  double red[NRED];
 #pragma unroll
-  for (int p = 0; p < HM_MAXP; ++p) sn[p] = simp[p] = 0.;
+  for (int i = 0; i < NRED; ++i) red[i] = 0.;
+  // A = 1 - int g b dnu from nu[0] (pyhalomodel.py:413-414): one Gauss-Legendre node per thread, chunk 0 only
+  if (chunk == 0) red[2 * HM_MAXP] = hm_lowmass_node(d, d.dc / sig[0], tid);
 
   double* wout = a.weights + (size_t)b * a.NW * a.nMp;
-  const int m = chunk * HM_WCHUNK + threadIdx.x;
+  const int m = chunk * HM_WCHUNK + tid;
+  double cW[HM_MAXP], w2_plain = 0.;
+#pragma unroll
+  for (int p = 0; p < HM_MAXP; ++p) cW[p] = 0.;
   if (m < a.nMp && m >= a.nM) {   // padding column
     for (int i = 0; i < a.NW; ++i) wout[(size_t)i * a.nMp + m] = 0.;
   } else if (m < a.nM) {
@@ -151,13 +157,9 @@ __global__ void __launch_bounds__(HM_WCHUNK) hm_weights_kernel(const hm_weights_
     const double bg = hm_b_nu(d, nu) * g;
     const double Mm = a.M[m];
     const double w1 = tw * (g / Mm);           // one-halo weight  (:530)
-    const double w2_plain = tw * (bg / Mm);    // two-halo weight  (:539)
-    const double w2_mass = w2_plain + ((m == 0) ? Aterm : 0.);   // + low-mass term for mass tracers
-
-    double cW[HM_MAXP];
+    w2_plain = tw * (bg / Mm);                 // two-halo weight  (:539); the low-mass term is patched in below
 #pragma unroll
     for (int p = 0; p < HM_MAXP; ++p) {
-      cW[p] = 0.;
       if (p < a.P) {
         const double amp = a.amplitude[p][(size_t)s * a.amp_stride[p] + m];
         const double norm = a.norm[p][b];
@@ -169,11 +171,11 @@ __global__ void __launch_bounds__(HM_WCHUNK) hm_weights_kernel(const hm_weights_
         if (a.mode[p] == HM_GRID_UK) { cW[p] = an; uS = 1. / norm; }
         else if (a.mode[p] == HM_GRID_WK) { cW[p] = 1.; uS = 1. / (amp * norm); }
         else { cW[p] = 1.; uS = 1. / norm; }
-        const double w2p = a.mass[p] ? w2_mass : w2_plain;
-        wout[(size_t)p * a.nMp + m] = w2p * cW[p];                                       // e_p
+        wout[(size_t)p * a.nMp + m] = w2_plain * cW[p];                                  // e_p
         wout[(size_t)(a.P + p) * a.nMp + m] = __dmul_rn(__dmul_rn(w1, fac), uS * uS);     // d_p
-        sn[p] = w1 * (amp / (norm * norm));                                              // shot noise integrand (:425)
-        simp[p] = w2p * an;                                                              // simple two-halo (:442-446)
+        red[p] = w1 * (amp / (norm * norm));                                             // shot noise integrand (:425)
+        red[HM_MAXP + p] = w2_plain * an;                                                // simple two-halo (:442-446)
+        if (m == 0) s_an0[p] = an;
       }
     }
     int idx = 2 * a.P;
@@ -181,16 +183,32 @@ __global__ void __launch_bounds__(HM_WCHUNK) hm_weights_kernel(const hm_weights_
       for (int v = u + 1; v < a.P; ++v) wout[(size_t)(idx++) * a.nMp + m] = w1 * cW[u] * cW[v];   // q_uv
   }
 
-  double* cp = a.cpart + ((size_t)b * a.nchunks + chunk) * 2 * HM_MAXP;
-  for (int p = 0; p < a.P; ++p) {
-    const double t1 = hm_block_sum(sn[p], scratch);
-    const double t2 = hm_block_sum(simp[p], scratch);
-    if (threadIdx.x == 0) {
-      cp[p] = a.discrete[p] ? t1 : 0.;
-      cp[HM_MAXP + p] = t2;
-    }
+  // one reduction phase for all 17 sums: warp butterflies, then a fixed-order sum over the 8 warps
+#pragma unroll
+  for (int i = 0; i < NRED; ++i) {
+    const double t = hm_warp_sum(red[i]);
+    if (lane == 0) sred[warp][i] = t;
   }
-  if (chunk == 0 && threadIdx.x == 0) {
+  __syncthreads();
+  if (tid < NRED) {
+    double t = 0.;
+#pragma unroll
+    for (int w = 0; w < HM_WCHUNK / 32; ++w) t += sred[w][tid];
+    stot[tid] = t;
+  }
+  __syncthreads();
+  const double A = 1. - stot[2 * HM_MAXP];
+  const double Aterm = A / M0;   // multiplies W(k, M[0]) for mass tracers (:541-542)
+  double* cp = a.cpart + ((size_t)b * a.nchunks + chunk) * 2 * HM_MAXP;
+  if (tid < a.P) {
+    cp[tid] = a.discrete[tid] ? stot[tid] : 0.;
+    const double low = (chunk == 0 && a.mass[tid]) ? Aterm * s_an0[tid] : 0.;
+    cp[HM_MAXP + tid] = stot[HM_MAXP + tid] + low;
+  }
+  if (chunk == 0 && tid == 0) {
+#pragma unroll
+    for (int p = 0; p < HM_MAXP; ++p)
+      if (p < a.P && a.mass[p]) wout[(size_t)p * a.nMp] = (w2_plain + Aterm) * cW[p];     // e_p[0] with the low-mass term
     double* sc = a.scal + (size_t)b * HM_NSCAL;
     sc[0] = A;
     sc[1] = d.rhom;
@@ -202,12 +220,12 @@ __global__ void __launch_bounds__(HM_WCHUNK) hm_weights_kernel(const hm_weights_
 // Shared pieces of the two quadrature kernels
 // ---------------------------------------------------------------------------------------------------------------
 struct hm_quad_args {
-  int nk, nM, nMp, F, B, ntiles, nslices;
+  int nk, nM, nMp, F, B, ntiles, nslices, nparts;
   long long nitems;
   const double* gridW[HM_MAXP];      // two-halo / cross source
   const double* gridU[HM_MAXP];      // auto one-halo source (== gridW unless HM_GRID_SEPARATE)
   const double* weights;
-  double* partial;                   // [B][nslices][NW][nk]
+  double* partial;                   // [B][nparts][nk][NW]
 };
 
 // v[0..32) per lane  ->  lane l holds the warp-wide sum of v[l]  (31 shuffles instead of 160).
@@ -332,7 +350,7 @@ __global__ void __launch_bounds__(256) hm_quad_kernel(const hm_quad_args a) {
       double t = 0.;
       for (int wi = 0; wi < nwarps; ++wi) t += red[wi][tid];
       const int r = tid / NW, i = tid - r * NW;
-      if (row0 + r < a.nk) a.partial[((size_t)b * NW + i) * a.nk + row0 + r] = t;
+      if (row0 + r < a.nk) a.partial[((size_t)b * a.nk + row0 + r) * NW + i] = t;
     }
     __syncthreads();
   }
@@ -369,9 +387,6 @@ __device__ __forceinline__ void hm_bulk_g2s(uint32_t dst, const void* src, uint3
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void hm_consumer_barrier() {   // named barrier 1: the 256 consumer threads only
-  asm volatile("bar.sync 1, %0;" ::"n"(32 * HM_CONSUMER_WARPS) : "memory");
-}
 
 template <int P, int R>
 struct hm_stream_cfg {
@@ -381,20 +396,36 @@ struct hm_stream_cfg {
   static constexpr int NG = (NV + 31) / 32;
   static constexpr int STAGE_DOUBLES = R * P * HM_MC;
   static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
-  static constexpr int RED_DOUBLES = 2 * HM_CONSUMER_WARPS * NG * 32;
-  static constexpr int BUDGET = 226 * 1024 - RED_DOUBLES * 8 - 256;
+  static constexpr int BUDGET = 226 * 1024 - 256;
   static constexpr int NS = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = NS * STAGE_BYTES + RED_DOUBLES * 8 + 256;
+  static constexpr int SMEM_BYTES = NS * STAGE_BYTES + 256;
+};
+
+// (model, mass slice, row tile) cursor over the item range of one CTA, advanced without integer division
+struct hm_item_cursor {
+  int b, slice, tile;
+  __device__ __forceinline__ void init(long long item, int nslices, int ntiles) {
+    const long long per_model = (long long)nslices * ntiles;
+    b = (int)(item / per_model);
+    const int rem = (int)(item - (long long)b * per_model);
+    slice = rem / ntiles;
+    tile = rem - slice * ntiles;
+  }
+  __device__ __forceinline__ void next(int nslices, int ntiles) {
+    if (++tile == ntiles) {
+      tile = 0;
+      if (++slice == nslices) { slice = 0; ++b; }
+    }
+  }
 };
 
 template <int P, int R>
 __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(const hm_quad_args a) {
   using C = hm_stream_cfg<P, R>;
-  constexpr int NW = C::NW, NV = C::NV, NG = C::NG, NS = C::NS;
+  constexpr int NW = C::NW, NG = C::NG, NS = C::NS;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* ring = reinterpret_cast<double*>(smem_raw);
-  double* red = ring + (size_t)NS * C::STAGE_DOUBLES;                    // [2][warps][NG*32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red + C::RED_DOUBLES);    // full[NS], empty[NS]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)NS * C::STAGE_DOUBLES);    // full[NS], empty[NS]
   const uint32_t bar_full = hm_smem_addr(bars), bar_empty = hm_smem_addr(bars + NS);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -411,21 +442,20 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
   const long long per = (a.nitems + gridDim.x - 1) / gridDim.x;
   const long long it0 = (long long)blockIdx.x * per;
   const long long it1 = (it0 + per < a.nitems) ? it0 + per : a.nitems;
-  const long long per_model = (long long)a.nslices * a.ntiles;
+  if (it0 >= it1) return;
+  const int nloc = (int)(it1 - it0);
+  hm_item_cursor cur;
+  cur.init(it0, a.nslices, a.ntiles);
 
   if (warp == HM_CONSUMER_WARPS) {
     // ------------------------------ producer: one lane drives the TMA engine ------------------------------
     if (lane == 0) {
-      long long n = 0;
-      for (long long item = it0; item < it1; ++item, ++n) {
-        const int b = (int)(item / per_model);
-        const int rem = (int)(item - (long long)b * per_model);
-        const int slice = rem / a.ntiles, tile = rem - slice * a.ntiles;
-        const int smp = b / a.F, m0 = slice * HM_MC, row0 = tile * R;
+      int s = 0;
+      uint32_t parity = 0;
+      for (int n = 0; n < nloc; ++n) {
+        const int smp = cur.b / a.F, m0 = cur.slice * HM_MC, row0 = cur.tile * R;
         const int cols = (a.nM - m0 < HM_MC) ? a.nM - m0 : HM_MC;
         const uint32_t bytes = (uint32_t)cols * 8u;
-        const int s = (int)(n % NS);
-        const uint32_t parity = (uint32_t)((n / NS) & 1);
         hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);        // slot drained by all consumer warps
         hm_mbar_arrive_expect_tx(bar_full + 8 * s, bytes * (uint32_t)(R * P));
         const uint32_t dst0 = hm_smem_addr(ring + (size_t)s * C::STAGE_DOUBLES);
@@ -437,32 +467,32 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
           for (int p = 0; p < P; ++p)
             hm_bulk_g2s(dst0 + (uint32_t)((r * P + p) * HM_MC * 8), a.gridW[p] + off, bytes, bar_full + 8 * s);
         }
+        cur.next(a.nslices, a.ntiles);
+        if (++s == NS) { s = 0; parity ^= 1u; }
       }
     }
     return;
   }
 
-  // ------------------------------------ consumers: 8 warps, 2 mass columns per thread ------------------------
+  // ---------------- consumers: 8 independent warps, 64 mass columns per warp, 2 per thread -----------------
+  // No CTA-wide synchronisation: every warp reduces its own 64 columns and writes its own partial row sums;
+  // the epilogue kernel adds the parts in fixed order.
   double wv[2][NW];
   int cur_b = -1, cur_slice = -1;
-  long long n = 0;
-  for (long long item = it0; item < it1; ++item, ++n) {
-    const int b = (int)(item / per_model);
-    const int rem = (int)(item - (long long)b * per_model);
-    const int slice = rem / a.ntiles, tile = rem - slice * a.ntiles;
-    const int m = slice * HM_MC + 2 * tid, row0 = tile * R;
+  int s = 0;
+  uint32_t parity = 0;
+  for (int n = 0; n < nloc; ++n) {
+    const int m = cur.slice * HM_MC + 2 * tid, row0 = cur.tile * R;
     const bool active = m < a.nM;
-    if (b != cur_b || slice != cur_slice) {   // weights of my two columns live in registers for the whole slice
-      cur_b = b; cur_slice = slice;
-      const double* __restrict__ w = a.weights + (size_t)b * NW * a.nMp + m;
+    if (cur.b != cur_b || cur.slice != cur_slice) {   // weights of my two columns stay in registers for the slice
+      cur_b = cur.b; cur_slice = cur.slice;
+      const double* __restrict__ w = a.weights + (size_t)cur.b * NW * a.nMp + m;
 #pragma unroll
       for (int i = 0; i < NW; ++i) {
         const double2 t = active ? *reinterpret_cast<const double2*>(w + (size_t)i * a.nMp) : make_double2(0., 0.);
         wv[0][i] = t.x; wv[1][i] = t.y;
       }
     }
-    const int s = (int)(n % NS);
-    const uint32_t parity = (uint32_t)((n / NS) & 1);
     hm_mbar_wait(bar_full + 8 * s, parity);                  // TMA bytes have landed
     const double* st = ring + (size_t)s * C::STAGE_DOUBLES + 2 * tid;
     double x[2][R][P];
@@ -483,22 +513,19 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
     hm_accumulate<P, R, false>(acc, wv[0], x[0], xu);
     hm_accumulate<P, R, false>(acc, wv[1], x[1], xu);
 
-    double* rbuf = red + (size_t)(n & 1) * (HM_CONSUMER_WARPS * NG * 32);
+    // partial[b][slice*8 + warp][row0 + r][i]: the R*NW values of this tile are contiguous -> coalesced store
+    double* dst = a.partial + (((size_t)cur.b * a.nparts + cur.slice * HM_CONSUMER_WARPS + warp) * a.nk + row0) * NW;
+    const int nvalid = ((a.nk - row0 < R) ? a.nk - row0 : R) * NW;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
       double v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = acc[g * 32 + i];
-      rbuf[warp * (NG * 32) + g * 32 + lane] = hm_warp_transpose_sum32(v, lane);
+      const double t = hm_warp_transpose_sum32(v, lane);
+      if (g * 32 + lane < nvalid) dst[g * 32 + lane] = t;
     }
-    hm_consumer_barrier();   // red is double buffered by item parity: one barrier per item suffices
-    if (tid < NV) {
-      double t = 0.;
-#pragma unroll
-      for (int wi = 0; wi < HM_CONSUMER_WARPS; ++wi) t += rbuf[wi * (NG * 32) + tid];
-      const int r = tid / NW, i = tid - r * NW;
-      if (row0 + r < a.nk) a.partial[(((size_t)b * a.nslices + slice) * NW + i) * a.nk + row0 + r] = t;
-    }
+    cur.next(a.nslices, a.ntiles);
+    if (++s == NS) { s = 0; parity ^= 1u; }
   }
 }
 
@@ -506,7 +533,7 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
 // Epilogue: one thread per (model, wavenumber)                                          pyhalomodel.py:456-501
 // ---------------------------------------------------------------------------------------------------------------
 struct hm_epi_args {
-  int nk, B, F, P, NW, S, nslices, nchunks;
+  int nk, B, F, P, NW, S, nparts, nchunks;
   int simple_twohalo, subtract_shotnoise, correct_discrete;
   double k_trunc;
   const double* k;
@@ -518,61 +545,85 @@ struct hm_epi_args {
   double* out;               // [B][S][3][nk]
 };
 
+// One CTA per (model, 32 wavenumbers).  Phase 1: PG part-groups x 32 rows of threads add the mass parts (coalesced:
+// 32 rows x NW values are contiguous); phase 2: one thread per (pair, row) finishes the spectra with coalesced
+// stores.  All sums run in a fixed order => bitwise reproducible.
+#define HM_EPI_ROWS 32
 template <int P>
-__global__ void __launch_bounds__(128) hm_epilogue_kernel(const hm_epi_args a) {
+__global__ void __launch_bounds__(256) hm_epilogue_kernel(const hm_epi_args a) {
   constexpr int S = P * (P + 1) / 2, NW = P + S;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (long long)a.B * a.nk) return;
-  const int b = (int)(gid / a.nk), row = (int)(gid - (long long)b * a.nk);
+  extern __shared__ double sf[];                       // [PG][NW][32] partial sums, then 2*HM_MAXP chunk sums
+  const int PG = blockDim.x / HM_EPI_ROWS;
+  double* scs = sf + (size_t)PG * NW * HM_EPI_ROWS;
+  const int tid = threadIdx.x, r = tid & 31, pg = tid >> 5;
+  const int tiles_per_model = (a.nk + HM_EPI_ROWS - 1) / HM_EPI_ROWS;
+  const int b = blockIdx.x / tiles_per_model;
+  const int row0 = (blockIdx.x - b * tiles_per_model) * HM_EPI_ROWS;
   const int smp = b / a.F;
   const double rhom = a.scal[(size_t)b * HM_NSCAL + 1];
+  const int row = row0 + r;
 
   double f[NW];
 #pragma unroll
-  for (int i = 0; i < NW; ++i) {
+  for (int i = 0; i < NW; ++i) f[i] = 0.;
+  if (row < a.nk) {
+#pragma unroll 4
+    for (int j = pg; j < a.nparts; j += PG) {
+      const double* pp = a.partial + (((size_t)b * a.nparts + j) * a.nk + row) * NW;
+#pragma unroll
+      for (int i = 0; i < NW; ++i) f[i] += pp[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NW; ++i) sf[((size_t)pg * NW + i) * HM_EPI_ROWS + r] = f[i];
+  if (tid < 2 * HM_MAXP) {     // tid < 8: shot noise of tracer tid; tid >= 8: simple two-halo integral
+    const double* cp = a.cpart + (size_t)b * a.nchunks * 2 * HM_MAXP + tid;
     double t = 0.;
-    for (int j = 0; j < a.nslices; ++j) t += a.partial[(((size_t)b * a.nslices + j) * NW + i) * a.nk + row];
-    f[i] = t;
+    for (int c = 0; c < a.nchunks; ++c) t += cp[(size_t)c * 2 * HM_MAXP];
+    scs[tid] = t * rhom;       // P_SN = rhom trapz((amplitude/norm^2) g/M) (:423-426); simple two-halo (:442-446)
   }
-  double sn[P], simp[P];
+  __syncthreads();
+
+  for (int idx = tid; idx < S * HM_EPI_ROWS; idx += blockDim.x) {
+    const int s = idx >> 5, rr = idx & 31;            // a warp works on one pair: (u, v) is warp-uniform
+    const int krow = row0 + rr;
+    if (krow >= a.nk) continue;
+    int u = 0, v = 0, i1h = 0;
+    {
+      int cnt = 0, icross = 2 * P;
 #pragma unroll
-  for (int p = 0; p < P; ++p) {
-    double t1 = 0., t2 = 0.;
-    const double* cp = a.cpart + (size_t)b * a.nchunks * 2 * HM_MAXP;
-    for (int c = 0; c < a.nchunks; ++c) {
-      t1 += cp[(size_t)c * 2 * HM_MAXP + p];
-      t2 += cp[(size_t)c * 2 * HM_MAXP + HM_MAXP + p];
+      for (int uu = 0; uu < P; ++uu)
+#pragma unroll
+        for (int vv = uu; vv < P; ++vv) {
+          if (cnt == s) { u = uu; v = vv; i1h = (uu == vv) ? P + uu : icross; }
+          if (uu != vv) ++icross;
+          ++cnt;
+        }
     }
-    sn[p] = t1 * rhom;       // P_SN = rhom trapz((amplitude/norm^2) g/M)   (:423-426)
-    simp[p] = t2 * rhom;     // k-independent two-halo integral             (:442-446)
-  }
-  const double plin = a.Pk_lin[(size_t)smp * a.nk + row];
-  double damp = 1.;
-  if (a.k_trunc > 0.) {                                                                      // :494-495
-    const double q = a.k[row] / a.k_trunc;
-    damp = 1. - exp(-(q * q));
-  }
-  int s = 0, icross = 2 * P;
-#pragma unroll
-  for (int u = 0; u < P; ++u)
-#pragma unroll
-    for (int v = u; v < P; ++v) {
-      const double Iu = a.simple_twohalo ? simp[u] : f[u] * rhom;                             // :540-543
-      const double Iv = a.simple_twohalo ? simp[v] : f[v] * rhom;
-      const double p2h = __dmul_rn(__dadd_rn(__dmul_rn(Iu, Iv), 0.), plin);                  // :524
-      double p1h = ((u == v) ? f[P + u] : f[icross]) * rhom;                                 // :532
-      if (u != v) ++icross;
-      if (u == v && a.discrete[u]) {                                                         // :484-491
-        if (a.correct_discrete && !a.subtract_shotnoise) p1h += sn[u];
-        else if (!a.correct_discrete && a.subtract_shotnoise) p1h -= sn[u];
-      }
-      if (a.k_trunc > 0.) p1h *= damp;
-      double* o = a.out + ((size_t)b * S + s) * 3 * a.nk + row;
-      o[0] = p2h;
-      o[a.nk] = p1h;
-      o[2 * (size_t)a.nk] = __dadd_rn(p2h, p1h);                                             // :500-501
-      ++s;
+    double fu = 0., fv = 0., f1 = 0.;
+    for (int g = 0; g < PG; ++g) {
+      const double* base = sf + (size_t)g * NW * HM_EPI_ROWS + rr;
+      fu += base[u * HM_EPI_ROWS];
+      fv += base[v * HM_EPI_ROWS];
+      f1 += base[i1h * HM_EPI_ROWS];
     }
+    const double Iu = a.simple_twohalo ? scs[HM_MAXP + u] : fu * rhom;                         // :540-543
+    const double Iv = a.simple_twohalo ? scs[HM_MAXP + v] : fv * rhom;
+    const double p2h = __dmul_rn(__dadd_rn(__dmul_rn(Iu, Iv), 0.), a.Pk_lin[(size_t)smp * a.nk + krow]);   // :524
+    double p1h = f1 * rhom;                                                                    // :532
+    if (u == v && a.discrete[u]) {                                                             // :484-491
+      if (a.correct_discrete && !a.subtract_shotnoise) p1h += scs[u];
+      else if (!a.correct_discrete && a.subtract_shotnoise) p1h -= scs[u];
+    }
+    if (a.k_trunc > 0.) {                                                                      // :494-495
+      const double q = a.k[krow] / a.k_trunc;
+      p1h *= 1. - exp(-(q * q));
+    }
+    double* o = a.out + ((size_t)b * S + s) * 3 * a.nk + krow;
+    o[0] = p2h;
+    o[a.nk] = p1h;
+    o[2 * (size_t)a.nk] = __dadd_rn(p2h, p1h);                                                 // :500-501
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -682,14 +733,17 @@ static int hm_launch_stream(hm_quad_args& a, cudaStream_t st) {
 
 template <int P>
 static int hm_launch_epilogue(const hm_epi_args& e, cudaStream_t st) {
-  const long long n = (long long)e.B * e.nk;
-  hm_epilogue_kernel<P><<<(int)((n + 127) / 128), 128, 0, st>>>(e);
+  constexpr int NW = P + P * (P + 1) / 2;
+  const int PG = (NW <= 20) ? 8 : 4;                   // part-groups per CTA; keeps shared memory under 48 KB
+  const int tiles = (e.nk + HM_EPI_ROWS - 1) / HM_EPI_ROWS;
+  const size_t smem = ((size_t)PG * NW * HM_EPI_ROWS + 2 * HM_MAXP) * sizeof(double);
+  hm_epilogue_kernel<P><<<e.B * tiles, PG * HM_EPI_ROWS, smem, st>>>(e);
   HM_LAUNCH_CHECK();
   return HM_OK;
 }
 
-extern "C" int hm_mass_quadrature(const hm_problem* pr, double* out_dev, const void* ws, size_t ws_bytes,
-                                  void* stream) {
+extern "C" int hm_mass_quadrature_stages(const hm_problem* pr, double* out_dev, const void* ws, size_t ws_bytes,
+                                         void* stream, int stages) {
   int rc = hm_check_device();
   if (rc) return rc;
   if ((rc = hm_validate(pr))) return rc;
@@ -698,6 +752,7 @@ extern "C" int hm_mass_quadrature(const hm_problem* pr, double* out_dev, const v
   if ((rc = hm_check_workspace("hm_mass_quadrature", L, ws, ws_bytes))) return rc;
   hm_quad_args a;
   a.nk = pr->nk; a.nM = pr->nM; a.nMp = L.nMp; a.F = pr->models_per_sample; a.B = (int)L.B; a.nslices = L.nslices;
+  a.nparts = L.nparts;
   bool sep = false, aligned = (pr->nM % 2 == 0);
   for (int p = 0; p < HM_MAXP; ++p) {
     const bool on = p < L.P;
@@ -711,7 +766,7 @@ extern "C" int hm_mass_quadrature(const hm_problem* pr, double* out_dev, const v
   a.partial = (double*)ws + L.partial_offset;
   hm_epi_args e;
   e.nk = pr->nk; e.B = (int)L.B; e.F = pr->models_per_sample; e.P = L.P; e.NW = L.NW; e.S = L.S;
-  e.nslices = L.nslices; e.nchunks = L.nchunks;
+  e.nparts = L.nparts; e.nchunks = L.nchunks;
   e.simple_twohalo = pr->simple_twohalo; e.subtract_shotnoise = pr->subtract_shotnoise;
   e.correct_discrete = pr->correct_discrete; e.k_trunc = pr->k_trunc; e.k = pr->k_dev; e.Pk_lin = pr->Pk_lin_dev;
   e.partial = a.partial; e.scal = (const double*)ws + L.scal_offset; e.cpart = (const double*)ws + L.cpart_offset;
@@ -720,9 +775,11 @@ extern "C" int hm_mass_quadrature(const hm_problem* pr, double* out_dev, const v
   cudaStream_t st = (cudaStream_t)stream;
 #define HM_CASE(PP, RR)                                                            \
   case PP:                                                                         \
-    rc = L.stream ? hm_launch_stream<PP, RR>(a, st) : hm_launch_fallback<PP, RR>(a, aligned, sep, st); \
-    if (rc) return rc;                                                             \
-    return hm_launch_epilogue<PP>(e, st);
+    if (stages & 1) {                                                              \
+      rc = L.stream ? hm_launch_stream<PP, RR>(a, st) : hm_launch_fallback<PP, RR>(a, aligned, sep, st); \
+      if (rc) return rc;                                                           \
+    }                                                                              \
+    return (stages & 2) ? hm_launch_epilogue<PP>(e, st) : HM_OK;
   switch (L.P) {
     HM_CASE(1, 8)
     HM_CASE(2, 4)
@@ -736,6 +793,11 @@ extern "C" int hm_mass_quadrature(const hm_problem* pr, double* out_dev, const v
 #undef HM_CASE
   hm_set_error("hm_mass_quadrature: unsupported tracer count %d", L.P);
   return HM_ERR_INVALID;
+}
+
+extern "C" int hm_mass_quadrature(const hm_problem* pr, double* out_dev, const void* ws, size_t ws_bytes,
+                                  void* stream) {
+  return hm_mass_quadrature_stages(pr, out_dev, ws, ws_bytes, stream, 3);
 }
 
 extern "C" int hm_power_spectrum(const hm_problem* pr, double* out_dev, double* lowmass_dev, void* ws,

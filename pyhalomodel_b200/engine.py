@@ -227,9 +227,10 @@ class PowerSpectrumPlan:
         check(lib().hm_halo_weights(C.byref(self.problem), _ptr(self.lowmass), _ptr(self.workspace),
                                     self.workspace_bytes, _stream()))
 
-    def quadrature(self):
-        check(lib().hm_mass_quadrature(C.byref(self.problem), _ptr(self.out), _ptr(self.workspace),
-                                       self.workspace_bytes, _stream()))
+    def quadrature(self, stages=3):
+        """stages: bit 0 = streaming kernel, bit 1 = epilogue kernel (both by default)."""
+        check(lib().hm_mass_quadrature_stages(C.byref(self.problem), _ptr(self.out), _ptr(self.workspace),
+                                              self.workspace_bytes, _stream(), int(stages)))
 
     def run(self):
         """Enqueue both stages on the current stream; returns (out [B,S,3,nk], A [B]) device tensors."""
