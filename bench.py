@@ -43,7 +43,7 @@ def parse():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--batch', type=int, default=16, help='models per GPU per step')
+    ap.add_argument('--batch', type=int, default=32, help='models per GPU per step')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-models', type=int, default=16, help='models in the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
@@ -190,12 +190,13 @@ def main():
     batch = workloads.build(B, NK, NM, TRACERS, seed=1234+rank, fiducial_first=(rank == 0))
     plan = batch.plan()
     S = plan.S
-    gathered = torch.empty((world,)+tuple(plan.out.shape), dtype=torch.float64, device='cuda') if world > 1 else None
+    from pyhalomodel_b200 import sweep
 
     def step():
         out, _ = plan.run()
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+        if world > 1:       # the one collective of the path: gather the spectra of every rank's models (NCCL)
+            return sweep.gather_spectra(out, world*B)
+        return out
 
     def barrier():
         if world > 1:
@@ -223,32 +224,32 @@ def main():
     ms_total = float(ms.item())
     value = world*B*S*K/(ms_total*1e-3)
 
-    # ---- roofline of the dominant kernel (mass quadrature alone), same stream, CUDA events ---------------------
+    # ---- roofline of the dominant kernel (the streaming mass-quadrature kernel alone), CUDA events on the
+    # launching stream; the weights and epilogue kernels are timed the same way for the step breakdown ----------
     reps = max(K, 20)
-    for _ in range(3):
-        plan.quadrature()
-    torch.cuda.synchronize()
-    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    q0.record()
-    for _ in range(reps):
-        plan.quadrature()
-    q1.record()
-    torch.cuda.synchronize()
-    quad_ms = q0.elapsed_time(q1)/reps
-    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0.record()
-    for _ in range(reps):
-        plan.weights()
-    w1.record()
-    torch.cuda.synchronize()
-    weights_ms = w0.elapsed_time(w1)/reps
+
+    def time_stage(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(reps):
+            fn()
+        a1.record()
+        torch.cuda.synchronize()
+        return a0.elapsed_time(a1)/reps
+
+    quad_ms = time_stage(lambda: plan.quadrature(1))
+    epi_ms = time_stage(lambda: plan.quadrature(2))
+    weights_ms = time_stage(plan.weights)
     clocks = sampler.summary(t0, t1)
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(peaks_path):
         peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'MEASURED_PEAKS.json hbm_gbs (burst copy)'
     else:
         peak, peak_src = 6650., 'fallback (B200_PROFILING.md)'
-    alg_bytes = plan.algorithmic_bytes()
+    alg_bytes = plan.stream_kernel_bytes()
     achieved = alg_bytes/(quad_ms*1e-3)/1e9
     traffic = None
     tpath = os.path.join(ROOT, 'profiles', 'quad_traffic.json')
@@ -256,9 +257,11 @@ def main():
         tj = json.load(open(tpath))
         if tj.get('batch') == B:
             traffic = tj.get('dram_bytes_per_launch')
-    roofline = dict(bound='hbm', kernel='hm_quad_stream_kernel<3,3> (+ hm_epilogue_kernel<3>, timed together)', achieved=achieved, peak=peak, unit='GB/s',
+    roofline = dict(bound='hbm', kernel='hm_quad_stream_kernel<3,3>', achieved=achieved, peak=peak, unit='GB/s',
                     frac=achieved/peak, traffic=traffic, algorithmic_bytes_per_launch=alg_bytes,
-                    kernel_ms=quad_ms, weights_kernel_ms=weights_ms, peak_source=peak_src)
+                    kernel_ms=quad_ms, epilogue_kernel_ms=epi_ms, weights_kernel_ms=weights_ms,
+                    step_algorithmic_bytes=plan.algorithmic_bytes(),
+                    step_achieved=plan.algorithmic_bytes()/(ms_total/K*1e-3)/1e9, peak_source=peak_src)
 
     # ---- end to end through the public API with host buffers --------------------------------------------------
     e2e = None

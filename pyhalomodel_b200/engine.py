@@ -238,6 +238,12 @@ class PowerSpectrumPlan:
                                       self.workspace_bytes, _stream()))
         return self.out, self.lowmass
 
+    def stream_kernel_bytes(self):
+        """Algorithmic bytes of the streaming quadrature kernel alone: every distinct grid once plus the weight
+        vectors of every model once (its partial-sum writes are an implementation artefact and not counted)."""
+        ngrids = sum(2 if t.mode == _lib.GRID_SEPARATE else 1 for t in self.tracers)
+        return 8*(self.G*ngrids*self.nk*self.nM + self.B*(self.P+self.S)*self.nM)
+
     def algorithmic_bytes(self):
         """Bytes the quadrature kernel must move per launch: every distinct grid once, the weight vectors once
         per model, P_lin once per sample, three output vectors per unique pair."""

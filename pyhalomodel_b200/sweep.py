@@ -1,0 +1,81 @@
+"""
+Batched sweeps over independent (cosmology, redshift, mass-function) models, sharded across the GPUs of one box.
+
+Every model of a sweep is independent (model.power_spectrum reads only its arguments, pyhalomodel.py:361-513), so
+the batch axis is partitioned contiguously across ranks -- one process per GPU, launched with torchrun -- and
+each rank builds and evaluates its own samples; nothing crosses the interconnect on the data path.  The only
+collective is the gather of the result spectra [B_local, S, 3, nk] (NCCL all-gather over NVLink; gloo in the
+CPU tests).  Shards may be uneven: they are padded to the largest shard for the collective and trimmed after.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items: int, world: int):
+    """Contiguous, balanced partition of range(n_items): the first n_items % world ranks get one extra item."""
+    base, extra = divmod(n_items, world)
+    bounds, lo = [], 0
+    for r in range(world):
+        hi = lo+base+(1 if r < extra else 0)
+        bounds.append((lo, hi))
+        lo = hi
+    return bounds
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    return shard_bounds(n_items, world)[rank]
+
+
+def gather_spectra(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
+    """All-gather per-rank results along dim 0 into global sample order.
+
+    local: [n_local, ...] on this rank, where n_local = len(shard_range(n_items, rank, world)).
+    Returns [n_items, ...] on every rank.  Works on CUDA tensors (nccl) and CPU tensors (gloo)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return local
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    bounds = shard_bounds(n_items, world)
+    lo, hi = bounds[rank]
+    if local.shape[0] != hi-lo:
+        raise ValueError('rank %d holds %d items, expected %d' % (rank, local.shape[0], hi-lo))
+    nmax = max(b-a for a, b in bounds)
+    send = local
+    if hi-lo < nmax:        # pad to the common shard size required by all_gather_into_tensor
+        pad = torch.zeros((nmax-(hi-lo),)+tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        send = torch.cat([local, pad], dim=0)
+    recv = torch.empty((world*nmax,)+tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+    if all(b-a == nmax for a, b in bounds):
+        return recv
+    return torch.cat([recv[r*nmax:r*nmax+(b-a)] for r, (a, b) in enumerate(bounds)], dim=0)
+
+
+class ShardedSweep:
+    """Owns this rank's shard of a sweep: `build(lo, hi)` must return an object with `.plan()` (e.g. a
+    workloads.Batch restricted to samples lo..hi-1).  run() evaluates the shard and returns the gathered
+    [n_samples*F, S, 3, nk] spectra on every rank."""
+
+    def __init__(self, n_samples: int, build, models_per_sample: int = 1, group=None):
+        self.n_samples, self.F, self.group = n_samples, models_per_sample, group
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.lo, self.hi = shard_range(n_samples, rank, world)
+        self.batch = build(self.lo, self.hi) if self.hi > self.lo else None
+        self.plan = self.batch.plan() if self.batch is not None else None
+
+    def run_local(self):
+        if self.plan is None:
+            return None
+        out, _ = self.plan.run()
+        return out
+
+    def run(self):
+        out = self.run_local()
+        if out is None:
+            raise RuntimeError('empty shard: more ranks than samples')
+        # models are sample-major, so gathering per-sample blocks keeps the global model order
+        S, nk = out.shape[1], out.shape[3]
+        per_sample = out.reshape(self.hi-self.lo, self.F, S, 3, nk)
+        return gather_spectra(per_sample, self.n_samples, self.group).reshape(self.n_samples*self.F, S, 3, nk)
