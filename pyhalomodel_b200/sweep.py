@@ -52,6 +52,46 @@ def gather_spectra(local: torch.Tensor, n_items: int, group=None) -> torch.Tenso
     return torch.cat([recv[r*nmax:r*nmax+(b-a)] for r, (a, b) in enumerate(bounds)], dim=0)
 
 
+class OverlappedGather:
+    """Gather equal-sized per-rank result blocks on a side stream so the collective of step n overlaps the
+    kernels of step n+1 (the spectra are tiny next to the grids: the cost to hide is NCCL launch latency).
+
+    submit(out) snapshots `out` into one of two staging buffers on the compute stream and enqueues the all-gather
+    on the communication stream; `latest()` synchronises and returns the most recent gathered tensor."""
+
+    def __init__(self, like: torch.Tensor, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.comm = torch.cuda.Stream(device=like.device)
+        self.stage = [torch.empty_like(like) for _ in range(2)]
+        self.recv = [torch.empty((self.world*like.shape[0],)+tuple(like.shape[1:]), dtype=like.dtype,
+                                 device=like.device) for _ in range(2)]
+        self.done = [None, None]
+        self.n = 0
+
+    def submit(self, out: torch.Tensor):
+        i = self.n & 1
+        compute = torch.cuda.current_stream(out.device)
+        if self.done[i] is not None:
+            compute.wait_event(self.done[i])          # the gather that last used this slot has finished
+        self.stage[i].copy_(out, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(compute)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(ready)
+            dist.all_gather_into_tensor(self.recv[i], self.stage[i], group=self.group)
+            self.done[i] = torch.cuda.Event()
+            self.done[i].record(self.comm)
+        self.n += 1
+
+    def latest(self):
+        if self.n == 0:
+            return None
+        i = (self.n-1) & 1
+        torch.cuda.current_stream().wait_event(self.done[i])
+        return self.recv[i]
+
+
 class ShardedSweep:
     """Owns this rank's shard of a sweep: `build(lo, hi)` must return an object with `.plan()` (e.g. a
     workloads.Batch restricted to samples lo..hi-1).  run() evaluates the shard and returns the gathered
