@@ -140,6 +140,30 @@ int hm_mass_quadrature(const hm_problem* prob, double* out_dev, const void* work
 int hm_mass_quadrature_stages(const hm_problem* prob, double* out_dev, const void* workspace_dev,
                               size_t workspace_bytes, void* stream, int stages);
 
+/* ---- many tracers: the one-halo cross terms as a per-wavenumber Gram contraction on the FP64 tensor cores ----------
+ * Same semantics and output layout as hm_power_spectrum for 2..HM_GRAM_MAX_TRACERS single-grid tracers
+ * (grid_mode HM_GRID_UK or HM_GRID_WK).  `tracers` is a HOST array of n_tracers descriptors whose pointer fields
+ * are device pointers.  Replaces the P(P+1)/2 x nk Python iterations of pyhalomodel.py:433-507. */
+#define HM_GRAM_MAX_TRACERS 64
+typedef struct hm_gram_problem {
+  int32_t nk, nM;
+  int32_t n_tracers;
+  int32_t n_samples;
+  int32_t models_per_sample;
+  int32_t simple_twohalo, subtract_shotnoise, correct_discrete;
+  double k_trunc;
+  const double* k_dev;
+  const double* M_dev;
+  const double* sigma_dev;
+  const double* Pk_lin_dev;
+  const hm_model_desc* models_dev;
+  hm_model_desc model_host;
+  const hm_tracer* tracers;      /* host array [n_tracers] */
+} hm_gram_problem;
+size_t hm_gram_workspace(const hm_gram_problem* prob);
+int hm_gram_power_spectrum(const hm_gram_problem* prob, double* out_dev, double* lowmass_dev,
+                           void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* ---- Fourier profiles ------------------------------------------------------------------------------------
  * Si(x), Ci(x) element-wise (scipy.special.sici as used at pyhalomodel.py:1033-1035,1044-1049). */
 int hm_sici(const double* x_dev, int64_t n, double* si_dev, double* ci_dev, void* stream);

@@ -32,6 +32,17 @@ class Problem(C.Structure):
                 ('models_dev', C.c_void_p), ('model_host', ModelDesc), ('tracers', Tracer*HM_MAX_TRACERS)]
 
 
+class GramProblem(C.Structure):
+    _fields_ = [('nk', C.c_int32), ('nM', C.c_int32), ('n_tracers', C.c_int32), ('n_samples', C.c_int32),
+                ('models_per_sample', C.c_int32), ('simple_twohalo', C.c_int32), ('subtract_shotnoise', C.c_int32),
+                ('correct_discrete', C.c_int32), ('k_trunc', C.c_double), ('k_dev', C.c_void_p),
+                ('M_dev', C.c_void_p), ('sigma_dev', C.c_void_p), ('Pk_lin_dev', C.c_void_p),
+                ('models_dev', C.c_void_p), ('model_host', ModelDesc), ('tracers', C.POINTER(Tracer))]
+
+
+HM_GRAM_MAX_TRACERS = 64
+
+
 class HaloB200Error(RuntimeError):
     pass
 
@@ -52,6 +63,9 @@ _SIGNATURES = {
     'hm_mass_quadrature': (C.c_int, [C.POINTER(Problem), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'hm_mass_quadrature_stages': (C.c_int, [C.POINTER(Problem), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
                                             C.c_int]),
+    'hm_gram_workspace': (C.c_size_t, [C.POINTER(GramProblem)]),
+    'hm_gram_power_spectrum': (C.c_int, [C.POINTER(GramProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                         C.c_void_p]),
     'hm_sici': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     'hm_window_nfw': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_void_p]),

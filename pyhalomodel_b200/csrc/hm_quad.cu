@@ -20,31 +20,8 @@
 //
 // Algorithmic bytes per launch of the streaming kernel: 8*(G*P*nk*nM + B*(P+S)*nM + B*nslices*(P+S)*nk).
 #include "hm_common.cuh"
-#include "hm_tables.h"
 
 #define HM_MAXP HM_MAX_TRACERS
-
-__constant__ double c_gl_x[16] = HM_GL16_X_INIT;
-__constant__ double c_gl_w[16] = HM_GL16_W_INIT;
-
-// ---------------------------------------------------------------------------------------------------------------
-// Low-mass correction: A = 1 - int_{nu0}^{inf} g b dnu                                   pyhalomodel.py:413-414
-// Composite 16-point Gauss-Legendre on 10 geometrically growing panels covering [nu0, nu0+40]; the integrand is
-// < 1e-300 beyond.  Agrees with scipy.integrate.quad to ~1e-14 absolute for all families (tests/).
-// Thread t in [0,160) owns one node; returns that node's contribution (0 for other threads).
-// ---------------------------------------------------------------------------------------------------------------
-#define HM_GL_PANELS 10
-#define HM_GL_NODES (16 * HM_GL_PANELS)
-__device__ __forceinline__ double hm_lowmass_node(const hm_model_desc& d, double nu0, int t) {
-  if (t >= HM_GL_NODES) return 0.;
-  const int panel = t >> 4, node = t & 15;
-  const double unit = 40. / (double)((1 << HM_GL_PANELS) - 1);
-  const double a = nu0 + unit * (double)((1 << panel) - 1);
-  const double b = nu0 + unit * (double)((1 << (panel + 1)) - 1);
-  const double half = 0.5 * (b - a);
-  const double x = 0.5 * (a + b) + half * c_gl_x[node];
-  return half * c_gl_w[node] * hm_g_nu(d, x) * hm_b_nu(d, x);
-}
 
 __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, const double* __restrict__ nu0,
                                   int B, double* __restrict__ A) {
@@ -227,21 +204,6 @@ struct hm_quad_args {
   const double* weights;
   double* partial;                   // [B][nparts][nk][NW]
 };
-
-// v[0..32) per lane  ->  lane l holds the warp-wide sum of v[l]  (31 shuffles instead of 160).
-__device__ __forceinline__ double hm_warp_transpose_sum32(double (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const double send = upper ? v[i] : v[i + off];
-      const double keep = upper ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
 
 // acc[r*NW + i] += w_i * (grid values the weight vector i multiplies), for one mass column.
 template <int P, int R, bool SEP>

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import HaloB200Error, ModelDesc, Problem, check, lib
+from ._lib import GramProblem, HaloB200Error, ModelDesc, Problem, check, lib
 
 F64 = torch.float64
 
@@ -250,3 +250,87 @@ class PowerSpectrumPlan:
         ngrids = sum(2 if t.mode == _lib.GRID_SEPARATE else 1 for t in self.tracers)
         return 8*(self.G*ngrids*self.nk*self.nM + self.B*(self.P+self.S)*self.nM + self.G*self.nk
                   + self.B*3*self.S*self.nk)
+
+
+class GramPlan:
+    """Many-tracer counterpart of PowerSpectrumPlan (2..64 single-grid tracers): the cross one-halo terms run as a
+    per-wavenumber Gram contraction on the FP64 tensor cores (csrc/hm_gram.cu).  Same output layout."""
+
+    def __init__(self, k, Pk_lin, M, sigma, tracers, models, models_per_sample=1, simple_twohalo=False,
+                 subtract_shotnoise=True, correct_discrete=True, k_trunc=None):
+        self.k, self.M = to_dev(k), to_dev(M)
+        nk, nM = self.k.shape[0], self.M.shape[0]
+        self.Pk_lin, self.sigma = to_dev(Pk_lin), to_dev(sigma)
+        if self.Pk_lin.dim() == 1:
+            self.Pk_lin = self.Pk_lin[None, :]
+        if self.sigma.dim() == 1:
+            self.sigma = self.sigma[None, :]
+        G = self.sigma.shape[0]
+        P = len(tracers)
+        if not 2 <= P <= _lib.HM_GRAM_MAX_TRACERS:
+            raise ValueError('the Gram path takes between 2 and %d tracers' % _lib.HM_GRAM_MAX_TRACERS)
+        B = G*models_per_sample
+        self.tracers = tracers
+        self.G, self.B, self.P, self.S, self.nk, self.nM = G, B, P, P*(P+1)//2, nk, nM
+        self.keep = []
+        pr = GramProblem()
+        pr.nk, pr.nM, pr.n_tracers, pr.n_samples, pr.models_per_sample = nk, nM, P, G, models_per_sample
+        pr.simple_twohalo, pr.subtract_shotnoise = int(bool(simple_twohalo)), int(bool(subtract_shotnoise))
+        pr.correct_discrete = int(bool(correct_discrete))
+        pr.k_trunc = float(k_trunc) if k_trunc is not None else 0.
+        pr.k_dev, pr.M_dev = self.k.data_ptr(), self.M.data_ptr()
+        pr.sigma_dev, pr.Pk_lin_dev = self.sigma.data_ptr(), self.Pk_lin.data_ptr()
+        if isinstance(models, torch.Tensor):
+            self.models_dev = models
+            pr.models_dev = models.data_ptr()
+        elif len(models) == 1 and B == 1:
+            self.models_dev, pr.models_dev, pr.model_host = None, None, models[0]
+        else:
+            self.models_dev = pack_models(models)
+            pr.models_dev = self.models_dev.data_ptr()
+        self.ctracers = (_lib.Tracer*P)()
+        for p, t in enumerate(tracers):
+            if t.mode not in (_lib.GRID_UK, _lib.GRID_WK):
+                raise ValueError('tracer %d: the Gram path needs profiles built by profile.Fourier' % p)
+            grid = to_dev(t.grid)
+            grid = grid if grid.dim() == 3 else grid[None]
+            if tuple(grid.shape) != (G, nk, nM):
+                raise ValueError('tracer %d: grid must be [G, nk, nM]' % p)
+            ct = self.ctracers[p]
+            ct.grid_dev = grid.data_ptr()
+            self.keep.append(grid)
+            if t.amplitude is not None:
+                amp = to_dev(t.amplitude).reshape(G, nM)
+                ct.amplitude_dev = amp.data_ptr()
+                self.keep.append(amp)
+            if t.variance is not None:
+                var = to_dev(t.variance).reshape(G, nM)
+                ct.variance_dev = var.data_ptr()
+                self.keep.append(var)
+            norm = t.normalisation
+            norm = to_dev(np.full(B, float(norm))) if np.isscalar(norm) else to_dev(norm).reshape(B)
+            ct.normalisation_dev = norm.data_ptr()
+            self.keep.append(norm)
+            ct.grid_mode, ct.mass_tracer, ct.discrete_tracer = int(t.mode), int(t.mass_tracer), int(t.discrete_tracer)
+        pr.tracers = self.ctracers
+        self.problem = pr
+        nbytes = lib().hm_gram_workspace(C.byref(pr))
+        dev = self.k.device
+        self.workspace = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        self.workspace_bytes = nbytes
+        self.out = torch.empty((B, self.S, 3, nk), dtype=F64, device=dev)
+        self.lowmass = torch.empty(B, dtype=F64, device=dev)
+
+    def run(self):
+        check(lib().hm_gram_power_spectrum(C.byref(self.problem), _ptr(self.out), _ptr(self.lowmass),
+                                           _ptr(self.workspace), self.workspace_bytes, _stream()))
+        return self.out, self.lowmass
+
+    def algorithmic_bytes(self):
+        """Every grid once, four per-(tracer, mass) vectors once per model, three output vectors per pair."""
+        return 8*(self.G*self.P*self.nk*self.nM + self.B*(2+2*self.P)*self.nM + self.G*self.nk
+                  + self.B*3*self.S*self.nk)
+
+    def gram_flops(self):
+        """Useful flops of the cross one-halo contraction: 2 per (unique pair incl. diagonal blocks, mass, k)."""
+        return 2.*self.B*self.S*self.nM*self.nk

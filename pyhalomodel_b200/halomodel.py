@@ -248,15 +248,15 @@ class model():
             raise NotImplementedError('beta_NL (pyhalomodel.py:546-571) is a "next" row of the B200 build')
         on_dev = _wants_device(k, Pk_lin, M, sigmaM)
         names = list(profiles.keys())
-        if len(names) > _lib.HM_MAX_TRACERS:
-            from . import manytracer
-            return manytracer.power_spectrum(self, k, Pk_lin, M, sigmaM, profiles, simple_twohalo=simple_twohalo,
-                                             subtract_shotnoise=subtract_shotnoise, correct_discrete=correct_discrete,
-                                             k_trunc=k_trunc, on_device=on_dev)
         tracers = [prof._tracer() for prof in profiles.values()]
-        plan = engine.PowerSpectrumPlan(k, Pk_lin, M, sigmaM, tracers, [self.descriptor()],
-                                        simple_twohalo=simple_twohalo, subtract_shotnoise=subtract_shotnoise,
-                                        correct_discrete=correct_discrete, k_trunc=k_trunc)
+        flags = dict(simple_twohalo=simple_twohalo, subtract_shotnoise=subtract_shotnoise,
+                     correct_discrete=correct_discrete, k_trunc=k_trunc)
+        if len(names) > _lib.HM_MAX_TRACERS:    # many tracers: Gram contraction on the FP64 tensor cores
+            if len(names) > _lib.HM_GRAM_MAX_TRACERS:
+                raise NotImplementedError('more than %d tracers per call' % _lib.HM_GRAM_MAX_TRACERS)
+            plan = engine.GramPlan(k, Pk_lin, M, sigmaM, tracers, [self.descriptor()], **flags)
+        else:
+            plan = engine.PowerSpectrumPlan(k, Pk_lin, M, sigmaM, tracers, [self.descriptor()], **flags)
         out, lowmass = plan.run()
         if on_dev:
             res, A = out[0], float(lowmass[0].item())

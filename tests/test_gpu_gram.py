@@ -1,0 +1,112 @@
+"""GPU (-m gpu): the many-tracer path (more than 8 tracers -> Gram contraction on the FP64 tensor cores, BASELINE
+config 4) against the oracle at sizes it finishes in seconds, and at config-4 size against the <=8-tracer
+streaming path on tracer subsets plus size-independent properties."""
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_spectra_close
+from oracle import halo_oracle as orc
+from pyhalomodel_b200 import synthetic as syn
+from test_gpu_parity import _synthetic_case
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+@pytest.fixture(scope='module')
+def halo():
+    assert torch.cuda.is_available()
+    import pyhalomodel_b200.pyhalomodel as h
+    return h
+
+
+def _tracers(api, model, g, hods, with_matter, with_pressure, nfw):
+    """Build the same dictionary of profiles with the oracle API or the B200 API."""
+    is_orc = api is orc
+    k, M, sig = g['k'], g['M'], g['sigmaM']
+    if is_orc:
+        rv, c = orc.virial_radius(M, model.Om_m, model.Dv), orc.concentration(M, model.z, halo_definition='Mvir')
+        Ug = orc.window_nfw(k, rv, c) if nfw else orc.window_isothermal(k, rv)
+        Fourier, hod_mean, hod_var, avg = orc.Profile.Fourier, orc.hod_mean, orc.hod_variance, \
+            (lambda N: orc.average(model, M, sig, N))
+        matter = lambda: orc.matter_profile(k, M, rv, c, model.Om_m)
+    else:
+        rv, c = model.virial_radius(M), api.concentration(M, model.z, halo_definition='Mvir')
+        Ug = api.window_function(k, rv, c, profile='NFW') if nfw else api.window_function(k, rv, profile='isothermal')
+        Fourier, hod_mean, hod_var, avg = api.profile.Fourier, api.HOD_mean, api.HOD_variance, \
+            (lambda N: model.average(M, sig, N))
+        matter = lambda: api.matter_profile(k, M, rv, c, model.Om_m)
+    profs = {}
+    if with_matter:
+        profs['m'] = matter()
+    for i, hod in enumerate(hods):
+        Nc, Ns = hod_mean(M, **hod)
+        Vc, Vs, _ = hod_var(Nc, Ns)
+        profs['g%d' % i] = Fourier(k, M, Ug, amplitude=Nc+Ns, normalisation=avg(Nc+Ns), variance=Vc+Vs,
+                                   discrete_tracer=True)
+    if with_pressure:
+        profs['p'] = Fourier(k, M, syn.pressure_profile(k, M, rv))
+    return profs
+
+
+@pytest.mark.parametrize('ntr,nk,nM,name', [(9, 13, 130, orc.TINKER10), (12, 10, 96, orc.ST99), (17, 7, 64, orc.SMT01),
+                                            (24, 5, 200, orc.PS74), (33, 4, 66, orc.DESPALI16)])
+def test_gram_path_vs_oracle(halo, ntr, nk, nM, name):
+    g = _synthetic_case(nk, nM, z=0.4)
+    rng = np.random.default_rng(ntr)
+    hods = [syn.draw_hod(rng) for _ in range(ntr-2)]
+    om = orc.make_model(g['z'], g['Om_m'], name=name, Dv=g['Dv'], dc=g['dc'])
+    hmod = halo.model(g['z'], g['Om_m'], name=name, Dv=g['Dv'], dc=g['dc'])
+    op = _tracers(orc, om, g, hods, True, True, nfw=False)
+    gp = _tracers(halo, hmod, g, hods, True, True, nfw=False)
+    for kw in ({}, dict(subtract_shotnoise=False, k_trunc=0.3), dict(simple_twohalo=True, correct_discrete=False)):
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            want = orc.power_spectrum(om, g['k'], g['Pk_lin'], g['M'], g['sigmaM'], op, **kw)
+            got = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], gp, **kw)
+        assert list(got[0].keys()) == list(want[0].keys())
+        for t in range(3):
+            for key in want[t]:
+                assert_spectra_close(got[t][key], want[t][key], rtol=RTOL, what='%s term %d %s' % (key, t, kw),
+                                     zero_scale=np.max(np.abs(want[2][key])))
+        assert got[1]['g0-m'] is got[1]['m-g0']
+
+
+def test_gram_64_tracers_vs_oracle_small_grid(halo):
+    """All 2080 unique pairs of 64 HOD tracers (config 4's tracer count) on a grid the oracle finishes in seconds."""
+    g = _synthetic_case(6, 128, z=0.2)
+    rng = np.random.default_rng(64)
+    hods = [syn.draw_hod(rng) for _ in range(64)]
+    om = orc.make_model(g['z'], g['Om_m'], Dv=g['Dv'], dc=g['dc'])
+    hmod = halo.model(g['z'], g['Om_m'], Dv=g['Dv'], dc=g['dc'])
+    want = orc.power_spectrum(om, g['k'], g['Pk_lin'], g['M'], g['sigmaM'], _tracers(orc, om, g, hods, False, False, True))
+    got = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], _tracers(halo, hmod, g, hods, False, False, True))
+    assert len(got[0]) == 64*64 and len({id(v) for v in got[2].values()}) == 2080
+    for t in range(3):
+        for key in want[t]:
+            assert_spectra_close(got[t][key], want[t][key], rtol=RTOL, what='%s term %d' % (key, t))
+
+
+def test_gram_config4_size_vs_streaming_path(halo):
+    """Config 4 at full size (64 HOD tracers, NFW, 256 k x 2048 M): every pair among 8-tracer subsets must agree
+    with the <=8-tracer streaming-quadrature path (itself oracle-checked), and the run is bitwise reproducible."""
+    g = _synthetic_case(256, 2048, z=0.)
+    rng = np.random.default_rng(4)
+    hods = [syn.draw_hod(rng) for _ in range(64)]
+    hmod = halo.model(g['z'], g['Om_m'], Dv=g['Dv'], dc=g['dc'])
+    profs = _tracers(halo, hmod, g, hods, False, False, True)
+    got = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs)
+    again = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs)
+    for key in ('g0-g0', 'g3-g60', 'g63-g63', 'g17-g18'):
+        for t in range(3):
+            assert np.array_equal(got[t][key], again[t][key])
+    for subset in ([0, 1, 2, 3, 4, 5, 6, 7], [0, 9, 18, 27, 36, 45, 54, 63], [56, 57, 58, 59, 60, 61, 62, 63]):
+        names = ['g%d' % i for i in subset]
+        ref = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], {n: profs[n] for n in names})
+        for t in range(3):
+            for u in names:
+                for v in names:
+                    assert_spectra_close(got[t][u+'-'+v], ref[t][u+'-'+v], rtol=1e-12, what='%s-%s term %d' % (u, v, t))
