@@ -21,7 +21,8 @@
 
 #define HM_GMAXP HM_GRAM_MAX_TRACERS
 #define HM_GMCH 64                 // masses per chunk
-#define HM_GLD (HM_GMCH + 4)       // padded row stride of the W tile (bank-conflict-free DMMA fragment loads)
+#define HM_GLD (HM_GMCH + 8)       // padded row stride of the W tile: 576 B = 64 mod 128, so the 16-byte DMMA
+                                   // fragment loads of a quarter warp (2 rows x 4 lanes) hit all 32 banks once
 #define HM_GNSCAL 4
 #define HM_GWARPS 8
 
@@ -98,7 +99,8 @@ __global__ void __launch_bounds__(256) hm_gram_weights_kernel(const hm_gram_warg
   const int m = chunk * 256 + tid;
   if (m >= a.nMp) return;
   if (m >= a.nM) {
-    for (int i = 0; i < 2 + 2 * a.P; ++i) gw[(size_t)i * a.nMp + m] = 0.;
+    gw[m] = 0.;
+    gw[(size_t)a.nMp + m] = 0.;
     return;
   }
   const double nu = d.dc / sig[m];
@@ -112,18 +114,28 @@ __global__ void __launch_bounds__(256) hm_gram_weights_kernel(const hm_gram_warg
   const double w2 = tw * ((bias * g) / Mm);    // two-halo weight (:539)
   gw[m] = w1;
   gw[(size_t)a.nMp + m] = w2;
-  for (int p = 0; p < a.P; ++p) {
+}
+
+// per-(tracer, mass) factors: c_p (W = c_p * grid) and d_p (auto one-halo weight); grid = (mass chunk, tracer, model)
+__global__ void __launch_bounds__(256) hm_gram_tracer_kernel(const hm_gram_wargs a) {
+  const int p = blockIdx.y, b = blockIdx.z, s = b / a.F;
+  const int m = blockIdx.x * 256 + threadIdx.x;
+  if (m >= a.nMp) return;
+  double* gw = a.gw + (size_t)b * a.gw_stride;
+  double c = 0., dw = 0.;
+  if (m < a.nM) {
     const size_t aoff = a.amp_stride_is_grid[p] ? (size_t)s * a.grid_sample_stride : (size_t)s * a.nM;
     const double amp = a.amplitude[p][aoff + m];
     const double norm = a.norm[p][b];
     double fac = (a.correct_discrete && a.discrete[p]) ? __dmul_rn(amp, __dadd_rn(amp, -1.)) : __dmul_rn(amp, amp);
     if (a.variance[p]) fac = __dadd_rn(fac, a.variance[p][(size_t)s * a.nM + m]);   // :466-473
-    double c, uS;
+    double uS;
     if (a.mode[p] == HM_GRID_UK) { c = amp / norm; uS = 1. / norm; }
     else { c = 1.; uS = 1. / (amp * norm); }                                        // HM_GRID_WK
-    gw[(size_t)(2 + p) * a.nMp + m] = c;
-    gw[(size_t)(2 + a.P + p) * a.nMp + m] = __dmul_rn(__dmul_rn(w1, fac), uS * uS);  // d_p (:475-477)
+    dw = __dmul_rn(__dmul_rn(gw[m], fac), uS * uS);                                 // d_p = w1 fac uS^2 (:475-477)
   }
+  gw[(size_t)(2 + p) * a.nMp + m] = c;
+  gw[(size_t)(2 + a.P + p) * a.nMp + m] = dw;
 }
 
 // shot noise P_SN = rhom trapz((amp/norm^2) g/M) (:423-426) and the simple two-halo integral (:442-446)
@@ -153,6 +165,7 @@ __global__ void __launch_bounds__(256) hm_gram_scalars_kernel(const hm_gram_warg
 // ---------------------------------------------------------------------------------------------------------------
 struct hm_gram_args {
   int nk, nM, nMp, P, NB, PT, NW, F, ntiles, nparts, MP;
+  long long nitems;
   size_t gw_stride;
   const double* grid[HM_GMAXP];
   const double* gw;
@@ -164,151 +177,263 @@ __device__ __forceinline__ void hm_dmma884(double& c0, double& c1, double a, dou
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-#define HM_GMAXFRAG 5     // ceil(36 / 8): upper-triangle 8x8 fragments per warp at P = 64
+
+// One mass chunk of one work item, prefetched into registers one chunk ahead of the DMMA phase.
+template <int RK>
+struct hm_gram_chunk {
+  double2 x[8][RK], cc[8], dd[8], w1v, w2v;
+};
+
+struct hm_gram_cursor {      // (item, chunk) iterator over the contiguous item range of a persistent CTA
+  int item, ch, nch_item;
+  int b, smp, row0, mbeg, mend;
+};
 
 template <int RK>
-__global__ void __launch_bounds__(32 * HM_GWARPS, 2) hm_gram_kernel(const hm_gram_args a) {
-  extern __shared__ __align__(16) double gsm[];
-  double* Ys = gsm;                                     // [RK][PT][HM_GLD]   W tile of the current mass chunk
-  double* w1s = Ys + (size_t)RK * a.PT * HM_GLD;        // [HM_GMCH]
-  double* ssum = w1s + HM_GMCH;                         // [RK][2][PT]        two-halo and auto one-halo sums
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int P = a.P, PT = a.PT, NB = a.NB;
+__device__ __forceinline__ void hm_gram_decode(hm_gram_cursor& c, const hm_gram_args& a) {
+  int it = c.item;
+  const int part = it % a.nparts; it /= a.nparts;
+  const int tile = it % a.ntiles;
+  c.b = it / a.ntiles;
+  c.smp = c.b / a.F;
+  c.row0 = tile * RK;
+  c.mbeg = part * a.MP;
+  c.mend = (c.mbeg + a.MP < a.nM) ? c.mbeg + a.MP : a.nM;
+  c.nch_item = (c.mend - c.mbeg + HM_GMCH - 1) / HM_GMCH;
+}
 
-  // item = (model, tile of RK wavenumbers, mass part)
-  int item = blockIdx.x;
-  const int part = item % a.nparts; item /= a.nparts;
-  const int tile = item % a.ntiles;
-  const int b = item / a.ntiles;
-  const int smp = b / a.F;
-  const int row0 = tile * RK;
-  const int mbeg = part * a.MP;
-  const int mend = (mbeg + a.MP < a.nM) ? mbeg + a.MP : a.nM;
-  const double* __restrict__ gw = a.gw + (size_t)b * a.gw_stride;
-
-  // my share of the upper-triangle fragments (i <= j), contiguous in row-major order so that A is reused
-  const int nfrag = NB * (NB + 1) / 2;
-  const int per = (nfrag + HM_GWARPS - 1) / HM_GWARPS;
-  int fi[HM_GMAXFRAG], fj[HM_GMAXFRAG], nmine = 0;
-  {
-    int f = 0;
-    for (int i = 0; i < NB; ++i)
-      for (int j = i; j < NB; ++j, ++f)
-        if (f >= warp * per && f < (warp + 1) * per && nmine < HM_GMAXFRAG) {
-#pragma unroll
-          for (int t = 0; t < HM_GMAXFRAG; ++t)
-            if (t == nmine) { fi[t] = i; fj[t] = j; }
-          ++nmine;
-        }
-  }
-  double acc[RK][HM_GMAXFRAG][2];
-#pragma unroll
-  for (int r = 0; r < RK; ++r)
-#pragma unroll
-    for (int t = 0; t < HM_GMAXFRAG; ++t) acc[r][t][0] = acc[r][t][1] = 0.;
-  for (int i = tid; i < RK * 2 * PT; i += blockDim.x) ssum[i] = 0.;
-
+template <int RK, int NBT>
+__device__ __forceinline__ void hm_gram_load(hm_gram_chunk<RK>& q, const hm_gram_cursor& c, const hm_gram_args& a,
+                                             int warp, int lane) {
+  const int m = c.mbeg + c.ch * HM_GMCH + 2 * lane;
+  const bool in = m < c.mend;                  // nM and MP are even: a lane's two masses are in or out together
+  const double* __restrict__ gw = a.gw + (size_t)c.b * a.gw_stride;
+  const double2 zero = make_double2(0., 0.);
+  q.w1v = in ? *reinterpret_cast<const double2*>(gw + m) : zero;
+  q.w2v = in ? *reinterpret_cast<const double2*>(gw + (size_t)a.nMp + m) : zero;
   size_t rowoff[RK];
 #pragma unroll
   for (int r = 0; r < RK; ++r) {
-    const int row = (row0 + r < a.nk) ? row0 + r : a.nk - 1;     // clamp: duplicates are never written
-    rowoff[r] = ((size_t)smp * a.nk + row) * (size_t)a.nM;
+    const int row = (c.row0 + r < a.nk) ? c.row0 + r : a.nk - 1;     // clamp: duplicates are never written
+    rowoff[r] = ((size_t)c.smp * a.nk + row) * (size_t)a.nM + m;
+  }
+#pragma unroll
+  for (int t = 0; t < NBT; ++t) {
+    const int p = warp + 8 * t;                // warp w owns tracers w, w+8, ...
+    const bool on = in && p < a.P;
+    q.cc[t] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + p) * a.nMp + m) : zero;
+    q.dd[t] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + a.P + p) * a.nMp + m) : zero;
+#pragma unroll
+    for (int r = 0; r < RK; ++r) q.x[t][r] = on ? hm_ldg_stream2(a.grid[p] + rowoff[r]) : zero;
+  }
+}
+
+// ---- DMMA over the fragments one warp owns -------------------------------------------------------------------
+// Fragment ownership (8x8 blocks of the upper triangle of the NBT x NBT block grid): warp pair WQ = warp/2 owns
+// block rows I1 = WQ and I2 = NBT-1-WQ (together NBT+1 fragments) and, within the pair, warp E = warp%2 takes
+// the block columns j = 2jj+E.  Everything is a template parameter, so DMMAs are unconditional, accumulators
+// are statically indexed registers and the balance is 4-5 fragments per warp at NBT = 8.
+template <int NBT, int WQ, int E>
+struct hm_gram_frag {
+  static constexpr int I1 = WQ, I2 = NBT - 1 - WQ;
+  static constexpr bool ROW1 = I1 <= I2, ROW2 = I1 < I2;
+  __host__ __device__ static constexpr bool v1(int jj) { return ROW1 && (2 * jj + E) >= I1 && (2 * jj + E) < NBT; }
+  __host__ __device__ static constexpr bool v2(int jj) { return ROW2 && (2 * jj + E) >= I2 && (2 * jj + E) < NBT; }
+};
+
+template <int RK, int NBT, int WQ, int E, int JJ, int HALF>
+__device__ __forceinline__ void hm_gram_mma_jj(double (&acc)[RK][2][4][2], int r, const double2& a1, const double2& a2,
+                                               const double2& bb) {
+  using F = hm_gram_frag<NBT, WQ, E>;
+  if constexpr (F::v1(JJ)) hm_dmma884(acc[r][0][JJ][0], acc[r][0][JJ][1], HALF ? a1.y : a1.x, HALF ? bb.y : bb.x);
+  if constexpr (F::v2(JJ)) hm_dmma884(acc[r][1][JJ][0], acc[r][1][JJ][1], HALF ? a2.y : a2.x, HALF ? bb.y : bb.x);
+}
+
+// C[u,v] += sum_m (w1 W_u) W_v over one staged 64-mass tile.  Two k4-steps per 16-byte fragment load: within an
+// 8-mass block step 0 takes masses {0,2,4,6} and step 1 {1,3,5,7} (any assignment works as long as A, B and w1
+// agree: the sum over masses is order-free).
+template <int RK, int NBT, int WQ, int E>
+__device__ __forceinline__ void hm_gram_mma(double (&acc)[RK][2][4][2], const double* __restrict__ Yt,
+                                            const double* __restrict__ w1t, int fr, int fk) {
+  using F = hm_gram_frag<NBT, WQ, E>;
+  constexpr int PT = 8 * NBT;
+  if constexpr (!F::ROW1) return;
+  const double* Yb = Yt + 2 * fk + (size_t)fr * HM_GLD;
+  const double* w1b = w1t + 2 * fk;
+#pragma unroll 2
+  for (int blk = 0; blk < HM_GMCH / 8; ++blk) {
+    const double2 w1p = *reinterpret_cast<const double2*>(w1b + 8 * blk);
+#pragma unroll
+    for (int r = 0; r < RK; ++r) {
+      const double* Yr = Yb + (size_t)r * PT * HM_GLD + 8 * blk;
+      double2 a1 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * F::I1) * HM_GLD);
+      double2 a2 = make_double2(0., 0.);
+      a1.x *= w1p.x; a1.y *= w1p.y;
+      if constexpr (F::ROW2) {
+        a2 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * F::I2) * HM_GLD);
+        a2.x *= w1p.x; a2.y *= w1p.y;
+      }
+      double2 b0 = make_double2(0., 0.), b1 = b0, b2 = b0, b3 = b0;
+      if constexpr (F::v1(0) || F::v2(0)) b0 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * (0 + E)) * HM_GLD);
+      if constexpr (F::v1(1) || F::v2(1)) b1 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * (2 + E)) * HM_GLD);
+      if constexpr (F::v1(2) || F::v2(2)) b2 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * (4 + E)) * HM_GLD);
+      if constexpr (F::v1(3) || F::v2(3)) b3 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * (6 + E)) * HM_GLD);
+      hm_gram_mma_jj<RK, NBT, WQ, E, 0, 0>(acc, r, a1, a2, b0);
+      hm_gram_mma_jj<RK, NBT, WQ, E, 1, 0>(acc, r, a1, a2, b1);
+      hm_gram_mma_jj<RK, NBT, WQ, E, 2, 0>(acc, r, a1, a2, b2);
+      hm_gram_mma_jj<RK, NBT, WQ, E, 3, 0>(acc, r, a1, a2, b3);
+      hm_gram_mma_jj<RK, NBT, WQ, E, 0, 1>(acc, r, a1, a2, b0);
+      hm_gram_mma_jj<RK, NBT, WQ, E, 1, 1>(acc, r, a1, a2, b1);
+      hm_gram_mma_jj<RK, NBT, WQ, E, 2, 1>(acc, r, a1, a2, b2);
+      hm_gram_mma_jj<RK, NBT, WQ, E, 3, 1>(acc, r, a1, a2, b3);
+    }
+  }
+}
+
+// Write one warp's fragments of a finished item and reset them.
+// C fragment layout (m8n8k4.f64): c0/c1 = C[8i + lane/4][8j + 2*(lane%4) + {0,1}]
+template <int RK, int NBT, int WQ, int E>
+__device__ __forceinline__ void hm_gram_flush(double (&acc)[RK][2][4][2], double* __restrict__ dst, int P, int nk,
+                                              int row0, int fr, int fk) {
+  using F = hm_gram_frag<NBT, WQ, E>;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const bool valid = (h == 0) ? F::v1(jj) : F::v2(jj);
+      if (valid) {
+        const int u = 8 * (h == 0 ? F::I1 : F::I2) + fr;
+#pragma unroll
+        for (int ee = 0; ee < 2; ++ee) {
+          const int v = 8 * (2 * jj + E) + 2 * fk + ee;
+          if (u < v && v < P) {                        // strict upper triangle, row-major index of (u, v)
+            const size_t idx = (size_t)2 * P + (size_t)u * P - (size_t)u * (u + 1) / 2 + (v - u - 1);
+#pragma unroll
+            for (int r = 0; r < RK; ++r)
+              if (row0 + r < nk) dst[idx * nk + row0 + r] = acc[r][h][jj][ee];
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < RK; ++r) acc[r][h][jj][0] = acc[r][h][jj][1] = 0.;
+    }
+}
+
+#define HM_GRAM_WARP_SWITCH(FN, ...)                           \
+  switch (warp) {                                              \
+    case 0: FN<RK, NBT, 0, 0>(__VA_ARGS__); break;             \
+    case 1: FN<RK, NBT, 0, 1>(__VA_ARGS__); break;             \
+    case 2: FN<RK, NBT, 1, 0>(__VA_ARGS__); break;             \
+    case 3: FN<RK, NBT, 1, 1>(__VA_ARGS__); break;             \
+    case 4: FN<RK, NBT, 2, 0>(__VA_ARGS__); break;             \
+    case 5: FN<RK, NBT, 2, 1>(__VA_ARGS__); break;             \
+    case 6: FN<RK, NBT, 3, 0>(__VA_ARGS__); break;             \
+    default: FN<RK, NBT, 3, 1>(__VA_ARGS__); break;            \
   }
 
-  for (int m0 = mbeg; m0 < mend; m0 += HM_GMCH) {
-    // ---- phase 1: load, scale to W, stage, and the diagonal work.  Warp w owns tracers w, w+8, ... ----------
-    const int m = m0 + 2 * lane;
-    const bool in = m < mend;                          // nM and MP are even: a lane's two masses are in or out together
-    const double2 w2v = in ? *reinterpret_cast<const double2*>(gw + (size_t)a.nMp + m) : make_double2(0., 0.);
-    if (warp == 0) {
-      const double2 w1v = in ? *reinterpret_cast<const double2*>(gw + m) : make_double2(0., 0.);
-      *reinterpret_cast<double2*>(w1s + 2 * lane) = w1v;
-    }
+// Persistent CTA (one per SM).  Per 64-mass chunk: DMMA over the staged W tile of chunk c while the loads of chunk
+// c+1 are in flight in registers; then scale chunk c+1 to W, stage it in the other buffer and add its diagonal sums.
+template <int RK, int NBT>
+__global__ void __launch_bounds__(32 * HM_GWARPS, 1) hm_gram_kernel(const hm_gram_args a) {
+  extern __shared__ __align__(16) double gsm[];
+  constexpr int PT = 8 * NBT;
+  const int P = a.P;
+  constexpr size_t tile_doubles = (size_t)RK * PT * HM_GLD;
+  double* Ys = gsm;                                     // [2][RK][PT][HM_GLD]  W tiles (double buffered)
+  double* w1s = Ys + 2 * tile_doubles;                  // [2][HM_GMCH]
+  double* ssum = w1s + 2 * HM_GMCH;                     // [2][RK][2][PT]       two-halo / auto one-halo sums, by item parity
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform: the role switch below does not diverge
+
+  const long long per = (a.nitems + gridDim.x - 1) / gridDim.x;
+  const long long it0 = (long long)blockIdx.x * per;
+  const long long it1 = (it0 + per < a.nitems) ? it0 + per : a.nitems;
+  if (it0 >= it1) return;
+
+  double acc[RK][2][4][2];
+#pragma unroll
+  for (int r = 0; r < RK; ++r)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) acc[r][h][jj][0] = acc[r][h][jj][1] = 0.;
+  for (int i = tid; i < 2 * RK * 2 * PT; i += blockDim.x) ssum[i] = 0.;
+
+  // scale a prefetched chunk to W, stage it in buffer `buf` and add its diagonal sums to ssum[parity]
+  auto stage = [&](const hm_gram_chunk<RK>& q, int buf, int parity) {
+    double* Y = Ys + (size_t)buf * tile_doubles;
+    if (warp == 0) *reinterpret_cast<double2*>(w1s + buf * HM_GMCH + 2 * lane) = q.w1v;
     double vals[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) vals[i] = 0.;
 #pragma unroll
-    for (int t = 0; t < 8; ++t) {
+    for (int t = 0; t < NBT; ++t) {                    // warp w owns tracers w, w+8, ...
       const int p = warp + 8 * t;
-      if (p < PT) {                                    // warp-uniform
-        double2 cc = make_double2(0., 0.), dd = make_double2(0., 0.);
-        double2 x[RK];
-#pragma unroll
-        for (int r = 0; r < RK; ++r) x[r] = make_double2(0., 0.);
-        if (p < P && in) {
-          cc = *reinterpret_cast<const double2*>(gw + (size_t)(2 + p) * a.nMp + m);
-          dd = *reinterpret_cast<const double2*>(gw + (size_t)(2 + P + p) * a.nMp + m);
-#pragma unroll
-          for (int r = 0; r < RK; ++r) x[r] = hm_ldg_stream2(a.grid[p] + rowoff[r] + m);
-        }
-#pragma unroll
-        for (int r = 0; r < RK; ++r) {
-          const double2 y = make_double2(cc.x * x[r].x, cc.y * x[r].y);
-          *reinterpret_cast<double2*>(Ys + ((size_t)r * PT + p) * HM_GLD + 2 * lane) = y;
-          if (RK * 2 * t + 2 * r + 1 < 32) {
-            vals[(t * RK + r) * 2] = fma(w2v.x, y.x, w2v.y * y.y);                           // sum_m w2 W_p   (:539)
-            vals[(t * RK + r) * 2 + 1] = fma(dd.x * x[r].x, x[r].x, (dd.y * x[r].y) * x[r].y);   // sum_m d_p U^2  (:475-477)
-          }
-        }
-      }
-    }
-    {
-      const double tot = hm_warp_transpose_sum32(vals, lane);     // lane j now holds value j of this warp
-      const int t = lane / (2 * RK), r = (lane >> 1) % RK, kind = lane & 1;
-      const int p = warp + 8 * t;
-      if (lane < 16 * RK && p < PT) ssum[((size_t)r * 2 + kind) * PT + p] += tot;   // only this warp touches these p
-    }
-    __syncthreads();
-
-    // ---- phase 2: DMMA over my fragments: C[u,v] += sum_m (w1 W_u) W_v ---------------------------------------
-    const int fr = lane >> 2, fk = lane & 3;
-#pragma unroll 4
-    for (int s4 = 0; s4 < HM_GMCH / 4; ++s4) {
-      const double w1e = w1s[4 * s4 + fk];
 #pragma unroll
       for (int r = 0; r < RK; ++r) {
-        const double* Yr = Ys + (size_t)r * PT * HM_GLD + 4 * s4 + fk;
-        int last_i = -1;
-        double afrag = 0.;
-#pragma unroll
-        for (int t = 0; t < HM_GMAXFRAG; ++t) {
-          if (t < nmine) {                             // warp-uniform
-            if (fi[t] != last_i) {
-              last_i = fi[t];
-              afrag = w1e * Yr[(size_t)(8 * fi[t] + fr) * HM_GLD];
-            }
-            const double bfrag = Yr[(size_t)(8 * fj[t] + fr) * HM_GLD];
-            hm_dmma884(acc[r][t][0], acc[r][t][1], afrag, bfrag);
-          }
+        const double2 x = q.x[t][r];
+        const double2 y = make_double2(q.cc[t].x * x.x, q.cc[t].y * x.y);
+        *reinterpret_cast<double2*>(Y + ((size_t)r * PT + p) * HM_GLD + 2 * lane) = y;
+        if ((t * RK + r) * 2 + 1 < 32) {
+          vals[(t * RK + r) * 2] = fma(q.w2v.x, y.x, q.w2v.y * y.y);                       // sum_m w2 W_p   (:539)
+          vals[(t * RK + r) * 2 + 1] = fma(q.dd[t].x * x.x, x.x, (q.dd[t].y * x.y) * x.y);  // sum_m d_p U^2  (:475-477)
         }
       }
     }
-    __syncthreads();
-  }
+    const double tot = hm_warp_transpose_sum32(vals, lane);       // lane j now holds value j of this warp
+    const int t = lane / (2 * RK), r = (lane >> 1) % RK, kind = lane & 1;
+    const int p = warp + 8 * t;
+    if (lane < 2 * RK * NBT)                            // only this warp touches these tracers: no race
+      ssum[(((size_t)parity * RK + r) * 2 + kind) * PT + p] += tot;
+  };
 
-  // ---- write this part's sums: partial[b][part][value][row] -----------------------------------------------------
-  double* dst = a.partial + ((size_t)b * a.nparts + part) * (size_t)a.NW * a.nk;
-  for (int i = tid; i < RK * 2 * P; i += blockDim.x) {
-    const int r = i / (2 * P), rem = i - r * 2 * P, kind = rem / P, p = rem - kind * P;
-    if (row0 + r < a.nk) dst[(size_t)(kind * P + p) * a.nk + row0 + r] = ssum[((size_t)r * 2 + kind) * PT + p];
-  }
-  // C fragment layout (m8n8k4.f64): c0/c1 = C[8i + lane/4][8j + 2*(lane%4) + {0,1}]
-#pragma unroll
-  for (int t = 0; t < HM_GMAXFRAG; ++t) {
-    if (t < nmine) {
-      const int u = 8 * fi[t] + (lane >> 2);
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int v = 8 * fj[t] + 2 * (lane & 3) + e;
-        if (u < v && v < P) {
-          // strict upper triangle, row-major: index of (u, v)
-          const size_t idx = (size_t)2 * P + (size_t)u * P - (size_t)u * (u + 1) / 2 + (v - u - 1);
-#pragma unroll
-          for (int r = 0; r < RK; ++r)
-            if (row0 + r < a.nk) dst[idx * a.nk + row0 + r] = acc[r][t][e];
-        }
-      }
+  hm_gram_cursor cur, nxt;
+  cur.item = (int)it0; cur.ch = 0;
+  hm_gram_decode<RK>(cur, a);
+  hm_gram_chunk<RK> q;
+  hm_gram_load<RK, NBT>(q, cur, a, warp, lane);
+  __syncthreads();                                      // ssum zeroed
+  stage(q, 0, cur.item & 1);
+  __syncthreads();
+
+  int buf = 0;
+  const int fr = lane >> 2, fk = lane & 3;
+  while (true) {
+    // ---- next chunk: issue its loads now, consume them after the DMMA phase ----------------------------------
+    nxt = cur;
+    bool have_next = true;
+    if (++nxt.ch == cur.nch_item) {
+      nxt.ch = 0;
+      ++nxt.item;
+      have_next = nxt.item < (int)it1;
+      if (have_next) hm_gram_decode<RK>(nxt, a);
     }
+    if (have_next) hm_gram_load<RK, NBT>(q, nxt, a, warp, lane);
+
+    // ---- DMMA phase ------------------------------------------------------------------------------------------
+    {
+      const double* Yt = Ys + (size_t)buf * tile_doubles;
+      const double* w1t = w1s + buf * HM_GMCH;
+      HM_GRAM_WARP_SWITCH(hm_gram_mma, acc, Yt, w1t, fr, fk)
+    }
+
+    // ---- item finished: write this part's sums, partial[b][part][value][row], and reset ------------------------
+    if (cur.ch + 1 == cur.nch_item) {
+      const int part = cur.item % a.nparts;
+      double* dst = a.partial + ((size_t)cur.b * a.nparts + part) * (size_t)a.NW * a.nk;
+      double* ss = ssum + (size_t)(cur.item & 1) * RK * 2 * PT;
+      for (int i = tid; i < RK * 2 * PT; i += blockDim.x) {
+        const int r = i / (2 * PT), rem = i - r * 2 * PT, kind = rem / PT, p = rem - kind * PT;
+        if (p < P && cur.row0 + r < a.nk) dst[(size_t)(kind * P + p) * a.nk + cur.row0 + r] = ss[i];
+        ss[i] = 0.;
+      }
+      HM_GRAM_WARP_SWITCH(hm_gram_flush, acc, dst, P, a.nk, cur.row0, fr, fk)
+    }
+    if (!have_next) break;
+    stage(q, buf ^ 1, nxt.item & 1);
+    __syncthreads();
+    buf ^= 1;
+    cur = nxt;
   }
 }
 
@@ -436,6 +561,8 @@ extern "C" int hm_gram_power_spectrum(const hm_gram_problem* pr, double* out_dev
   w.gw = wsd; w.scal = wsd + L.scal_offset; w.tscal = wsd + L.tscal_offset; w.lowmass = lowmass_dev;
   hm_gram_weights_kernel<<<dim3(L.nchunks, (unsigned)L.B), 256, 0, st>>>(w);
   HM_LAUNCH_CHECK();
+  hm_gram_tracer_kernel<<<dim3(L.nchunks, L.P, (unsigned)L.B), 256, 0, st>>>(w);
+  HM_LAUNCH_CHECK();
   hm_gram_scalars_kernel<<<dim3(L.P, (unsigned)L.B), 256, 0, st>>>(w);
   HM_LAUNCH_CHECK();
 
@@ -444,15 +571,22 @@ extern "C" int hm_gram_power_spectrum(const hm_gram_problem* pr, double* out_dev
   g.F = pr->models_per_sample; g.ntiles = L.ntiles; g.nparts = L.nparts; g.MP = L.MP; g.gw_stride = L.gw_stride;
   for (int p = 0; p < HM_GMAXP; ++p) g.grid[p] = (p < L.P) ? pr->tracers[p].grid_dev : nullptr;
   g.gw = wsd; g.partial = wsd + L.partial_offset;
-  const size_t smem = ((size_t)L.RK * L.PT * HM_GLD + HM_GMCH + (size_t)L.RK * 2 * L.PT) * sizeof(double);
+  // the kernel is instantiated for block grids of 2, 4 and 8 (16, 32, 64 tracer rows); pad up to the next one
+  const int NBT = (L.NB <= 2) ? 2 : (L.NB <= 4) ? 4 : 8;
+  const size_t smem = (2 * (size_t)L.RK * (8 * NBT) * HM_GLD + 2 * HM_GMCH + 2 * (size_t)L.RK * 2 * (8 * NBT)) * sizeof(double);
   static bool configured = false;
   if (!configured) {
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
     configured = true;
   }
-  const long long items = (long long)L.B * L.ntiles * L.nparts;
-  HM_REQUIRE(items < (1LL << 31), "too many work items for one launch");
-  hm_gram_kernel<2><<<(unsigned)items, 32 * HM_GWARPS, smem, st>>>(g);
+  g.nitems = (long long)L.B * L.ntiles * L.nparts;
+  HM_REQUIRE(g.nitems < (1LL << 31), "too many work items for one launch");
+  const long long grid = g.nitems < hm_num_sms() ? g.nitems : hm_num_sms();
+  if (NBT == 2) hm_gram_kernel<2, 2><<<(unsigned)grid, 32 * HM_GWARPS, smem, st>>>(g);
+  else if (NBT == 4) hm_gram_kernel<2, 4><<<(unsigned)grid, 32 * HM_GWARPS, smem, st>>>(g);
+  else hm_gram_kernel<2, 8><<<(unsigned)grid, 32 * HM_GWARPS, smem, st>>>(g);
   HM_LAUNCH_CHECK();
 
   hm_gram_eargs e;

@@ -37,6 +37,10 @@ class Batch:
     def B(self):
         return len(self.models)
 
+    def gram_plan(self, **flags):
+        return engine.GramPlan(self.k, self.Pk_lin, self.M, self.sigma, self.tracers,
+                               [m.descriptor() for m in self.models], models_per_sample=self.F, **flags)
+
     def plan(self, **flags):
         return engine.PowerSpectrumPlan(self.k, self.Pk_lin, self.M, self.sigma, self.tracers,
                                         [m.descriptor() for m in self.models], models_per_sample=self.F, **flags)
@@ -107,6 +111,35 @@ def build(G, nk, nM, tracers=('m', 'g', 'p'), families=(TINKER10,), seed=1234, f
         else:
             raise ValueError('unknown tracer '+name)
         b.names.append(name)
+    return b
+
+
+def build_many_tracer(n_tracers=64, nk=256, nM=2048, seed=4, family=TINKER10):
+    """BASELINE config 4: `n_tracers` Zheng05 HOD galaxy samples (NFW profile, Bernoulli+Poisson variance, discrete)
+    on one cosmology; returns a Batch whose .gram_plan() evaluates all n(n+1)/2 unique pairs."""
+    rng = np.random.default_rng(seed)
+    k, M = syn.k_grid(nk), syn.M_grid(nM)
+    cs = dict(Om_m=0.3, sigma8=0.8, ns=0.96, h=0.7, z=0.)
+    Pk, sigma, dcDv = _cosmo_inputs([cs], k, M)
+    b = Batch()
+    b.k, b.M, b.F = engine.to_dev(k), engine.to_dev(M), 1
+    b.Pk_lin, b.sigma = engine.to_dev(Pk), sigma
+    hmod = model(cs['z'], cs['Om_m'], name=family, Dv=dcDv[0][1], dc=dcDv[0][0])
+    b.models = [hmod]
+    b.meta = [dict(cosmo=cs, dc=dcDv[0][0], Dv=dcDv[0][1], hods=[])]
+    b.rv = engine.to_dev(hmod.virial_radius(M))[None]
+    b.c = engine.to_dev(concentration(M, cs['z'], halo_definition='Mvir'))[None]
+    U = engine.window_nfw(b.k, b.rv, b.c)
+    for i in range(n_tracers):
+        hod = syn.draw_hod(rng)
+        Nc, Ns = HOD_mean(M, method='Zheng et al. (2005)', **hod)
+        Vc, Vs, _ = HOD_variance(Nc, Ns)
+        N, V = engine.to_dev(Nc+Ns)[None], engine.to_dev(Vc+Vs)[None]
+        norm = engine.average(hmod.descriptor(), b.M, b.sigma[0], N[0])
+        # every tracer owns its grid, as separate profile objects do in the reference API
+        b.tracers.append(engine.Tracer(U.clone(), N, norm, variance=V, mode=_lib.GRID_UK, discrete_tracer=True))
+        b.names.append('g%d' % i)
+        b.meta[0]['hods'].append(hod)
     return b
 
 
