@@ -381,7 +381,10 @@ struct hm_item_cursor {
   }
 };
 
-template <int P, int R>
+// FM > 1: the FM models of one sample (e.g. the five mass functions evaluated on one cosmology) share its grids.
+// An item is then (sample, slice, tile): the tile is read from HBM ONCE and accumulated against FM weight sets
+// held in registers (BASELINE config 3), instead of once per model.
+template <int P, int R, int FM>
 __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(const hm_quad_args a) {
   using C = hm_stream_cfg<P, R>;
   constexpr int NW = C::NW, NG = C::NG, NS = C::NS;
@@ -415,7 +418,7 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
       int s = 0;
       uint32_t parity = 0;
       for (int n = 0; n < nloc; ++n) {
-        const int smp = cur.b / a.F, m0 = cur.slice * HM_MC, row0 = cur.tile * R;
+        const int smp = (FM > 1) ? cur.b : cur.b / a.F, m0 = cur.slice * HM_MC, row0 = cur.tile * R;
         const int cols = (a.nM - m0 < HM_MC) ? a.nM - m0 : HM_MC;
         const uint32_t bytes = (uint32_t)cols * 8u;
         hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);        // slot drained by all consumer warps
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
   // ---------------- consumers: 8 independent warps, 64 mass columns per warp, 2 per thread -----------------
   // No CTA-wide synchronisation: every warp reduces its own 64 columns and writes its own partial row sums;
   // the epilogue kernel adds the parts in fixed order.
-  double wv[2][NW];
+  double wv[FM][2][NW];
   int cur_b = -1, cur_slice = -1;
   int s = 0;
   uint32_t parity = 0;
@@ -448,11 +451,14 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
     const bool active = m < a.nM;
     if (cur.b != cur_b || cur.slice != cur_slice) {   // weights of my two columns stay in registers for the slice
       cur_b = cur.b; cur_slice = cur.slice;
-      const double* __restrict__ w = a.weights + (size_t)cur.b * NW * a.nMp + m;
 #pragma unroll
-      for (int i = 0; i < NW; ++i) {
-        const double2 t = active ? *reinterpret_cast<const double2*>(w + (size_t)i * a.nMp) : make_double2(0., 0.);
-        wv[0][i] = t.x; wv[1][i] = t.y;
+      for (int f = 0; f < FM; ++f) {
+        const double* __restrict__ w = a.weights + ((size_t)cur.b * FM + f) * NW * a.nMp + m;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+          const double2 t = active ? *reinterpret_cast<const double2*>(w + (size_t)i * a.nMp) : make_double2(0., 0.);
+          wv[f][0][i] = t.x; wv[f][1][i] = t.y;
+        }
       }
     }
     hm_mbar_wait(bar_full + 8 * s, parity);                  // TMA bytes have landed
@@ -469,22 +475,29 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
     __syncwarp();
     if (lane == 0) hm_mbar_arrive(bar_empty + 8 * s);        // values are in registers: release the slot early
 
-    double acc[NG * 32];
-#pragma unroll
-    for (int i = 0; i < NG * 32; ++i) acc[i] = 0.;
-    hm_accumulate<P, R, false>(acc, wv[0], x[0], xu);
-    hm_accumulate<P, R, false>(acc, wv[1], x[1], xu);
-
-    // partial[b][slice*8 + warp][row0 + r][i]: the R*NW values of this tile are contiguous -> coalesced store
-    double* dst = a.partial + (((size_t)cur.b * a.nparts + cur.slice * HM_CONSUMER_WARPS + warp) * a.nk + row0) * NW;
+    // all FM*R*NW sums of this tile go through ONE transposing reduction (lane j ends up with value j)
+    constexpr int NVF = FM * R * NW, NGF = (NVF + 31) / 32;
     const int nvalid = ((a.nk - row0 < R) ? a.nk - row0 : R) * NW;
+    double acc[NGF * 32];
 #pragma unroll
-    for (int g = 0; g < NG; ++g) {
+    for (int i = 0; i < NGF * 32; ++i) acc[i] = 0.;
+#pragma unroll
+    for (int f = 0; f < FM; ++f) {
+      hm_accumulate<P, R, false>(acc + f * R * NW, wv[f][0], x[0], xu);
+      hm_accumulate<P, R, false>(acc + f * R * NW, wv[f][1], x[1], xu);
+    }
+#pragma unroll
+    for (int g = 0; g < NGF; ++g) {
       double v[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = acc[g * 32 + i];
       const double t = hm_warp_transpose_sum32(v, lane);
-      if (g * 32 + lane < nvalid) dst[g * 32 + lane] = t;
+      const int idx = g * 32 + lane, f = idx / (R * NW), rem = idx - f * (R * NW);
+      if (f < FM && rem < nvalid) {
+        // partial[model][slice*8 + warp][row0 + r][i]: the R*NW values of a tile are contiguous -> coalesced store
+        const size_t model = (size_t)cur.b * FM + f;
+        a.partial[((model * a.nparts + cur.slice * HM_CONSUMER_WARPS + warp) * a.nk + row0) * NW + rem] = t;
+      }
     }
     cur.next(a.nslices, a.ntiles);
     if (++s == NS) { s = 0; parity ^= 1u; }
@@ -675,22 +688,32 @@ static int hm_launch_fallback(hm_quad_args& a, bool vec2, bool sep, cudaStream_t
   return HM_OK;
 }
 
-template <int P, int R>
-static int hm_launch_stream(hm_quad_args& a, cudaStream_t st) {
+template <int P, int R, int FM>
+static int hm_launch_stream_fm(hm_quad_args& a, cudaStream_t st) {
   using C = hm_stream_cfg<P, R>;
   static bool configured = false;
   if (!configured) {
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_quad_stream_kernel<P, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_quad_stream_kernel<P, R, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM_BYTES));
     configured = true;
   }
   a.ntiles = (a.nk + R - 1) / R;
-  a.nitems = (long long)a.B * a.nslices * a.ntiles;
+  a.nitems = (long long)(a.B / FM) * a.nslices * a.ntiles;     // FM > 1: items enumerate samples, not models
   long long grid = hm_num_sms();
   if (grid > a.nitems) grid = a.nitems;
-  hm_quad_stream_kernel<P, R><<<(int)grid, HM_STREAM_THREADS, C::SMEM_BYTES, st>>>(a);
+  hm_quad_stream_kernel<P, R, FM><<<(int)grid, HM_STREAM_THREADS, C::SMEM_BYTES, st>>>(a);
   HM_LAUNCH_CHECK();
   return HM_OK;
+}
+
+template <int P, int R>
+static int hm_launch_stream(hm_quad_args& a, cudaStream_t st) {
+  // the fused multi-family variant holds F weight sets in registers: instantiated where they fit (P <= 2, F = 5:
+  // the five mass functions of BASELINE config 3); other combinations read the shared grids once per model
+  if constexpr (P <= 2) {
+    if (a.F == 5) return hm_launch_stream_fm<P, (P == 1 ? 3 : 1), 5>(a, st);   // 30 / 25 sums: one reduction
+  }
+  return hm_launch_stream_fm<P, R, 1>(a, st);
 }
 
 template <int P>

@@ -303,39 +303,46 @@ def test_full_size_c2_vs_oracle_and_properties(halo):
         assert np.array_equal(twice[1][key], got[1][key])                         # one-halo does not see P_lin
 
 
-def test_batched_plan_equals_single_models(halo):
-    """The batch entry (G samples x F models per sample sharing grids) reproduces per-model calls bit for bit."""
+@pytest.mark.parametrize('names,with_gal', [([orc.PS74, orc.ST99, orc.TINKER10], True), (list(orc.FAMILIES), True),
+                                            (list(orc.FAMILIES), False)])
+def test_batched_plan_equals_single_models(halo, names, with_gal):
+    """The batch entry (G samples x F models per sample sharing grids) reproduces per-model calls bit for bit;
+    F = 5 takes the fused multi-family variant of the streaming kernel (grids read once for all five)."""
     from pyhalomodel_b200 import engine, _lib
-    nk, nM, G = 40, 128, 3
+    nk, nM, G = 41, 128, 3
     rng = np.random.default_rng(3)
     cases = [_synthetic_case(nk, nM, z=z, Om_m=Om) for z, Om in [(0., 0.3), (0.7, 0.27), (1.5, 0.33)]]
     k, M = cases[0]['k'], cases[0]['M']
-    names = [orc.PS74, orc.ST99, orc.TINKER10]
     models, grids_m, grids_g, amp_g, var_g, norm_g, norm_m, singles = [], [], [], [], [], [], [], []
     for cs in cases:
         hod = syn.draw_hod(rng)
         for name in names:
             hmod = halo.model(cs['z'], cs['Om_m'], name=name, Dv=cs['Dv'], dc=cs['dc'])
-            profs = _gpu_profiles(halo, hmod, cs, [hod], False)
+            profs = _gpu_profiles(halo, hmod, cs, [hod] if with_gal else [], False)
             singles.append(hmod.power_spectrum(k, cs['Pk_lin'], M, cs['sigmaM'], profs))
             models.append(hmod.descriptor())
-            norm_g.append(profs['g0'].normalisation)
             norm_m.append(profs['m'].normalisation)
+            if with_gal:
+                norm_g.append(profs['g0'].normalisation)
         grids_m.append(profs['m']._grid)
-        grids_g.append(profs['g0']._grid)
-        amp_g.append(profs['g0']._amplitude)
-        var_g.append(profs['g0']._variance)
+        if with_gal:
+            grids_g.append(profs['g0']._grid)
+            amp_g.append(profs['g0']._amplitude)
+            var_g.append(profs['g0']._variance)
     Mdev = engine.to_dev(M)
     tr = [engine.Tracer(torch.stack(grids_m), Mdev[None, :].expand(G, -1).contiguous(), np.array(norm_m),
-                        mode=_lib.GRID_UK, mass_tracer=True),
-          engine.Tracer(torch.stack(grids_g), torch.stack(amp_g), np.array(norm_g), variance=torch.stack(var_g),
-                        mode=_lib.GRID_UK, discrete_tracer=True)]
+                        mode=_lib.GRID_UK, mass_tracer=True)]
+    keys = ['m-m']
+    if with_gal:
+        tr.append(engine.Tracer(torch.stack(grids_g), torch.stack(amp_g), np.array(norm_g), variance=torch.stack(var_g),
+                                mode=_lib.GRID_UK, discrete_tracer=True))
+        keys = ['m-m', 'm-g0', 'g0-g0']
     plan = engine.PowerSpectrumPlan(k, np.stack([c['Pk_lin'] for c in cases]), M, np.stack([c['sigmaM'] for c in cases]),
                                     tr, models, models_per_sample=len(names))
     out, A = plan.run()
     out = out.cpu().numpy()
     for b, single in enumerate(singles):
-        for s, key in enumerate(['m-m', 'm-g0', 'g0-g0']):
+        for s, key in enumerate(keys):
             for t in range(3):
                 assert np.array_equal(out[b, s, t], single[t][key]), (b, key, t)
 
