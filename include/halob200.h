@@ -121,6 +121,11 @@ int hm_low_mass_correction(const hm_model_desc* models_dev, const double* nu0_de
 int hm_average(const hm_model_desc* model_host, const double* M_dev, const double* sigma_dev, int32_t nM,
                const double* f_dev, int32_t nf, double* out_dev, void* stream);
 
+/* Batched model.average for sweeps: out[b] = <f_s> under model b, with sample s = b / models_per_sample.
+ * models_dev: [B]; sigma_dev, f_dev: [n_samples][nM]; out_dev: [B]. */
+int hm_average_batch(const hm_model_desc* models_dev, const double* M_dev, const double* sigma_dev, int32_t nM,
+                     int32_t n_samples, int32_t models_per_sample, const double* f_dev, double* out_dev, void* stream);
+
 /* ---- the hot path: model.power_spectrum (pyhalomodel.py:361-513, beta=None) --------------------------------
  * out_dev: [B][S][3][nk] with S = P(P+1)/2 unique pairs ordered (0,0),(0,1),..,(0,P-1),(1,1),.. and the three
  * terms ordered (Pk_2h, Pk_1h, Pk_hm).  lowmass_dev (optional, [B]) receives A so the caller can raise the

@@ -57,6 +57,8 @@ _SIGNATURES = {
     'hm_low_mass_correction': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     'hm_average': (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                              C.c_void_p, C.c_void_p]),
+    'hm_average_batch': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
     'hm_power_spectrum_workspace': (C.c_size_t, [C.POINTER(Problem)]),
     'hm_power_spectrum': (C.c_int, [C.POINTER(Problem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'hm_halo_weights': (C.c_int, [C.POINTER(Problem), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

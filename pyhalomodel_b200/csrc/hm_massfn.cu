@@ -55,3 +55,37 @@ extern "C" int hm_average(const hm_model_desc* model_host, const double* M_dev, 
   HM_LAUNCH_CHECK();
   return HM_OK;
 }
+
+// Batched variant for sweeps: out[b] = <f_{b/F}> under model b.  One CTA per model.
+__global__ void __launch_bounds__(256) hm_average_batch_kernel(const hm_model_desc* __restrict__ models,
+                                                               const double* __restrict__ M,
+                                                               const double* __restrict__ sigma, int nM, int F,
+                                                               const double* __restrict__ f, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  const int b = blockIdx.x, s = b / F;
+  const hm_model_desc d = models[b];
+  const double* sig = sigma + (size_t)s * nM;
+  const double* fs = f + (size_t)s * nM;
+  double acc = 0.;
+  for (int m = threadIdx.x; m < nM; m += blockDim.x) {
+    const double nu = d.dc / sig[m];
+    const double nu_hi = (m + 1 < nM) ? d.dc / sig[m + 1] : nu;
+    const double nu_lo = (m > 0) ? d.dc / sig[m - 1] : nu;
+    acc += (0.5 * (nu_hi - nu_lo)) * ((fs[m] / M[m]) * hm_g_nu(d, nu));
+  }
+  const double tot = hm_block_sum(acc, scratch);
+  if (threadIdx.x == 0) out[b] = tot * d.rhom;
+}
+
+extern "C" int hm_average_batch(const hm_model_desc* models_dev, const double* M_dev, const double* sigma_dev,
+                                int32_t nM, int32_t n_samples, int32_t models_per_sample, const double* f_dev,
+                                double* out_dev, void* stream) {
+  int rc = hm_check_device();
+  if (rc) return rc;
+  HM_REQUIRE(models_dev && M_dev && sigma_dev && f_dev && out_dev, "NULL pointer");
+  HM_REQUIRE(nM >= 2 && n_samples >= 1 && models_per_sample >= 1, "bad sizes");
+  hm_average_batch_kernel<<<n_samples * models_per_sample, 256, 0, (cudaStream_t)stream>>>(
+      models_dev, M_dev, sigma_dev, nM, models_per_sample, f_dev, out_dev);
+  HM_LAUNCH_CHECK();
+  return HM_OK;
+}

@@ -92,6 +92,16 @@ def average(desc: ModelDesc, M, sigma, funcs):
     return out
 
 
+def average_batch(models_dev, M, sigma, funcs, models_per_sample=1):
+    """sigma, funcs: [G, nM]; models_dev: packed descriptors of the G*F models -> [G*F] halo averages."""
+    M, sigma, funcs = to_dev(M), to_dev(sigma), to_dev(funcs)
+    G, nM = sigma.shape
+    out = torch.empty(G*models_per_sample, dtype=F64, device=M.device)
+    check(lib().hm_average_batch(_ptr(models_dev), _ptr(M), _ptr(sigma), nM, G, models_per_sample, _ptr(funcs),
+                                 _ptr(out), _stream()))
+    return out
+
+
 def sici(x):
     x = to_dev(x)
     si, ci = torch.empty_like(x), torch.empty_like(x)
