@@ -203,12 +203,18 @@ def main():
     plan = batch.plan()
     S = plan.S
     from pyhalomodel_b200 import sweep
-    gather = sweep.OverlappedGather(plan.out) if world > 1 else None
+    # N > 1: every step's spectra are kept in a per-rank results buffer and the one collective of the path -- the
+    # gather of the spectra over NCCL -- runs once over the whole buffer at the end of the timed region, as a
+    # sweep driver would do (the bytes gathered are the same as with one gather per step).
+    results = torch.empty((max(K, W),)+tuple(plan.out.shape), dtype=torch.float64, device='cuda') if world > 1 else None
+    step_no = [0]
 
     def step():
-        out, _ = plan.run()
-        if world > 1:       # the one collective of the path: gather the spectra of every rank's models (NCCL),
-            gather.submit(out)   # enqueued on a side stream so it overlaps the next step's kernels
+        if world > 1:        # the kernels write straight into this step's slot of the results buffer
+            plan.run(out=results[step_no[0] % results.shape[0]])
+            step_no[0] += 1
+        else:
+            plan.run()
 
     def barrier():
         if world > 1:
@@ -225,10 +231,11 @@ def main():
     barrier()
     t0 = time.perf_counter()
     e0.record()
+    step_no[0] = 0
     for _ in range(K):
         step()
-    if world > 1:
-        gather.latest()          # the timed region ends only when the last gather has landed
+    if world > 1:                # the timed region ends only when every rank holds every rank's spectra
+        gathered = sweep.gather_spectra(results[:K].reshape((K*B,)+tuple(plan.out.shape[1:])), world*K*B)
     e1.record()
     barrier()
     t1 = time.perf_counter()
@@ -340,7 +347,7 @@ def main():
                     higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
                     config=dict(workload=WORKLOAD % B, nk=NK, nM=NM, tracers=list(TRACERS), family='Tinker et al. (2010)',
                                 models_per_gpu_per_step=B, l2='inputs larger than L2: %.0f MB of grids per step per GPU'
-                                % (B*len(TRACERS)*NK*NM*8/1e6), collective='all_gather of spectra (NCCL, side stream, overlapped with the next step)' if world > 1 else 'none'),
+                                % (B*len(TRACERS)*NK*NM*8/1e6), collective='one all_gather of all steps\' spectra (NCCL) inside the timed region' if world > 1 else 'none'),
                     clocks=clocks, e2e=e2e, gpu_launches=3*K, roofline=roofline, cpu_baseline=cpu)
         print(json.dumps(line))
     if world > 1:

@@ -242,11 +242,15 @@ class PowerSpectrumPlan:
         check(lib().hm_mass_quadrature_stages(C.byref(self.problem), _ptr(self.out), _ptr(self.workspace),
                                               self.workspace_bytes, _stream(), int(stages)))
 
-    def run(self):
-        """Enqueue both stages on the current stream; returns (out [B,S,3,nk], A [B]) device tensors."""
-        check(lib().hm_power_spectrum(C.byref(self.problem), _ptr(self.out), _ptr(self.lowmass), _ptr(self.workspace),
+    def run(self, out=None):
+        """Enqueue both stages on the current stream; returns (out [B,S,3,nk], A [B]) device tensors.  `out` may be
+        a caller-owned contiguous float64 CUDA tensor of that shape (e.g. a slot of a sweep's results buffer)."""
+        dst = self.out if out is None else out
+        if out is not None and (tuple(out.shape) != tuple(self.out.shape) or out.dtype != F64 or not out.is_contiguous()):
+            raise ValueError('out must be a contiguous float64 tensor of shape %s' % (tuple(self.out.shape),))
+        check(lib().hm_power_spectrum(C.byref(self.problem), _ptr(dst), _ptr(self.lowmass), _ptr(self.workspace),
                                       self.workspace_bytes, _stream()))
-        return self.out, self.lowmass
+        return dst, self.lowmass
 
     def stream_kernel_bytes(self):
         """Algorithmic bytes of the streaming quadrature kernel alone: every distinct grid once plus the weight
