@@ -178,12 +178,6 @@ __device__ __forceinline__ void hm_dmma884(double& c0, double& c1, double a, dou
 }
 
 
-// One mass chunk of one work item, prefetched into registers one chunk ahead of the DMMA phase.
-template <int RK>
-struct hm_gram_chunk {
-  double2 x[8][RK], cc[8], dd[8], w1v, w2v;
-};
-
 struct hm_gram_cursor {      // (item, chunk) iterator over the contiguous item range of a persistent CTA
   int item, ch, nch_item;
   int b, smp, row0, mbeg, mend;
@@ -200,32 +194,6 @@ __device__ __forceinline__ void hm_gram_decode(hm_gram_cursor& c, const hm_gram_
   c.mbeg = part * a.MP;
   c.mend = (c.mbeg + a.MP < a.nM) ? c.mbeg + a.MP : a.nM;
   c.nch_item = (c.mend - c.mbeg + HM_GMCH - 1) / HM_GMCH;
-}
-
-template <int RK, int NBT>
-__device__ __forceinline__ void hm_gram_load(hm_gram_chunk<RK>& q, const hm_gram_cursor& c, const hm_gram_args& a,
-                                             int warp, int lane) {
-  const int m = c.mbeg + c.ch * HM_GMCH + 2 * lane;
-  const bool in = m < c.mend;                  // nM and MP are even: a lane's two masses are in or out together
-  const double* __restrict__ gw = a.gw + (size_t)c.b * a.gw_stride;
-  const double2 zero = make_double2(0., 0.);
-  q.w1v = in ? *reinterpret_cast<const double2*>(gw + m) : zero;
-  q.w2v = in ? *reinterpret_cast<const double2*>(gw + (size_t)a.nMp + m) : zero;
-  size_t rowoff[RK];
-#pragma unroll
-  for (int r = 0; r < RK; ++r) {
-    const int row = (c.row0 + r < a.nk) ? c.row0 + r : a.nk - 1;     // clamp: duplicates are never written
-    rowoff[r] = ((size_t)c.smp * a.nk + row) * (size_t)a.nM + m;
-  }
-#pragma unroll
-  for (int t = 0; t < NBT; ++t) {
-    const int p = warp + 8 * t;                // warp w owns tracers w, w+8, ...
-    const bool on = in && p < a.P;
-    q.cc[t] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + p) * a.nMp + m) : zero;
-    q.dd[t] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + a.P + p) * a.nMp + m) : zero;
-#pragma unroll
-    for (int r = 0; r < RK; ++r) q.x[t][r] = on ? hm_ldg_stream2(a.grid[p] + rowoff[r]) : zero;
-  }
 }
 
 // ---- DMMA over the fragments one warp owns -------------------------------------------------------------------
@@ -331,25 +299,135 @@ __device__ __forceinline__ void hm_gram_flush(double (&acc)[RK][2][4][2], double
     default: FN<RK, NBT, 3, 1>(__VA_ARGS__); break;            \
   }
 
-// Persistent CTA (one per SM).  Per 64-mass chunk: DMMA over the staged W tile of chunk c while the loads of chunk
-// c+1 are in flight in registers; then scale chunk c+1 to W, stage it in the other buffer and add its diagonal sums.
+// ---- named barriers between the two warp roles (ids 1..4; 0 is __syncthreads) ---------------------------------
+#define HM_GBAR_FULL 1      // + buf: prep warps arrive, MMA warps wait
+#define HM_GBAR_EMPTY 3     // + buf: MMA warps arrive, prep warps wait
+#define HM_GTHREADS (64 * HM_GWARPS)
+__device__ __forceinline__ void hm_bar_sync(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(HM_GTHREADS) : "memory");
+}
+__device__ __forceinline__ void hm_bar_arrive(int id) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(HM_GTHREADS) : "memory");
+}
+
+__device__ __forceinline__ bool hm_gram_advance(hm_gram_cursor& c, long long it1) {   // false when the range is done
+  if (++c.ch < c.nch_item) return true;
+  c.ch = 0;
+  return ++c.item < (int)it1;
+}
+
+// Persistent, warp-specialised CTA (one per SM, 16 warps):
+//   prep warps 8..15  stream the tracer rows of the next 64-mass chunk from HBM (16-byte loads), scale them to
+//                     W = c_p * grid, stage the W tile in shared memory (double buffered) and accumulate the
+//                     diagonal work -- two-halo sums sum_m w2 W_p and auto one-halo sums sum_m d_p grid_p^2 --
+//                     in per-lane shared-memory accumulators that are reduced once per item;
+//   MMA warps 0..7    run DMMA over their fragments of the staged tile.
+// The roles hand tiles over with named barriers (bar.arrive / bar.sync), so loads, staging and tensor work of
+// different chunks overlap and there is no CTA-wide synchronisation.
 template <int RK, int NBT>
-__global__ void __launch_bounds__(32 * HM_GWARPS, 1) hm_gram_kernel(const hm_gram_args a) {
+__global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_args a) {
   extern __shared__ __align__(16) double gsm[];
   constexpr int PT = 8 * NBT;
-  const int P = a.P;
   constexpr size_t tile_doubles = (size_t)RK * PT * HM_GLD;
-  double* Ys = gsm;                                     // [2][RK][PT][HM_GLD]  W tiles (double buffered)
+  constexpr int NDV = NBT * RK * 2;                     // diagonal sums per prep warp (<= 32)
+  double* Ys = gsm;                                     // [2][RK][PT][HM_GLD]  W tiles
   double* w1s = Ys + 2 * tile_doubles;                  // [2][HM_GMCH]
-  double* ssum = w1s + 2 * HM_GMCH;                     // [2][RK][2][PT]       two-halo / auto one-halo sums, by item parity
+  double* sdiag = w1s + 2 * HM_GMCH;                    // [HM_GWARPS][NDV][33]  per-lane diagonal accumulators
+  const int P = a.P;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform: the role switch below does not diverge
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform: role dispatch does not diverge
 
   const long long per = (a.nitems + gridDim.x - 1) / gridDim.x;
   const long long it0 = (long long)blockIdx.x * per;
   const long long it1 = (it0 + per < a.nitems) ? it0 + per : a.nitems;
   if (it0 >= it1) return;
+  for (int i = tid; i < HM_GWARPS * NDV * 33; i += blockDim.x) sdiag[i] = 0.;
+  __syncthreads();
 
+  hm_gram_cursor cur;
+  cur.item = (int)it0; cur.ch = 0;
+  hm_gram_decode<RK>(cur, a);
+
+  if (warp >= HM_GWARPS) {
+    // =============================== prep warps ===============================
+    const int pw = warp - HM_GWARPS;                    // owns tracers pw, pw+8, ...
+    double* myd = sdiag + (size_t)pw * NDV * 33 + lane;
+    const double2 zero = make_double2(0., 0.);
+    int n = 0;
+    while (true) {
+      const int buf = n & 1;
+      const int m = cur.mbeg + cur.ch * HM_GMCH + 2 * lane;
+      const bool in = m < cur.mend;                     // nM and MP are even: a lane's two masses are in or out together
+      const double* __restrict__ gw = a.gw + (size_t)cur.b * a.gw_stride;
+      size_t rowoff[RK];
+#pragma unroll
+      for (int r = 0; r < RK; ++r) {
+        const int row = (cur.row0 + r < a.nk) ? cur.row0 + r : a.nk - 1;     // clamp: duplicates are never written
+        rowoff[r] = ((size_t)cur.smp * a.nk + row) * (size_t)a.nM + m;
+      }
+      const double2 w2v = in ? *reinterpret_cast<const double2*>(gw + (size_t)a.nMp + m) : zero;
+      const double2 w1v = (pw == 0 && in) ? *reinterpret_cast<const double2*>(gw + m) : zero;
+      double* Y = Ys + (size_t)buf * tile_doubles + 2 * lane;
+      constexpr int TH = (NBT + 1) / 2;                 // tracers per half: bounds the registers held by loads
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        double2 x[TH][RK], cc[TH], dd[TH];
+#pragma unroll
+        for (int tt = 0; tt < TH; ++tt) {
+          const int t = half * TH + tt, p = pw + 8 * t;
+          const bool on = in && t < NBT && p < P;
+          cc[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + p) * a.nMp + m) : zero;
+          dd[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + P + p) * a.nMp + m) : zero;
+#pragma unroll
+          for (int r = 0; r < RK; ++r) x[tt][r] = on ? hm_ldg_stream2(a.grid[p] + rowoff[r]) : zero;
+        }
+        if (half == 0 && n >= 2) hm_bar_sync(HM_GBAR_EMPTY + buf);        // MMA warps are done with this buffer
+#pragma unroll
+        for (int tt = 0; tt < TH; ++tt) {
+          const int t = half * TH + tt, p = pw + 8 * t;
+          if (t < NBT) {
+#pragma unroll
+            for (int r = 0; r < RK; ++r) {
+              const double2 xv = x[tt][r];
+              const double2 y = make_double2(cc[tt].x * xv.x, cc[tt].y * xv.y);
+              *reinterpret_cast<double2*>(Y + ((size_t)r * PT + p) * HM_GLD) = y;
+              double* dv = myd + (size_t)((t * RK + r) * 2) * 33;
+              dv[0] += fma(w2v.x, y.x, w2v.y * y.y);                                 // sum_m w2 W_p   (:539)
+              dv[33] += fma(dd[tt].x * xv.x, xv.x, (dd[tt].y * xv.y) * xv.y);          // sum_m d_p U^2  (:475-477)
+            }
+          }
+        }
+      }
+      if (pw == 0) *reinterpret_cast<double2*>(w1s + buf * HM_GMCH + 2 * lane) = w1v;
+      __threadfence_block();
+      hm_bar_arrive(HM_GBAR_FULL + buf);
+
+      if (cur.ch + 1 == cur.nch_item) {                 // item finished: reduce and write my tracers' diagonal sums
+        __syncwarp();
+        const int part = cur.item % a.nparts;
+        double* dst = a.partial + ((size_t)cur.b * a.nparts + part) * (size_t)a.NW * a.nk;
+        if (lane < NDV) {
+          const double* row = sdiag + ((size_t)pw * NDV + lane) * 33;
+          double tot = 0.;
+#pragma unroll 8
+          for (int l = 0; l < 32; ++l) tot += row[l];                        // fixed order => reproducible
+          const int t = lane / (2 * RK), r = (lane >> 1) % RK, kind = lane & 1, p = pw + 8 * t;
+          if (p < P && cur.row0 + r < a.nk) dst[(size_t)(kind * P + p) * a.nk + cur.row0 + r] = tot;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int v = 0; v < NDV; ++v) myd[(size_t)v * 33] = 0.;
+        __syncwarp();
+      }
+      ++n;
+      const int prev_item = cur.item;
+      if (!hm_gram_advance(cur, it1)) break;
+      if (cur.item != prev_item) hm_gram_decode<RK>(cur, a);
+    }
+    return;
+  }
+
+  // ================================ MMA warps ================================
   double acc[RK][2][4][2];
 #pragma unroll
   for (int r = 0; r < RK; ++r)
@@ -357,83 +435,26 @@ __global__ void __launch_bounds__(32 * HM_GWARPS, 1) hm_gram_kernel(const hm_gra
     for (int h = 0; h < 2; ++h)
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) acc[r][h][jj][0] = acc[r][h][jj][1] = 0.;
-  for (int i = tid; i < 2 * RK * 2 * PT; i += blockDim.x) ssum[i] = 0.;
-
-  // scale a prefetched chunk to W, stage it in buffer `buf` and add its diagonal sums to ssum[parity]
-  auto stage = [&](const hm_gram_chunk<RK>& q, int buf, int parity) {
-    double* Y = Ys + (size_t)buf * tile_doubles;
-    if (warp == 0) *reinterpret_cast<double2*>(w1s + buf * HM_GMCH + 2 * lane) = q.w1v;
-    double vals[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) vals[i] = 0.;
-#pragma unroll
-    for (int t = 0; t < NBT; ++t) {                    // warp w owns tracers w, w+8, ...
-      const int p = warp + 8 * t;
-#pragma unroll
-      for (int r = 0; r < RK; ++r) {
-        const double2 x = q.x[t][r];
-        const double2 y = make_double2(q.cc[t].x * x.x, q.cc[t].y * x.y);
-        *reinterpret_cast<double2*>(Y + ((size_t)r * PT + p) * HM_GLD + 2 * lane) = y;
-        if ((t * RK + r) * 2 + 1 < 32) {
-          vals[(t * RK + r) * 2] = fma(q.w2v.x, y.x, q.w2v.y * y.y);                       // sum_m w2 W_p   (:539)
-          vals[(t * RK + r) * 2 + 1] = fma(q.dd[t].x * x.x, x.x, (q.dd[t].y * x.y) * x.y);  // sum_m d_p U^2  (:475-477)
-        }
-      }
-    }
-    const double tot = hm_warp_transpose_sum32(vals, lane);       // lane j now holds value j of this warp
-    const int t = lane / (2 * RK), r = (lane >> 1) % RK, kind = lane & 1;
-    const int p = warp + 8 * t;
-    if (lane < 2 * RK * NBT)                            // only this warp touches these tracers: no race
-      ssum[(((size_t)parity * RK + r) * 2 + kind) * PT + p] += tot;
-  };
-
-  hm_gram_cursor cur, nxt;
-  cur.item = (int)it0; cur.ch = 0;
-  hm_gram_decode<RK>(cur, a);
-  hm_gram_chunk<RK> q;
-  hm_gram_load<RK, NBT>(q, cur, a, warp, lane);
-  __syncthreads();                                      // ssum zeroed
-  stage(q, 0, cur.item & 1);
-  __syncthreads();
-
-  int buf = 0;
   const int fr = lane >> 2, fk = lane & 3;
+  int n = 0;
   while (true) {
-    // ---- next chunk: issue its loads now, consume them after the DMMA phase ----------------------------------
-    nxt = cur;
-    bool have_next = true;
-    if (++nxt.ch == cur.nch_item) {
-      nxt.ch = 0;
-      ++nxt.item;
-      have_next = nxt.item < (int)it1;
-      if (have_next) hm_gram_decode<RK>(nxt, a);
-    }
-    if (have_next) hm_gram_load<RK, NBT>(q, nxt, a, warp, lane);
-
-    // ---- DMMA phase ------------------------------------------------------------------------------------------
+    const int buf = n & 1;
+    hm_bar_sync(HM_GBAR_FULL + buf);                    // the W tile of this chunk is staged
     {
       const double* Yt = Ys + (size_t)buf * tile_doubles;
       const double* w1t = w1s + buf * HM_GMCH;
       HM_GRAM_WARP_SWITCH(hm_gram_mma, acc, Yt, w1t, fr, fk)
     }
-
-    // ---- item finished: write this part's sums, partial[b][part][value][row], and reset ------------------------
-    if (cur.ch + 1 == cur.nch_item) {
+    hm_bar_arrive(HM_GBAR_EMPTY + buf);                 // all my reads of the tile have been consumed by DMMAs
+    if (cur.ch + 1 == cur.nch_item) {                   // item finished: write and reset my fragments
       const int part = cur.item % a.nparts;
       double* dst = a.partial + ((size_t)cur.b * a.nparts + part) * (size_t)a.NW * a.nk;
-      double* ss = ssum + (size_t)(cur.item & 1) * RK * 2 * PT;
-      for (int i = tid; i < RK * 2 * PT; i += blockDim.x) {
-        const int r = i / (2 * PT), rem = i - r * 2 * PT, kind = rem / PT, p = rem - kind * PT;
-        if (p < P && cur.row0 + r < a.nk) dst[(size_t)(kind * P + p) * a.nk + cur.row0 + r] = ss[i];
-        ss[i] = 0.;
-      }
       HM_GRAM_WARP_SWITCH(hm_gram_flush, acc, dst, P, a.nk, cur.row0, fr, fk)
     }
-    if (!have_next) break;
-    stage(q, buf ^ 1, nxt.item & 1);
-    __syncthreads();
-    buf ^= 1;
-    cur = nxt;
+    ++n;
+    const int prev_item = cur.item;
+    if (!hm_gram_advance(cur, it1)) break;
+    if (cur.item != prev_item) hm_gram_decode<RK>(cur, a);
   }
 }
 
@@ -464,10 +485,12 @@ __global__ void __launch_bounds__(256) hm_gram_epilogue_kernel(const hm_gram_ear
   const long long rem = gid - (long long)b * per_model;
   const int s = (int)(rem / a.nk), row = (int)(rem - (long long)s * a.nk);
   const int smp = b / a.F, P = a.P;
-  // pair s -> (u, v), u <= v, row-major
-  int u = 0, left = s;
-  while (left >= P - u) { left -= P - u; ++u; }
-  const int v = u + left;
+  // pair s -> (u, v), u <= v, row-major: rows start at off(u) = u P - u(u-1)/2; invert with a float guess + fix-up
+  int u = (int)(((2. * P + 1.) - sqrt((2. * P + 1.) * (2. * P + 1.) - 8. * (double)s)) * 0.5);
+  u = u < 0 ? 0 : (u > P - 1 ? P - 1 : u);
+  while (u > 0 && u * P - u * (u - 1) / 2 > s) --u;
+  while ((u + 1) * P - (u + 1) * u / 2 <= s) ++u;
+  const int v = u + (s - (u * P - u * (u - 1) / 2));
   const double A = a.scal[(size_t)b * HM_GNSCAL], rhom = a.scal[(size_t)b * HM_GNSCAL + 1];
   const size_t i1h = (u == v) ? (size_t)(P + u)
                               : (size_t)2 * P + (size_t)u * P - (size_t)u * (u + 1) / 2 + (v - u - 1);
@@ -573,20 +596,21 @@ extern "C" int hm_gram_power_spectrum(const hm_gram_problem* pr, double* out_dev
   g.gw = wsd; g.partial = wsd + L.partial_offset;
   // the kernel is instantiated for block grids of 2, 4 and 8 (16, 32, 64 tracer rows); pad up to the next one
   const int NBT = (L.NB <= 2) ? 2 : (L.NB <= 4) ? 4 : 8;
-  const size_t smem = (2 * (size_t)L.RK * (8 * NBT) * HM_GLD + 2 * HM_GMCH + 2 * (size_t)L.RK * 2 * (8 * NBT)) * sizeof(double);
+  const size_t smem = (2 * (size_t)L.RK * (8 * NBT) * HM_GLD + 2 * HM_GMCH
+                       + (size_t)HM_GWARPS * (NBT * L.RK * 2) * 33) * sizeof(double);
   static bool configured = false;
   if (!configured) {
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 180 * 1024));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     configured = true;
   }
   g.nitems = (long long)L.B * L.ntiles * L.nparts;
   HM_REQUIRE(g.nitems < (1LL << 31), "too many work items for one launch");
   const long long grid = g.nitems < hm_num_sms() ? g.nitems : hm_num_sms();
-  if (NBT == 2) hm_gram_kernel<2, 2><<<(unsigned)grid, 32 * HM_GWARPS, smem, st>>>(g);
-  else if (NBT == 4) hm_gram_kernel<2, 4><<<(unsigned)grid, 32 * HM_GWARPS, smem, st>>>(g);
-  else hm_gram_kernel<2, 8><<<(unsigned)grid, 32 * HM_GWARPS, smem, st>>>(g);
+  if (NBT == 2) hm_gram_kernel<2, 2><<<(unsigned)grid, HM_GTHREADS, smem, st>>>(g);
+  else if (NBT == 4) hm_gram_kernel<2, 4><<<(unsigned)grid, HM_GTHREADS, smem, st>>>(g);
+  else hm_gram_kernel<2, 8><<<(unsigned)grid, HM_GTHREADS, smem, st>>>(g);
   HM_LAUNCH_CHECK();
 
   hm_gram_eargs e;
