@@ -97,6 +97,10 @@ typedef struct hm_problem {
   const hm_model_desc* models_dev; /* [B] device array, or NULL to use `model_host` (B must be 1)   */
   hm_model_desc model_host;
   hm_tracer tracers[8];
+  /* optional non-linear halo bias (power_spectrum(beta=), model._I_beta, pyhalomodel.py:546-571) */
+  const double* beta_dev;       /* [G][nk][nM][nM] beta_NL(k, M1, M2), or NULL                              */
+  int32_t beta_do_I11;          /* module switch do_I11      (pyhalomodel.py:45)                             */
+  int32_t beta_do_I12_I21;      /* module switch do_I12_I21  (pyhalomodel.py:46)                             */
 } hm_problem;
 #define HM_MAX_TRACERS 8
 

@@ -370,17 +370,38 @@ def _two_halo_integral(hm, M, nu, W, mass, A):
     return I*hm.rhom
 
 
-def _two_halo(hm, Pk_lin, M, nu, Wu, Wv, mass_u, mass_v, A):
-    """pyhalomodel.py:515-524 (beta=None branch: I_NL = 0.)"""
+DO_I11 = True        # module switches of pyhalomodel.py:45-46
+DO_I12_I21 = True
+
+
+def _beta_integral(hm, beta, M, nu, Wu, Wv, mass_u, mass_v, A):
+    """Non-linear halo bias double integral, pyhalomodel.py:546-571 (np.trapz is np.trapezoid in numpy >= 2)."""
+    g, b = mass_function_nu(hm, nu), linear_bias_nu(hm, nu)
+    integrand = beta*np.outer(Wu, Wv)*np.outer(g, g)*np.outer(b, b)/np.outer(M, M)
+    integral = np.trapezoid(np.trapezoid(integrand, nu), nu)             # utility.trapz2d, utility.py:46-52
+    if DO_I11 and mass_u and mass_v:
+        integral += beta[0, 0]*(A**2)*Wu[0]*Wv[0]/M[0]**2
+    if DO_I12_I21 and mass_u:
+        integral += (A*Wu[0]/M[0])*np.trapezoid(beta[0, :]*Wv*g*b/M, nu)
+    if DO_I12_I21 and mass_v:
+        integral += (A*Wv[0]/M[0])*np.trapezoid(beta[:, 0]*Wu*g*b/M, nu)
+    return integral*hm.rhom**2
+
+
+def _two_halo(hm, Pk_lin, M, nu, Wu, Wv, mass_u, mass_v, A, beta=None):
+    """pyhalomodel.py:515-524"""
+    I_NL = 0. if beta is None else _beta_integral(hm, beta, M, nu, Wu, Wv, mass_u, mass_v, A)
     Iu = _two_halo_integral(hm, M, nu, Wu, mass_u, A)
     Iv = _two_halo_integral(hm, M, nu, Wv, mass_v, A)
-    return (Iu*Iv+0.)*Pk_lin
+    return (Iu*Iv+I_NL)*Pk_lin
 
 
-def power_spectrum(hm: HaloModel, k, Pk_lin, M, sigmaM, profiles: dict, simple_twohalo=False,
+def power_spectrum(hm: HaloModel, k, Pk_lin, M, sigmaM, profiles: dict, beta=None, simple_twohalo=False,
                    subtract_shotnoise=True, correct_discrete=True, k_trunc=None):
-    """pyhalomodel.py:361-513 with beta=None.  Returns (Pk_2h, Pk_1h, Pk_hm) dictionaries keyed 'u-v'
+    """pyhalomodel.py:361-513.  Returns (Pk_2h, Pk_1h, Pk_hm) dictionaries keyed 'u-v'
     for every ordered pair; the lower-triangle keys alias the upper-triangle arrays (:503-507)."""
+    if simple_twohalo and (beta is not None):
+        raise ValueError('A simple two-halo term is not compatible with non-linear halo bias')
     if not is_increasing(M):
         raise ValueError('Halo mass array must be increasing monotonically')
     if not isinstance(profiles, dict):
@@ -411,7 +432,8 @@ def power_spectrum(hm: HaloModel, k, Pk_lin, M, sigmaM, profiles: dict, simple_t
             for ik in range(len(Pk_lin)):                                                   # :453-480
                 if not simple_twohalo:
                     p2h[ik] = _two_halo(hm, Pk_lin[ik], M, nu, pu.Wk[ik, :], pv.Wk[ik, :],
-                                        pu.mass_tracer, pv.mass_tracer, A)
+                                        pu.mass_tracer, pv.mass_tracer, A,
+                                        beta=None if beta is None else beta[ik, :, :])
                 if nu_name == nv_name:
                     if correct_discrete and pu.discrete_tracer:
                         fac = pu.amplitude*(pu.amplitude-1.)

@@ -37,12 +37,13 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
 // ---------------------------------------------------------------------------------------------------------------
 // Workspace layout (doubles):
 //   weights [B][NW][nMp]            per-mass weight vectors
-//   scal    [B][HM_NSCAL]           A, rhom
+//   scal    [B][HM_NSCAL]           A, rhom, w2[0], -, c_p[0] (8): the last two feed the beta_NL edge terms
+//   inl     [B][S][nk]              non-linear-bias two-halo term I_NL (only when beta is given)
 //   cpart   [B][nchunks][2*HM_MAXP] per-mass-chunk partial sums of the shot-noise and simple-two-halo integrals
 //   partial [B][nparts][nk][NW]     partial row sums over mass sub-ranges written by the quadrature kernel
 //                                   (streaming kernel: one part per consumer warp per 512-mass slice)
 // ---------------------------------------------------------------------------------------------------------------
-#define HM_NSCAL 4
+#define HM_NSCAL 12
 #define HM_WCHUNK 256        // masses per CTA of the weights kernel
 #define HM_MC 512            // masses per slice of the streaming kernel (256 consumer threads x double2)
 #define HM_CONSUMER_WARPS 8
@@ -51,7 +52,7 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
 struct hm_layout {
   int P, S, NW, nMp, nchunks, nslices, nparts;
   bool stream;
-  size_t B, scal_offset, cpart_offset, partial_offset, total_bytes;
+  size_t B, scal_offset, cpart_offset, partial_offset, inl_offset, total_bytes;
 };
 
 static bool hm_can_stream(const hm_problem* pr) {
@@ -78,7 +79,8 @@ static hm_layout hm_make_layout(const hm_problem* pr) {
   L.scal_offset = align(L.B * (size_t)L.NW * (size_t)L.nMp);
   L.cpart_offset = align(L.scal_offset + L.B * HM_NSCAL);
   L.partial_offset = align(L.cpart_offset + L.B * (size_t)L.nchunks * 2 * HM_MAXP);
-  L.total_bytes = (L.partial_offset + L.B * (size_t)L.nparts * L.NW * (size_t)pr->nk) * sizeof(double);
+  L.inl_offset = align(L.partial_offset + L.B * (size_t)L.nparts * L.NW * (size_t)pr->nk);
+  L.total_bytes = (L.inl_offset + (pr->beta_dev ? L.B * (size_t)L.S * pr->nk : 0)) * sizeof(double);
   return L;
 }
 
@@ -189,6 +191,9 @@ __global__ void __launch_bounds__(HM_WCHUNK) hm_weights_kernel(const hm_weights_
     double* sc = a.scal + (size_t)b * HM_NSCAL;
     sc[0] = A;
     sc[1] = d.rhom;
+    sc[2] = w2_plain;                                   // w2[0] and c_p[0]: edge terms of the beta_NL integral
+#pragma unroll
+    for (int p = 0; p < HM_MAXP; ++p) sc[4 + p] = cW[p];
     if (a.lowmass) a.lowmass[b] = A;
   }
 }
@@ -505,6 +510,129 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Non-linear halo bias: I_NL(k) = rhom^2 [ trapz2d(beta W1 W2 g1 g2 b1 b2 / M1 M2) + low-mass edge terms ]
+// (model._I_beta, pyhalomodel.py:546-571).  With a_p[m] = w2[m] W_p(k,m) the double trapezoid is the bilinear form
+// a_u^T beta_k a_v, and the edge terms are L_u (beta_k[0,:] . a_v) (I12), L_v (beta_k[:,0] . a_u) (I21) and
+// L_u L_v beta_k[0,0] (I11) with L_p = mass_p A W_p(k,M0)/M0.  Pure HBM streaming of beta[k] (nM x nM doubles per
+// wavenumber): one CTA per (model, k), a warp per matrix row, the P vectors a_v staged in shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+struct hm_beta_args {
+  int nk, nM, nMp, F, do_I11, do_I12_I21;
+  const double* M;
+  const double* beta;                // [G][nk][nM][nM]
+  const double* gridW[HM_MAXP];
+  int mass[HM_MAXP];
+  const double* weights;
+  const double* scal;
+  double* inl;                       // [B][S][nk]
+};
+
+template <int P>
+__global__ void __launch_bounds__(256) hm_beta2h_kernel(const hm_beta_args a) {
+  constexpr int S = P * (P + 1) / 2, NW = P + S;
+  extern __shared__ __align__(16) double bsm[];
+  double* av = bsm;                                     // [P][nMp]  a_p[m] = w2[m] W_p(k,m) (no low-mass term)
+  double* red = av + (size_t)P * a.nMp;                 // [8 warps][S + P]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ik = blockIdx.x % a.nk, b = blockIdx.x / a.nk, smp = b / a.F;
+  const double* sc = a.scal + (size_t)b * HM_NSCAL;
+  const double A = sc[0], rhom = sc[1], w20 = sc[2], M0 = a.M[0];
+  const double* w = a.weights + (size_t)b * NW * a.nMp;
+  const size_t goff = ((size_t)smp * a.nk + ik) * (size_t)a.nM;
+  for (int m = tid; m < a.nMp; m += blockDim.x)
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      double v = 0.;
+      if (m < a.nM) {
+        const double g = a.gridW[p][goff + m];
+        v = (m == 0) ? (w20 * sc[4 + p]) * g : w[(size_t)p * a.nMp + m] * g;   // e_p[0] carries the low-mass term: rebuild a_p[0]
+      }
+      av[(size_t)p * a.nMp + m] = v;
+    }
+  __syncthreads();
+
+  const double* bk = a.beta + ((size_t)smp * a.nk + ik) * (size_t)a.nM * a.nM;
+  double pair_acc = 0.;      // lane s < S: sum_m1 a_u[m1] y_v[m1];  lane S+p: sum_m1 beta[m1,0] a_p[m1]  (column 0)
+  double y0 = 0.;            // lane p < P of warp 0: y_p at row 0 = beta[0,:] . a_p
+  int pu = 0, pv = 0;
+  {
+    int cnt = 0;
+#pragma unroll
+    for (int uu = 0; uu < P; ++uu)
+#pragma unroll
+      for (int vv = uu; vv < P; ++vv) {
+        if (cnt == lane) { pu = uu; pv = vv; }
+        ++cnt;
+      }
+    if (lane >= S && lane < S + P) pu = lane - S;
+  }
+  for (int m1 = warp; m1 < a.nM; m1 += 8) {
+    const double* row = bk + (size_t)m1 * a.nM;
+    double y[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) y[p] = 0.;
+    for (int c = lane; c < a.nM; c += 32) {
+      const double bv = hm_ldg_stream1(row + c);
+#pragma unroll
+      for (int p = 0; p < P; ++p) y[p] = fma(bv, av[(size_t)p * a.nMp + c], y[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) y[p] = hm_warp_sum(y[p]);        // every lane holds y_p[m1] = beta[m1,:] . a_p
+    double yv = 0.;
+#pragma unroll
+    for (int p = 0; p < P; ++p) yv = (p == pv) ? y[p] : yv;
+    if (lane < S) pair_acc = fma(av[(size_t)pu * a.nMp + m1], yv, pair_acc);
+    else if (lane < S + P) pair_acc = fma(row[0], av[(size_t)pu * a.nMp + m1], pair_acc);
+    if (m1 == 0) {
+#pragma unroll
+      for (int p = 0; p < P; ++p) y0 = (p == lane) ? y[p] : y0;
+    }
+  }
+  if (lane < S + P) red[warp * (S + P) + lane] = pair_acc;
+  __shared__ double y0s[HM_MAXP];
+  if (warp == 0 && lane < P) y0s[lane] = y0;
+  __syncthreads();
+  if (tid < S) {
+    double tot = 0.;
+    for (int wi = 0; wi < 8; ++wi) tot += red[wi * (S + P) + tid];
+    int u = 0, v = 0, cnt = 0;
+#pragma unroll
+    for (int uu = 0; uu < P; ++uu)
+#pragma unroll
+      for (int vv = uu; vv < P; ++vv) {
+        if (cnt == tid) { u = uu; v = vv; }
+        ++cnt;
+      }
+    double col_u = 0.;
+    for (int wi = 0; wi < 8; ++wi) col_u += red[wi * (S + P) + S + u];
+    // L_p = A W_p(k, M0)/M0 for mass tracers (:560-570); W_p(k, M0) = c_p[0] grid_p[k, 0]
+    const double Lu = a.mass[u] ? A * (sc[4 + u] * a.gridW[u][goff]) / M0 : 0.;
+    const double Lv = a.mass[v] ? A * (sc[4 + v] * a.gridW[v][goff]) / M0 : 0.;
+    if (a.do_I11 && a.mass[u] && a.mass[v]) tot += bk[0] * Lu * Lv;                    // :559-560
+    if (a.do_I12_I21 && a.mass[u]) tot += Lu * y0s[v];                                 // :561-565  beta[0,:] with W_v
+    if (a.do_I12_I21 && a.mass[v]) tot += Lv * col_u;                                  // :566-570  beta[:,0] with W_u
+    a.inl[((size_t)b * S + tid) * a.nk + ik] = tot * rhom * rhom;                      // :571
+  }
+}
+
+template <int P>
+static int hm_launch_beta(const hm_beta_args& a, int B, cudaStream_t st) {
+  const size_t smem = ((size_t)P * a.nMp + 8 * (P * (P + 1) / 2 + P)) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_beta2h_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  if (smem > 200 * 1024) {
+    hm_set_error("beta_NL: %d tracers x %d masses do not fit in shared memory", P, a.nM);
+    return HM_ERR_INVALID;
+  }
+  hm_beta2h_kernel<P><<<B * a.nk, 256, smem, st>>>(a);
+  HM_LAUNCH_CHECK();
+  return HM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Epilogue: one thread per (model, wavenumber)                                          pyhalomodel.py:456-501
 // ---------------------------------------------------------------------------------------------------------------
 struct hm_epi_args {
@@ -516,6 +644,7 @@ struct hm_epi_args {
   const double* partial;
   const double* scal;
   const double* cpart;
+  const double* inl;         // [B][S][nk] or NULL
   int discrete[HM_MAXP];
   double* out;               // [B][S][3][nk]
 };
@@ -584,7 +713,8 @@ __global__ void __launch_bounds__(256) hm_epilogue_kernel(const hm_epi_args a) {
     }
     const double Iu = a.simple_twohalo ? scs[HM_MAXP + u] : fu * rhom;                         // :540-543
     const double Iv = a.simple_twohalo ? scs[HM_MAXP + v] : fv * rhom;
-    const double p2h = __dmul_rn(__dadd_rn(__dmul_rn(Iu, Iv), 0.), a.Pk_lin[(size_t)smp * a.nk + krow]);   // :524
+    const double I_NL = a.inl ? a.inl[((size_t)b * S + s) * a.nk + krow] : 0.;                 // :520-521
+    const double p2h = __dmul_rn(__dadd_rn(__dmul_rn(Iu, Iv), I_NL), a.Pk_lin[(size_t)smp * a.nk + krow]);   // :524
     double p1h = f1 * rhom;                                                                    // :532
     if (u == v && a.discrete[u]) {                                                             // :484-491
       if (a.correct_discrete && !a.subtract_shotnoise) p1h += scs[u];
@@ -611,6 +741,8 @@ static int hm_validate(const hm_problem* pr) {
   HM_REQUIRE(pr->n_samples >= 1 && pr->models_per_sample >= 1, "need at least one sample and one model per sample");
   HM_REQUIRE(pr->M_dev && pr->sigma_dev && pr->Pk_lin_dev, "M, sigma and Pk_lin are required");
   HM_REQUIRE(pr->k_trunc <= 0. || pr->k_dev, "k is required when k_trunc is set");
+  HM_REQUIRE(!(pr->beta_dev && pr->simple_twohalo), "a simple two-halo term is not compatible with beta_NL");
+  HM_REQUIRE(!pr->beta_dev || pr->n_tracers <= 6, "beta_NL is supported for up to 6 tracers per call");
   const long long B = (long long)pr->n_samples * pr->models_per_sample;
   HM_REQUIRE(B <= 65535, "at most 65535 models per call");
   HM_REQUIRE(pr->models_dev || B == 1, "models_dev is required for more than one model");
@@ -755,6 +887,12 @@ extern "C" int hm_mass_quadrature_stages(const hm_problem* pr, double* out_dev, 
   e.simple_twohalo = pr->simple_twohalo; e.subtract_shotnoise = pr->subtract_shotnoise;
   e.correct_discrete = pr->correct_discrete; e.k_trunc = pr->k_trunc; e.k = pr->k_dev; e.Pk_lin = pr->Pk_lin_dev;
   e.partial = a.partial; e.scal = (const double*)ws + L.scal_offset; e.cpart = (const double*)ws + L.cpart_offset;
+  e.inl = pr->beta_dev ? (const double*)ws + L.inl_offset : nullptr;
+  hm_beta_args bt;
+  bt.nk = pr->nk; bt.nM = pr->nM; bt.nMp = L.nMp; bt.F = pr->models_per_sample;
+  bt.do_I11 = pr->beta_do_I11; bt.do_I12_I21 = pr->beta_do_I12_I21; bt.M = pr->M_dev; bt.beta = pr->beta_dev;
+  for (int p = 0; p < HM_MAXP; ++p) { bt.gridW[p] = a.gridW[p]; bt.mass[p] = (p < L.P) ? pr->tracers[p].mass_tracer : 0; }
+  bt.weights = a.weights; bt.scal = e.scal; bt.inl = (double*)ws + L.inl_offset;
   for (int p = 0; p < HM_MAXP; ++p) e.discrete[p] = (p < L.P) ? pr->tracers[p].discrete_tracer : 0;
   e.out = out_dev;
   cudaStream_t st = (cudaStream_t)stream;
@@ -763,6 +901,7 @@ extern "C" int hm_mass_quadrature_stages(const hm_problem* pr, double* out_dev, 
     if (stages & 1) {                                                              \
       rc = L.stream ? hm_launch_stream<PP, RR>(a, st) : hm_launch_fallback<PP, RR>(a, aligned, sep, st); \
       if (rc) return rc;                                                           \
+      if (pr->beta_dev && (rc = hm_launch_beta<PP>(bt, (int)L.B, st))) return rc;  \
     }                                                                              \
     return (stages & 2) ? hm_launch_epilogue<PP>(e, st) : HM_OK;
   switch (L.P) {

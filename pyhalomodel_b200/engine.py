@@ -160,7 +160,8 @@ class PowerSpectrumPlan:
     no host work in the steady state; CUDA-graph friendly)."""
 
     def __init__(self, k, Pk_lin, M, sigma, tracers, models, models_per_sample=1, simple_twohalo=False,
-                 subtract_shotnoise=True, correct_discrete=True, k_trunc=None):
+                 subtract_shotnoise=True, correct_discrete=True, k_trunc=None, beta=None, do_I11=True,
+                 do_I12_I21=True):
         self.k, self.M = to_dev(k), to_dev(M)
         nk, nM = self.k.shape[0], self.M.shape[0]
         self.Pk_lin, self.sigma = to_dev(Pk_lin), to_dev(sigma)
@@ -172,6 +173,15 @@ class PowerSpectrumPlan:
         if tuple(self.Pk_lin.shape) != (G, nk) or self.sigma.shape[1] != nM:
             raise ValueError('Pk_lin must be [G, nk] and sigma [G, nM]')
         P = len(tracers)
+        self.beta = None
+        if beta is not None:    # beta_NL(k, M1, M2) per sample (pyhalomodel.py:372, :546-571)
+            self.beta = to_dev(beta)
+            if self.beta.dim() == 3:
+                self.beta = self.beta[None]
+            if tuple(self.beta.shape) != (G, nk, nM, nM):
+                raise ValueError('beta must be [G, nk, nM, nM]')
+            if P > 6:
+                raise NotImplementedError('beta_NL is supported for up to 6 tracers per call')
         if not 1 <= P <= _lib.HM_MAX_TRACERS:
             raise ValueError('between 1 and %d tracers are supported by the quadrature path' % _lib.HM_MAX_TRACERS)
         B = G*models_per_sample
@@ -225,6 +235,9 @@ class PowerSpectrumPlan:
             ct.normalisation_dev = norm.data_ptr()
             self.keep.append(norm)
             ct.grid_mode, ct.mass_tracer, ct.discrete_tracer = int(t.mode), int(t.mass_tracer), int(t.discrete_tracer)
+        if self.beta is not None:
+            pr.beta_dev = self.beta.data_ptr()
+        pr.beta_do_I11, pr.beta_do_I12_I21 = int(bool(do_I11)), int(bool(do_I12_I21))
         self.problem = pr
         nbytes = lib().hm_power_spectrum_workspace(C.byref(pr))
         dev = self.k.device

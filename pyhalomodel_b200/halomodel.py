@@ -30,6 +30,9 @@ Dv_rel_tol = 1e-3
 Tinker_z_dep = False    # redshift-dependent Tinker et al. (2010) parameters (pyhalomodel.py:20, :163-167)
 Tinker_PBS = False      # peak-background-split bias for Tinker et al. (2010) (pyhalomodel.py:22, :264-271)
 halo_integration = 'trapezoid'    # the only mass integrator with a parity oracle (pyhalomodel.py:27)
+# beta_NL (pyhalomodel.py:44-46)
+do_I11 = True      # add the low-M1 and low-M2 portion of the beta_NL integral
+do_I12_I21 = True  # add the low-M1 or low-M2 portions
 
 _FAMILY = {'Press & Schecter (1974)': _lib.PS74, 'Sheth & Tormen (1999)': _lib.ST99,
            'Sheth, Mo & Tormen (2001)': _lib.SMT01, 'Tinker et al. (2010)': _lib.TINKER10,
@@ -226,8 +229,8 @@ class model():
                        subtract_shotnoise=True, correct_discrete=True, k_trunc=None, verbose=False) -> tuple:
         '''
         Halo-model power spectra; returns the two-halo, one-halo and total dictionaries keyed 'u-v' for every
-        ordered pair of profiles (pyhalomodel.py:361-513).  Arguments as in the reference.  `beta`
-        (non-linear halo bias) is not on the B200 path yet and raises NotImplementedError.
+        ordered pair of profiles (pyhalomodel.py:361-513).  Arguments as in the reference, including `beta`
+        (beta_NL(k, M1, M2), the non-linear halo bias of pyhalomodel.py:546-571; up to 6 profiles per call).
         '''
         if verbose:
             t_start = time()
@@ -244,9 +247,7 @@ class model():
                 raise ValueError('k arrays must all be identical to those in profiles')
             if np.shape(Mh) != np.shape(prof.M) or (Mh != prof.M).all():
                 raise ValueError('Mass arrays must be identical to those in profiles')
-        if beta is not None:
-            raise NotImplementedError('beta_NL (pyhalomodel.py:546-571) is a "next" row of the B200 build')
-        on_dev = _wants_device(k, Pk_lin, M, sigmaM)
+        on_dev = _wants_device(k, Pk_lin, M, sigmaM, beta)
         names = list(profiles.keys())
         tracers = [prof._tracer() for prof in profiles.values()]
         flags = dict(simple_twohalo=simple_twohalo, subtract_shotnoise=subtract_shotnoise,
@@ -254,9 +255,12 @@ class model():
         if len(names) > _lib.HM_MAX_TRACERS:    # many tracers: Gram contraction on the FP64 tensor cores
             if len(names) > _lib.HM_GRAM_MAX_TRACERS:
                 raise NotImplementedError('more than %d tracers per call' % _lib.HM_GRAM_MAX_TRACERS)
+            if beta is not None:
+                raise NotImplementedError('beta_NL with more than %d tracers per call' % _lib.HM_MAX_TRACERS)
             plan = engine.GramPlan(k, Pk_lin, M, sigmaM, tracers, [self.descriptor()], **flags)
         else:
-            plan = engine.PowerSpectrumPlan(k, Pk_lin, M, sigmaM, tracers, [self.descriptor()], **flags)
+            plan = engine.PowerSpectrumPlan(k, Pk_lin, M, sigmaM, tracers, [self.descriptor()], beta=beta,
+                                            do_I11=do_I11, do_I12_I21=do_I12_I21, **flags)
         out, lowmass = plan.run()
         if on_dev:
             res, A = out[0], float(lowmass[0].item())

@@ -252,6 +252,41 @@ def golden_power_c2_small():
          **{a: np.array(b) for a, b in avg.items()}, **flatten('P', P2, P1, PH, ['m', 'g', 'p']))
 
 
+def synthetic_beta(k, M):
+    """A smooth, deliberately asymmetric beta_NL(k, M1, M2) so that row/column mix-ups are visible."""
+    lm = np.log10(M)
+    x1, x2 = (lm[:, None]-13.)/2., (lm[None, :]-13.)/2.
+    shape = 0.6*np.exp(-0.5*(x1-0.3)**2)*np.exp(-0.25*(x2+0.2)**2)+0.15*np.sin(1.3*x1)*np.cos(0.7*x2)-0.1*x1
+    kk = k[:, None, None]
+    return (kk/0.3)**0.8*np.exp(-(kk/1.5)**2)*shape[None, :, :]
+
+
+def golden_power_beta():
+    """Non-linear halo bias (beta_NL, pyhalomodel.py:546-571): Tinker10, m + g + p on 14 k x 56 M, with the two
+    module switches do_I11 / do_I12_I21 in all four states."""
+    nk, nM = 14, 56
+    k, M = syn.k_grid(nk, 1e-2, 3.), syn.M_grid(nM, 1e10, 1e16)
+    Om_m, z = 0.31, 0.25
+    Plin0 = syn.LinearSpectrum(Om_m, 0.69, 0.965, 0.81)
+    dc, Dv = dcDv(z, Om_m)
+    hmod = ref.model(z, Om_m, name=SHORT['Tinker2010'], Dv=Dv, dc=dc)
+    sig, R = sigma_of_M(hmod, M, Plin0, z)
+    Pk = Plin0(k, z)
+    profs, extra = build_profiles(hmod, k, M, sig, z, hod=syn.zheng_defaults(), with_pressure=True)
+    beta = synthetic_beta(k, M)
+    out = dict(k=k, M=M, Pk_lin=Pk, sigmaM=sig, z=np.array(z), Om_m=np.array(Om_m), dcDv=np.array([dc, Dv]),
+               rho_g=extra['rho_g'], beta=beta)
+    for i11 in (True, False):
+        for i12 in (True, False):
+            ref.do_I11, ref.do_I12_I21 = i11, i12
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                P2, P1, PH = hmod.power_spectrum(k, Pk, M, sig, profs, beta=beta)
+            out.update(flatten('I11_%d_I12_%d' % (i11, i12), P2, P1, PH, ['m', 'g', 'p']))
+    ref.do_I11, ref.do_I12_I21 = True, True
+    save('power_beta.npz', **out)
+
+
 if __name__ == '__main__':
     golden_massfn()
     golden_windows()
@@ -260,3 +295,4 @@ if __name__ == '__main__':
     golden_power_families()
     golden_power_flags()
     golden_power_c2_small()
+    golden_power_beta()

@@ -389,3 +389,37 @@ def test_multiplicity_and_mass_function(halo):
     want = orc.mass_function_nu(om, nu)*(-(nu/6.)*2.*d)
     np.testing.assert_allclose(F, want, rtol=1e-8)
     np.testing.assert_allclose(hmod.mass_function(M, sig), want*hmod.rhom/M**2, rtol=1e-8)
+
+
+def test_power_beta_nl_golden(halo):
+    """beta_NL two-halo term (model._I_beta, pyhalomodel.py:546-571) against the live-reference golden, in the four
+    states of the module switches do_I11 / do_I12_I21, plus the oracle on a ragged, odd-nM case."""
+    g = load_golden('power_beta.npz')
+    dc, Dv = g['dcDv']
+    hmod = halo.model(float(g['z']), float(g['Om_m']), name=orc.TINKER10, Dv=Dv, dc=dc)
+    profs = _profiles(halo, hmod, g, hod=syn.zheng_defaults(), pressure=True)
+    try:
+        for i11 in (True, False):
+            for i12 in (True, False):
+                halo.do_I11, halo.do_I12_I21 = i11, i12
+                out = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs, beta=g['beta'])
+                _check(out, g, 'I11_%d_I12_%d' % (i11, i12), ['m', 'g', 'p'])
+    finally:
+        halo.do_I11, halo.do_I12_I21 = True, True
+    # one-halo terms do not see beta; the two-halo term reduces to the standard one for beta = 0
+    base = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs)
+    zero = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs, beta=np.zeros_like(g['beta']))
+    for key in base[0]:
+        assert np.array_equal(out[1][key], base[1][key])
+        assert np.array_equal(zero[0][key], base[0][key])
+    # odd nM (fallback quadrature kernel) and two tracers against the oracle
+    cs = _synthetic_case(9, 45, z=0.6)
+    rng = np.random.default_rng(11)
+    beta = rng.normal(0., 0.3, size=(9, 45, 45))
+    om = orc.make_model(cs['z'], cs['Om_m'], name=orc.ST99, Dv=cs['Dv'], dc=cs['dc'])
+    hm2 = halo.model(cs['z'], cs['Om_m'], name=orc.ST99, Dv=cs['Dv'], dc=cs['dc'])
+    want = orc.power_spectrum(om, cs['k'], cs['Pk_lin'], cs['M'], cs['sigmaM'], _oracle_profiles(om, cs, [syn.zheng_defaults()], False), beta=beta)
+    got = hm2.power_spectrum(cs['k'], cs['Pk_lin'], cs['M'], cs['sigmaM'], _gpu_profiles(halo, hm2, cs, [syn.zheng_defaults()], False), beta=beta)
+    for t in range(3):
+        for key in want[t]:
+            assert_spectra_close(got[t][key], want[t][key], rtol=RTOL, what='beta odd %s term %d' % (key, t))

@@ -191,3 +191,21 @@ def test_error_behaviour():
         orc.power_spectrum(hm, g['k']*2., g['Pk_lin'], g['M'], g['sigmaM'], profs)
     with pytest.raises(ValueError):
         orc.Profile.Fourier(g['k'], g['M'], np.ones((3, 3)))
+
+
+def test_power_beta_nl():
+    """Non-linear halo bias (pyhalomodel.py:546-571) under the four states of do_I11 / do_I12_I21."""
+    g = load_golden('power_beta.npz')
+    dc, Dv = g['dcDv']
+    hm = orc.make_model(float(g['z']), float(g['Om_m']), name=orc.TINKER10, Dv=Dv, dc=dc)
+    profs = _profiles(hm, g, hod=syn.zheng_defaults(), pressure=True)
+    try:
+        for i11 in (True, False):
+            for i12 in (True, False):
+                orc.DO_I11, orc.DO_I12_I21 = i11, i12
+                out = orc.power_spectrum(hm, g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs, beta=g['beta'])
+                _check(*out, g, 'I11_%d_I12_%d' % (i11, i12), ['m', 'g', 'p'], rtol=1e-13)
+    finally:
+        orc.DO_I11, orc.DO_I12_I21 = True, True
+    with pytest.raises(ValueError):
+        orc.power_spectrum(hm, g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs, beta=g['beta'], simple_twohalo=True)
