@@ -523,6 +523,7 @@ __global__ void __launch_bounds__(256) hm_gram_epilogue_kernel(const hm_gram_ear
   o[0] = p2h;
   o[a.nk] = p1h;
   o[2 * (size_t)a.nk] = __dadd_rn(p2h, p1h);                                                           // :500-501
+  __threadfence_system();      // `out` may be a peer GPU's buffer (fused gather): see hm_epilogue_kernel
 }
 
 // ---------------------------------------------------------------------------------------------------------------

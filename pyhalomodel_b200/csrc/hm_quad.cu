@@ -729,6 +729,9 @@ __global__ void __launch_bounds__(256) hm_epilogue_kernel(const hm_epi_args a) {
     o[a.nk] = p1h;
     o[2 * (size_t)a.nk] = __dadd_rn(p2h, p1h);                                                 // :500-501
   }
+  // `out` may live on a peer GPU (sweep.PeerGatherBuffer: the gather is fused into these stores): make them
+  // visible system-wide before the kernel retires, so that a barrier after it is enough for the reader
+  __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -52,6 +52,35 @@ def gather_spectra(local: torch.Tensor, n_items: int, group=None) -> torch.Tenso
     return torch.cat([recv[r*nmax:r*nmax+(b-a)] for r, (a, b) in enumerate(bounds)], dim=0)
 
 
+class PeerGatherBuffer:
+    """Gather fused into the kernels: a symmetric (peer-mapped over NVLink/NVSwitch) results buffer
+    [world, slots, *block] lives on every rank; `slot(i)` returns THIS rank's block of slot i inside the ROOT
+    rank's copy, so a kernel given that tensor as its output (PowerSpectrumPlan.run(out=...)) stores its spectra
+    straight into the root's memory with peer stores -- no collective kernel, nothing to overlap, and the SMs
+    stay with the quadrature.  After every rank has synchronised its stream and passed a barrier, the root's
+    `local` tensor holds everybody's results.  The NCCL path (gather_spectra) is the baseline it is checked against."""
+
+    def __init__(self, block_shape, slots, dtype=torch.float64, root=0, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank, self.root = dist.get_world_size(group), dist.get_rank(group), root
+        self.shape = (self.world, slots)+tuple(block_shape)
+        dev = torch.device('cuda', torch.cuda.current_device())
+        self.local = symm_mem.empty(self.shape, dtype=dtype, device=dev)
+        self.handle = symm_mem.rendezvous(self.local, group=self.group)
+        self.on_root = self.handle.get_buffer(root, self.shape, dtype)      # the root's buffer, mapped here
+        self.slots = slots
+
+    def slot(self, i):
+        return self.on_root[self.rank, i % self.slots]
+
+    def finish(self):
+        """Make every rank's peer stores visible on the root: stream sync + barrier."""
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        return self.local if self.rank == self.root else None
+
+
 class OverlappedGather:
     """Gather equal-sized per-rank result blocks on a side stream so the collective of step n overlaps the
     kernels of step n+1 (the spectra are tiny next to the grids: the cost to hide is NCCL launch latency).
