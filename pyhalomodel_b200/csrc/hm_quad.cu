@@ -730,8 +730,10 @@ __global__ void __launch_bounds__(256) hm_epilogue_kernel(const hm_epi_args a) {
     o[2 * (size_t)a.nk] = __dadd_rn(p2h, p1h);                                                 // :500-501
   }
   // `out` may live on a peer GPU (sweep.PeerGatherBuffer: the gather is fused into these stores): make them
-  // visible system-wide before the kernel retires, so that a barrier after it is enough for the reader
-  __threadfence_system();
+  // visible system-wide before the kernel retires, so that a barrier after it is enough for the reader.  Fences
+  // are cumulative: one system-scope fence by a thread that has synchronised with the whole CTA covers its stores.
+  __syncthreads();
+  if (tid == 0) __threadfence_system();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
