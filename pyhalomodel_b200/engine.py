@@ -18,8 +18,14 @@ from ._lib import GramProblem, HaloB200Error, ModelDesc, Problem, check, lib
 F64 = torch.float64
 
 
+_HAVE_CUDA = None
+
+
 def device():
-    if not torch.cuda.is_available():
+    global _HAVE_CUDA
+    if _HAVE_CUDA is None:
+        _HAVE_CUDA = bool(torch.cuda.is_available())
+    if not _HAVE_CUDA:
         raise HaloB200Error('no CUDA device visible: pyhalomodel_b200 runs on B200 only and has no CPU fallback')
     return torch.device('cuda', torch.cuda.current_device())
 
@@ -31,6 +37,10 @@ def is_host(x):
 
 def to_dev(x, shape=None):
     """numpy / list / scalar / torch tensor  ->  contiguous float64 CUDA tensor (a copy only when needed)."""
+    if isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == F64 and x.is_contiguous():
+        if shape is not None and tuple(x.shape) != tuple(shape):
+            raise ValueError('expected shape %s, got %s' % (tuple(shape), tuple(x.shape)))
+        return x
     dev = device()
     if isinstance(x, torch.Tensor):
         t = x.to(device=dev, dtype=F64, non_blocking=True)
@@ -43,6 +53,21 @@ def to_dev(x, shape=None):
     if shape is not None and tuple(t.shape) != tuple(shape):
         raise ValueError('expected shape %s, got %s' % (tuple(shape), tuple(t.shape)))
     return t
+
+
+def to_dev_many(arrays):
+    """Upload several small host arrays with ONE host-to-device copy (latency matters more than bytes for the
+    per-call vectors k, P_lin, M, sigma(M)); entries that already live on the device pass through."""
+    host = [(i, np.ascontiguousarray(np.asarray(a, dtype=np.float64)).reshape(-1)) for i, a in enumerate(arrays)
+            if not (isinstance(a, torch.Tensor) and a.is_cuda)]
+    out = [to_dev(a) if (isinstance(a, torch.Tensor) and a.is_cuda) else None for a in arrays]
+    if host:
+        flat = torch.from_numpy(np.concatenate([h for _, h in host])).to(device(), non_blocking=True)
+        off = 0
+        for i, h in host:
+            out[i] = flat[off:off+h.size].reshape(np.shape(arrays[i]))
+            off += h.size
+    return out
 
 
 def to_host(t):
@@ -162,9 +187,12 @@ class PowerSpectrumPlan:
     def __init__(self, k, Pk_lin, M, sigma, tracers, models, models_per_sample=1, simple_twohalo=False,
                  subtract_shotnoise=True, correct_discrete=True, k_trunc=None, beta=None, do_I11=True,
                  do_I12_I21=True):
-        self.k, self.M = to_dev(k), to_dev(M)
+        P = len(tracers)
+        # per-call vectors and scalar normalisations travel in one host-to-device copy
+        scalar_norms = [t.normalisation for t in tracers if np.isscalar(t.normalisation)]
+        self.k, self.M, self.Pk_lin, self.sigma, norms_dev = to_dev_many(
+            [k, M, Pk_lin, sigma, np.asarray(scalar_norms, dtype=np.float64)])
         nk, nM = self.k.shape[0], self.M.shape[0]
-        self.Pk_lin, self.sigma = to_dev(Pk_lin), to_dev(sigma)
         if self.Pk_lin.dim() == 1:
             self.Pk_lin = self.Pk_lin[None, :]
         if self.sigma.dim() == 1:
@@ -172,7 +200,7 @@ class PowerSpectrumPlan:
         G = self.sigma.shape[0]
         if tuple(self.Pk_lin.shape) != (G, nk) or self.sigma.shape[1] != nM:
             raise ValueError('Pk_lin must be [G, nk] and sigma [G, nM]')
-        P = len(tracers)
+        n_scalar = 0
         self.beta = None
         if beta is not None:    # beta_NL(k, M1, M2) per sample (pyhalomodel.py:372, :546-571)
             self.beta = to_dev(beta)
@@ -231,7 +259,12 @@ class PowerSpectrumPlan:
                 ct.variance_dev = var.data_ptr()
                 self.keep.append(var)
             norm = t.normalisation
-            norm = to_dev(np.full(B, float(norm))) if np.isscalar(norm) else to_dev(norm).reshape(B)
+            if np.isscalar(norm):
+                norm = norms_dev[n_scalar:n_scalar+1]
+                n_scalar += 1
+                norm = norm if B == 1 else norm.expand(B).contiguous()
+            else:
+                norm = to_dev(norm).reshape(B)
             ct.normalisation_dev = norm.data_ptr()
             self.keep.append(norm)
             ct.grid_mode, ct.mass_tracer, ct.discrete_tracer = int(t.mode), int(t.mass_tracer), int(t.discrete_tracer)
