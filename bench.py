@@ -212,7 +212,7 @@ def main():
 
     def step():
         if world > 1:
-            plan.run(out=peer.slot(step_no[0]))
+            plan.run(out=peer.slot(step_no[0]), peer=True)
             step_no[0] += 1
         else:
             plan.run()

@@ -101,6 +101,10 @@ typedef struct hm_problem {
   const double* beta_dev;       /* [G][nk][nM][nM] beta_NL(k, M1, M2), or NULL                              */
   int32_t beta_do_I11;          /* module switch do_I11      (pyhalomodel.py:45)                             */
   int32_t beta_do_I12_I21;      /* module switch do_I12_I21  (pyhalomodel.py:46)                             */
+  /* out_dev lives on a peer GPU (gather fused into the epilogue's stores): the epilogue then ends with a
+   * system-scope fence so that a barrier after the kernel is enough for the reader */
+  int32_t output_is_peer;
+  int32_t reserved2;
 } hm_problem;
 #define HM_MAX_TRACERS 8
 
@@ -168,6 +172,8 @@ typedef struct hm_gram_problem {
   const hm_model_desc* models_dev;
   hm_model_desc model_host;
   const hm_tracer* tracers;      /* host array [n_tracers] */
+  int32_t output_is_peer;        /* as in hm_problem */
+  int32_t reserved2;
 } hm_gram_problem;
 size_t hm_gram_workspace(const hm_gram_problem* prob);
 int hm_gram_power_spectrum(const hm_gram_problem* prob, double* out_dev, double* lowmass_dev,

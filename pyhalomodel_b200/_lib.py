@@ -30,7 +30,8 @@ class Problem(C.Structure):
                 ('correct_discrete', C.c_int32), ('k_trunc', C.c_double), ('k_dev', C.c_void_p),
                 ('M_dev', C.c_void_p), ('sigma_dev', C.c_void_p), ('Pk_lin_dev', C.c_void_p),
                 ('models_dev', C.c_void_p), ('model_host', ModelDesc), ('tracers', Tracer*HM_MAX_TRACERS),
-                ('beta_dev', C.c_void_p), ('beta_do_I11', C.c_int32), ('beta_do_I12_I21', C.c_int32)]
+                ('beta_dev', C.c_void_p), ('beta_do_I11', C.c_int32), ('beta_do_I12_I21', C.c_int32),
+                ('output_is_peer', C.c_int32), ('reserved2', C.c_int32)]
 
 
 class GramProblem(C.Structure):
@@ -38,7 +39,8 @@ class GramProblem(C.Structure):
                 ('models_per_sample', C.c_int32), ('simple_twohalo', C.c_int32), ('subtract_shotnoise', C.c_int32),
                 ('correct_discrete', C.c_int32), ('k_trunc', C.c_double), ('k_dev', C.c_void_p),
                 ('M_dev', C.c_void_p), ('sigma_dev', C.c_void_p), ('Pk_lin_dev', C.c_void_p),
-                ('models_dev', C.c_void_p), ('model_host', ModelDesc), ('tracers', C.POINTER(Tracer))]
+                ('models_dev', C.c_void_p), ('model_host', ModelDesc), ('tracers', C.POINTER(Tracer)),
+                ('output_is_peer', C.c_int32), ('reserved2', C.c_int32)]
 
 
 HM_GRAM_MAX_TRACERS = 64

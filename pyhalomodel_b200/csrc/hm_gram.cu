@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
 // ---------------------------------------------------------------------------------------------------------------
 struct hm_gram_eargs {
   int nk, nM, nMp, P, S, NW, F, nparts, B;
-  int simple_twohalo, subtract_shotnoise, correct_discrete;
+  int simple_twohalo, subtract_shotnoise, correct_discrete, fence_out;
   double k_trunc;
   size_t gw_stride;
   const double* k;
@@ -480,7 +480,7 @@ struct hm_gram_eargs {
 __global__ void __launch_bounds__(256) hm_gram_epilogue_kernel(const hm_gram_eargs a) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long per_model = (long long)a.S * a.nk;
-  if (gid >= per_model * a.B) return;
+  if (gid < per_model * a.B) {
   const int b = (int)(gid / per_model);
   const long long rem = gid - (long long)b * per_model;
   const int s = (int)(rem / a.nk), row = (int)(rem - (long long)s * a.nk);
@@ -523,7 +523,11 @@ __global__ void __launch_bounds__(256) hm_gram_epilogue_kernel(const hm_gram_ear
   o[0] = p2h;
   o[a.nk] = p1h;
   o[2 * (size_t)a.nk] = __dadd_rn(p2h, p1h);                                                           // :500-501
-  __threadfence_system();      // `out` may be a peer GPU's buffer (fused gather): see hm_epilogue_kernel
+  }
+  if (a.fence_out) {           // `out` is a peer GPU's buffer (fused gather): one cumulative system-scope fence
+    __syncthreads();           // per CTA, see hm_epilogue_kernel
+    if (threadIdx.x == 0) __threadfence_system();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -619,6 +623,7 @@ extern "C" int hm_gram_power_spectrum(const hm_gram_problem* pr, double* out_dev
   e.nparts = L.nparts; e.B = (int)L.B;
   e.simple_twohalo = pr->simple_twohalo; e.subtract_shotnoise = pr->subtract_shotnoise;
   e.correct_discrete = pr->correct_discrete; e.k_trunc = pr->k_trunc; e.gw_stride = L.gw_stride;
+  e.fence_out = pr->output_is_peer;
   e.k = pr->k_dev; e.M = pr->M_dev; e.Pk_lin = pr->Pk_lin_dev; e.partial = g.partial; e.gw = wsd;
   e.scal = w.scal; e.tscal = w.tscal;
   for (int p = 0; p < HM_GMAXP; ++p) {

@@ -637,7 +637,7 @@ static int hm_launch_beta(const hm_beta_args& a, int B, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------------
 struct hm_epi_args {
   int nk, B, F, P, NW, S, nparts, nchunks;
-  int simple_twohalo, subtract_shotnoise, correct_discrete;
+  int simple_twohalo, subtract_shotnoise, correct_discrete, fence_out;
   double k_trunc;
   const double* k;
   const double* Pk_lin;      // [G][nk]
@@ -732,8 +732,10 @@ __global__ void __launch_bounds__(256) hm_epilogue_kernel(const hm_epi_args a) {
   // `out` may live on a peer GPU (sweep.PeerGatherBuffer: the gather is fused into these stores): make them
   // visible system-wide before the kernel retires, so that a barrier after it is enough for the reader.  Fences
   // are cumulative: one system-scope fence by a thread that has synchronised with the whole CTA covers its stores.
-  __syncthreads();
-  if (tid == 0) __threadfence_system();
+  if (a.fence_out) {
+    __syncthreads();
+    if (tid == 0) __threadfence_system();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -891,6 +893,7 @@ extern "C" int hm_mass_quadrature_stages(const hm_problem* pr, double* out_dev, 
   e.nparts = L.nparts; e.nchunks = L.nchunks;
   e.simple_twohalo = pr->simple_twohalo; e.subtract_shotnoise = pr->subtract_shotnoise;
   e.correct_discrete = pr->correct_discrete; e.k_trunc = pr->k_trunc; e.k = pr->k_dev; e.Pk_lin = pr->Pk_lin_dev;
+  e.fence_out = pr->output_is_peer;
   e.partial = a.partial; e.scal = (const double*)ws + L.scal_offset; e.cpart = (const double*)ws + L.cpart_offset;
   e.inl = pr->beta_dev ? (const double*)ws + L.inl_offset : nullptr;
   hm_beta_args bt;

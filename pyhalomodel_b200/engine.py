@@ -288,12 +288,14 @@ class PowerSpectrumPlan:
         check(lib().hm_mass_quadrature_stages(C.byref(self.problem), _ptr(self.out), _ptr(self.workspace),
                                               self.workspace_bytes, _stream(), int(stages)))
 
-    def run(self, out=None):
+    def run(self, out=None, peer=False):
         """Enqueue both stages on the current stream; returns (out [B,S,3,nk], A [B]) device tensors.  `out` may be
-        a caller-owned contiguous float64 CUDA tensor of that shape (e.g. a slot of a sweep's results buffer)."""
+        a caller-owned contiguous float64 CUDA tensor of that shape (e.g. a slot of a sweep's results buffer);
+        peer=True says it lives on another GPU (sweep.PeerGatherBuffer), so the epilogue fences system-wide."""
         dst = self.out if out is None else out
         if out is not None and (tuple(out.shape) != tuple(self.out.shape) or out.dtype != F64 or not out.is_contiguous()):
             raise ValueError('out must be a contiguous float64 tensor of shape %s' % (tuple(self.out.shape),))
+        self.problem.output_is_peer = int(bool(peer))
         check(lib().hm_power_spectrum(C.byref(self.problem), _ptr(dst), _ptr(self.lowmass), _ptr(self.workspace),
                                       self.workspace_bytes, _stream()))
         return dst, self.lowmass

@@ -10,7 +10,7 @@ batch = workloads.build(4, 64, 256, ('m', 'g', 'p'), seed=100+rank, fiducial_fir
 plan = batch.plan()
 peer = sweep.PeerGatherBuffer(plan.out.shape, 3)
 for i in range(3):
-    plan.run(out=peer.slot(i))
+    plan.run(out=peer.slot(i), peer=True)
 root = peer.finish()
 mine = plan.run()[0].clone(); torch.cuda.synchronize()
 ref_all = sweep.gather_spectra(mine, world*4)
