@@ -46,7 +46,8 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'lts__t_bytes.sum', 'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_sector_hit_rate.pct',
         'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
-        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+        'sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_dynamic',
         'launch__occupancy_limit_shared_mem', 'launch__waves_per_multiprocessor', 'sm__cycles_elapsed.max']
 
@@ -70,7 +71,7 @@ def full(src, dst, traffic_json=None, batch=None):
                           capture_output=True, text=True).stdout
     ops = {}
     for line in sass.splitlines():
-        for op in ('UBLKCP', 'SYNCS', 'DFMA', 'DMUL', 'DADD', 'SHFL', 'LDS', 'LDG', 'STG', 'UTMALDG'):
+        for op in ('UBLKCP', 'SYNCS', 'DMMA', 'DFMA', 'DMUL', 'DADD', 'SHFL', 'LDS', 'LDG', 'STG', 'BAR', 'UTMALDG'):
             if (' '+op) in line or (','+op) in line or ('"'+op) in line:
                 ops[op] = ops.get(op, 0)+1
     out.append('## SASS mnemonics present (static count over the profiled kernels): '+json.dumps(ops))
