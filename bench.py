@@ -210,12 +210,16 @@ def main():
     peer = sweep.PeerGatherBuffer(plan.out.shape, max(K, W)) if world > 1 else None
     step_no = [0]
 
+    # consecutive steps are software-pipelined over two CUDA streams (double-buffered plans): the weights and
+    # epilogue kernels of one step run beside the persistent streaming kernel of the next (engine.PipelinedPlans)
+    pipe = engine.PipelinedPlans(batch.plan)
+
     def step():
         if world > 1:
-            plan.run(out=peer.slot(step_no[0]), peer=True)
+            pipe.submit(out=peer.slot(step_no[0]), peer=True)
             step_no[0] += 1
         else:
-            plan.run()
+            pipe.submit()
 
     def barrier():
         if world > 1:
@@ -225,6 +229,7 @@ def main():
     # ---- HBM-resident throughput ------------------------------------------------------------------------------
     for _ in range(W):
         step()
+    pipe.drain()
     barrier()
     sampler = ClockSampler(local_rank)
     time.sleep(0.25)
@@ -235,6 +240,7 @@ def main():
     step_no[0] = 0
     for _ in range(K):
         step()
+    pipe.drain()                 # the timed stream waits for both pipeline streams
     e1.record()                  # (the barrier below completes the gather: all peer stores have landed on rank 0)
     barrier()
     t1 = time.perf_counter()
@@ -360,7 +366,7 @@ def main():
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total/K,
                     higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
                     config=dict(workload=WORKLOAD % B, nk=NK, nM=NM, tracers=list(TRACERS), family='Tinker et al. (2010)',
-                                models_per_gpu_per_step=B, l2='inputs larger than L2: %.0f MB of grids per step per GPU'
+                                models_per_gpu_per_step=B, pipelining='consecutive steps alternate between two CUDA streams (double-buffered workspaces)', l2='inputs larger than L2: %.0f MB of grids per step per GPU'
                                 % (B*len(TRACERS)*NK*NM*8/1e6), collective=('gather to rank 0 fused into the epilogue kernel (peer stores over NVLink into a symmetric buffer); '
                                             'verified against NCCL all_gather: %s' % gather_ok) if world > 1 else 'none'),
                     clocks=clocks, e2e=e2e, gpu_launches=3*K, roofline=roofline, cpu_baseline=cpu)

@@ -858,7 +858,9 @@ static int hm_launch_stream(hm_quad_args& a, cudaStream_t st) {
 template <int P>
 static int hm_launch_epilogue(const hm_epi_args& e, cudaStream_t st) {
   constexpr int NW = P + P * (P + 1) / 2;
-  const int PG = (NW <= 20) ? 8 : 4;                   // part-groups per CTA; keeps shared memory under 48 KB
+  // part-groups per CTA: small enough (<= 9 KB of shared memory) that epilogue CTAs co-reside with the persistent
+  // streaming CTAs of the NEXT step when consecutive steps are pipelined over two streams
+  const int PG = (NW <= 9) ? 4 : (NW <= 20) ? 2 : 1;
   const int tiles = (e.nk + HM_EPI_ROWS - 1) / HM_EPI_ROWS;
   const size_t smem = ((size_t)PG * NW * HM_EPI_ROWS + 2 * HM_MAXP) * sizeof(double);
   hm_epilogue_kernel<P><<<e.B * tiles, PG * HM_EPI_ROWS, smem, st>>>(e);

@@ -314,6 +314,37 @@ class PowerSpectrumPlan:
                   + self.B*3*self.S*self.nk)
 
 
+class PipelinedPlans:
+    """Software pipelining of consecutive steps of a sweep: two plans (double-buffered workspaces and outputs)
+    alternate between two CUDA streams, so the small weights and epilogue kernels of one step run beside the
+    persistent streaming kernel of the neighbouring step (their CTAs fit in the registers and the ~9 KB of shared
+    memory the streaming CTAs leave free on every SM).  submit() enqueues one step; drain() joins the streams."""
+
+    def __init__(self, make_plan):
+        self.plans = [make_plan(), make_plan()]
+        self.streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        self.n = 0
+        self.forked = False
+
+    def submit(self, out=None, peer=False):
+        main = torch.cuda.current_stream()
+        if not self.forked:
+            for st in self.streams:
+                st.wait_stream(main)
+            self.forked = True
+        i = self.n & 1
+        with torch.cuda.stream(self.streams[i]):
+            res = self.plans[i].run(out=out, peer=peer)
+        self.n += 1
+        return res
+
+    def drain(self):
+        main = torch.cuda.current_stream()
+        for st in self.streams:
+            main.wait_stream(st)
+        self.forked = False
+
+
 class GramPlan:
     """Many-tracer counterpart of PowerSpectrumPlan (2..64 single-grid tracers): the cross one-halo terms run as a
     per-wavenumber Gram contraction on the FP64 tensor cores (csrc/hm_gram.cu).  Same output layout."""
