@@ -189,6 +189,13 @@ int hm_window_nfw(const double* k_dev, const double* rv_dev, const double* c_dev
 int hm_window_isothermal(const double* k_dev, const double* rv_dev, int32_t nk, int32_t nM, int32_t G,
                          double* out_dev, void* stream);
 
+/* W(k,M) = int_0^rv j0(k r) P(r;M) dr on R = linspace(0, rv, nr) by a sample rule (profile.configuration with
+ * win_integration in {trapezoid, simps, romb}; _halo_window, pyhalomodel.py:930-961).  profile_samples_dev:
+ * [nM][nr] = P(R_j; M); weights_dev: [nr] quadrature weights per unit spacing; out_dev: [nk][nM]. */
+int hm_window_configuration(const double* k_dev, const double* rv_dev, const double* profile_samples_dev,
+                            const double* weights_dev, int32_t nk, int32_t nM, int32_t nr, double* out_dev,
+                            void* stream);
+
 /* ---- sigma(R) ----------------------------------------------------------------------------------------------
  * sigma(R) = sqrt( sum_j dlnk k_j^3 P(k_j) T(k_j R)^2 / (2 pi^2) ) on the caller's integration grid
  * (cosmology._sigmaR_brute_log, cosmology.py:89-106; T with the Taylor switch of :41-48).

@@ -236,6 +236,36 @@ class Profile:
                    mass_tracer=mass_tracer, discrete_tracer=discrete_tracer)
 
 
+WIN_INTEGRATION = 'romb'      # pyhalomodel.py:30-38 (sample-based choices only)
+NR_WIN_INTEGRATION = 1+2**8    # pyhalomodel.py:38
+
+
+def halo_window(k, M, rv, c, diff_profile):
+    """pyhalomodel.py:930-961, sample-based branches"""
+    R = np.linspace(0., rv, NR_WIN_INTEGRATION)
+    integrand = _special.spherical_jn(0, k*R)*diff_profile(R, M, rv, c)
+    if WIN_INTEGRATION == 'trapezoid':
+        return _integrate.trapezoid(integrand, R)
+    if WIN_INTEGRATION == 'simps':
+        return _integrate.simpson(integrand, x=R)
+    if WIN_INTEGRATION == 'romb':
+        return _integrate.romb(integrand, R[1]-R[0])
+    raise ValueError('Halo window function integration method not recognised')
+
+
+def configuration_profile(k, M, rv, c, diff_profile, amplitude=None, normalisation=1., variance=None,
+                          mass_tracer=False, discrete_tracer=False):
+    """profile.configuration, pyhalomodel.py:886-925"""
+    amp0 = np.array([halo_window(0., _M, _rv, _c, diff_profile) for _M, _rv, _c in zip(M, rv, c)])
+    Uk = np.zeros((len(k), len(M)))
+    for ik, _k in enumerate(k):
+        for iM, (_M, _rv, _c) in enumerate(zip(M, rv, c)):
+            Uk[ik, iM] = halo_window(_k, _M, _rv, _c, diff_profile)/amp0[iM]
+    amp = amp0 if amplitude is None else np.array(amplitude, dtype=float)
+    return Profile.Fourier(k, M, Uk, amplitude=amp, normalisation=normalisation, variance=variance,
+                           mass_tracer=mass_tracer, discrete_tracer=discrete_tracer)
+
+
 # ---------------------------------------------------------------------------------------------
 # Fourier windows, concentration, HOD                          pyhalomodel.py:1006-1221
 # ---------------------------------------------------------------------------------------------

@@ -162,3 +162,43 @@ extern "C" int hm_window_isothermal(const double* k_dev, const double* rv_dev, i
   HM_LAUNCH_CHECK();
   return HM_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Configuration-space profiles: W(k, M) = int_0^rv j0(k r) P(r; M) dr on the reference's fixed radial grid
+// R = linspace(0, rv, nr) with a sample-based rule (profile.configuration / _halo_window, pyhalomodel.py:886-961,
+// win_integration in {trapezoid, simps, romb}: all three are fixed linear combinations of the samples, passed
+// here as quadrature weights per unit spacing).  P is sampled by the caller (it is a Python callable there).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hm_window_config_kernel(const double* __restrict__ k, const double* __restrict__ rv,
+                                                               const double* __restrict__ Psamp,
+                                                               const double* __restrict__ wq, int nk, int nM, int nr,
+                                                               double* __restrict__ out) {
+  const long long total = (long long)nk * nM;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ik = (int)(i / nM), m = (int)(i - (long long)ik * nM);
+    const double kk = k[ik], r_v = rv[m];
+    const double dR = r_v / (double)(nr - 1);
+    const double* P = Psamp + (size_t)m * nr;
+    double acc = 0.;
+    for (int j = 0; j < nr; ++j) {
+      const double R = (j == nr - 1) ? r_v : dR * (double)j;       // np.linspace hits the end point exactly
+      const double x = kk * R;
+      const double j0 = (x == 0.) ? 1. : sin(x) / x;               // spherical_jn(0, x)
+      acc = fma(wq[j], j0 * P[j], acc);
+    }
+    out[i] = acc * dR;
+  }
+}
+
+extern "C" int hm_window_configuration(const double* k_dev, const double* rv_dev, const double* profile_samples_dev,
+                                       const double* weights_dev, int32_t nk, int32_t nM, int32_t nr,
+                                       double* out_dev, void* stream) {
+  int rc = hm_check_device();
+  if (rc) return rc;
+  HM_REQUIRE(k_dev && rv_dev && profile_samples_dev && weights_dev && out_dev, "NULL pointer");
+  HM_REQUIRE(nk > 0 && nM > 0 && nr >= 2, "bad sizes");
+  hm_window_config_kernel<<<hm_grid_for((long long)nk * nM), 256, 0, (cudaStream_t)stream>>>(
+      k_dev, rv_dev, profile_samples_dev, weights_dev, nk, nM, nr, out_dev);
+  HM_LAUNCH_CHECK();
+  return HM_OK;
+}

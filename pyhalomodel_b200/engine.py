@@ -153,6 +153,16 @@ def window_isothermal(k, rv):
     return out if batched else out[0]
 
 
+def window_configuration(k, rv, samples, weights):
+    """k [nk], rv [nM], samples [nM, nr] = P(R_j; M) on R = linspace(0, rv, nr), weights [nr] -> W [nk, nM]."""
+    k, rv, samples, weights = to_dev(k), to_dev(rv), to_dev(samples), to_dev(weights)
+    nM, nr = samples.shape
+    out = torch.empty((k.shape[0], nM), dtype=F64, device=k.device)
+    check(lib().hm_window_configuration(_ptr(k), _ptr(rv), _ptr(samples), _ptr(weights), k.shape[0], nM, nr, _ptr(out),
+                                        _stream()))
+    return out
+
+
 def sigma_tophat(kgrid, Pk, dlnk, R):
     """kgrid [nkg]; Pk [nkg] or [G, nkg]; R [nR] or [G, nR] -> sigma with R's shape (cosmology.py:89-106)."""
     kgrid, Pk, R = to_dev(kgrid), to_dev(Pk), to_dev(R)

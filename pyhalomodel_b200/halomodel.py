@@ -30,6 +30,12 @@ Dv_rel_tol = 1e-3
 Tinker_z_dep = False    # redshift-dependent Tinker et al. (2010) parameters (pyhalomodel.py:20, :163-167)
 Tinker_PBS = False      # peak-background-split bias for Tinker et al. (2010) (pyhalomodel.py:22, :264-271)
 halo_integration = 'trapezoid'    # the only mass integrator with a parity oracle (pyhalomodel.py:27)
+# W(k) integration scheme in r for configuration-space profiles (pyhalomodel.py:30-39).  The reference's default,
+# adaptive scipy quad with epsrel=1e-3, cannot be reproduced bit for bit (and its code path is broken under
+# scipy >= 1.14); the three sample-based schemes it offers are: 'trapezoid', 'simps', 'romb'.
+win_integration = 'romb'
+nr_win_integration = 1+2**8   # number of points in r; romb needs 2^m+1
+
 # beta_NL (pyhalomodel.py:44-46)
 do_I11 = True      # add the low-M1 and low-M2 portion of the beta_NL integral
 do_I12_I21 = True  # add the low-M1 or low-M2 portions
@@ -297,6 +303,29 @@ class model():
         return ordered
 
 
+def _sample_rule_weights(scheme, nr):
+    """Weights per unit spacing of the sample-based rules of scipy.integrate the reference selects with
+    `win_integration` (pyhalomodel.py:938-948): every one is linear in the samples."""
+    if scheme == 'trapezoid':
+        w = np.ones(nr)
+        w[0] = w[-1] = 0.5
+        return w
+    if scheme in ('simps', 'simpson'):
+        if nr % 2 == 0:
+            raise ValueError('the Simpson rule here needs an odd number of samples')
+        w = np.ones(nr)
+        w[1:-1:2], w[2:-1:2] = 4., 2.
+        return w/3.
+    if scheme == 'romb':
+        n = nr-1
+        if n < 1 or n & (n-1):
+            raise ValueError('Romberg integration needs 2^m+1 samples')
+        from scipy.integrate import romb
+        eye = np.eye(nr)
+        return np.array([romb(eye[i], dx=1.) for i in range(nr)])
+    raise ValueError('Halo window function integration method not recognised')
+
+
 def _split3(block, on_dev):
     if on_dev:
         return block[0].clone(), block[1].clone(), block[2].clone()
@@ -349,6 +378,34 @@ class profile():
             self._mode = _lib.GRID_UK
         self._grid = grid
         return self
+
+    @classmethod
+    def configuration(cls, k, M, rv, c, differential_profile, amplitude=None, normalisation=1., variance=None,
+                      mass_tracer=False, discrete_tracer=False):
+        '''
+        Configuration-space halo profile (pyhalomodel.py:886-925): differential_profile(r, M, rv, c) is the halo
+        profile times 4 pi r^2; its Fourier transform W(k,M) = int_0^rv j0(kr) P(r) dr is evaluated on the device with
+        the reference's sample-based rules (module switch `win_integration`: 'trapezoid', 'simps' or 'romb' on
+        `nr_win_integration` points; the callable is sampled on the host).  If amplitude is None the profile is taken
+        to be correctly normalised, otherwise it is renormalised to `amplitude`.
+        '''
+        Mh = np.asarray(engine.to_host(M) if isinstance(M, torch.Tensor) else M, dtype=float)
+        rvh = np.asarray(engine.to_host(rv) if isinstance(rv, torch.Tensor) else rv, dtype=float)
+        ch = np.asarray(engine.to_host(c) if isinstance(c, torch.Tensor) else c, dtype=float)
+        nr = int(nr_win_integration)
+        wq = _sample_rule_weights(win_integration, nr)
+        samples = np.empty((len(Mh), nr))
+        for iM, (_M, _rv, _c) in enumerate(zip(Mh, rvh, ch)):      # the callable is user Python code (:939-940)
+            samples[iM] = differential_profile(np.linspace(0., _rv, nr), _M, _rv, _c)
+        kk = np.concatenate([[0.], np.asarray(engine.to_host(k) if isinstance(k, torch.Tensor) else k, dtype=float)])
+        W = engine.window_configuration(kk, rvh, samples, wq)       # row 0 is k = 0: the profile amplitudes (:909-911)
+        amp0, W = W[0], W[1:]
+        Uk = W/amp0                                                 # :917, :919
+        amp = amp0 if amplitude is None else engine.to_dev(amplitude)
+        prof = cls.Fourier(engine.to_dev(k), engine.to_dev(M), Uk, amplitude=amp, normalisation=normalisation,
+                           variance=variance, mass_tracer=mass_tracer, discrete_tracer=discrete_tracer)
+        prof._on_dev = _wants_device(k, M, rv, c)
+        return prof
 
     # lazily materialised views with the reference's field names
     @property

@@ -287,6 +287,43 @@ def golden_power_beta():
     save('power_beta.npz', **out)
 
 
+def diff_profile_nfw(r, M, rv, c):
+    """4 pi r^2 rho_NFW(r), truncated at rv, normalised to M (cf. the commented example at pyhalomodel.py:995-1000)."""
+    rs = rv/c
+    return M*(r/rs**2)/(1.+r/rs)**2/(np.log(1.+c)-c/(1.+c))
+
+
+def diff_profile_gas(r, M, rv, c):
+    """A dimensionful beta-model-like 'gas' profile times 4 pi r^2 (amplitude left free: amplitude=None)."""
+    return 1e-3*M**0.8*4.*np.pi*r**2/(1.+(r/(0.3*rv))**2)**1.2
+
+
+def golden_configuration():
+    """profile.configuration (pyhalomodel.py:886-961) with the three sample-based win_integration schemes.  The
+    installed scipy removed integrate.simps/quadrature/romberg, which the reference names at call time, so they are
+    aliased here exactly as SURVEY.md section 8(c) describes."""
+    from scipy import integrate
+    integrate.simps = integrate.simpson
+    integrate.quadrature = integrate.romberg = None
+    k, M = syn.k_grid(20, 1e-2, 30.), syn.M_grid(12, 1e11, 1e15)
+    hmod = ref.model(0.3, 0.3, name=SHORT['Tinker2010'], Dv=330., dc=1.686)
+    rv, c = hmod.virial_radius(M), ref.concentration(M, 0.3, halo_definition='Mvir')
+    out = dict(k=k, M=M, rv=rv, c=c, rhom=np.array(hmod.rhom))
+    old = ref.win_integration
+    try:
+        for tag, scheme in (('trapezoid', integrate.trapezoid), ('simps', integrate.simps), ('romb', integrate.romb)):
+            ref.win_integration = scheme
+            pm = ref.profile.configuration(k, M, rv, c, diff_profile_nfw, amplitude=M, normalisation=hmod.rhom, mass_tracer=True)
+            pg = ref.profile.configuration(k, M, rv, c, diff_profile_gas)
+            for name, pr in (('nfw', pm), ('gas', pg)):
+                out['%s_%s_Uk' % (tag, name)], out['%s_%s_Wk' % (tag, name)] = pr.Uk, pr.Wk
+                out['%s_%s_amp' % (tag, name)] = pr.amplitude
+    finally:
+        ref.win_integration = old
+    out['U_nfw_exact'] = ref.window_function(k, rv, c, profile='NFW')
+    save('configuration.npz', **out)
+
+
 if __name__ == '__main__':
     golden_massfn()
     golden_windows()
@@ -296,3 +333,4 @@ if __name__ == '__main__':
     golden_power_flags()
     golden_power_c2_small()
     golden_power_beta()
+    golden_configuration()

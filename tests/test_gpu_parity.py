@@ -423,3 +423,45 @@ def test_power_beta_nl_golden(halo):
     for t in range(3):
         for key in want[t]:
             assert_spectra_close(got[t][key], want[t][key], rtol=RTOL, what='beta odd %s term %d' % (key, t))
+
+
+def test_configuration_profiles_golden(halo):
+    """profile.configuration (j0 transform of a callable profile on the reference's fixed radial grid) against the
+    live-reference golden for the three sample-based schemes, and in a power spectrum against the oracle."""
+    from test_oracle_golden import _diff_profile_gas, _diff_profile_nfw
+    g = load_golden('configuration.npz')
+    k, M, rv, c = g['k'], g['M'], g['rv'], g['c']
+    try:
+        for tag in ('trapezoid', 'simps', 'romb'):
+            halo.win_integration = tag
+            pm = halo.profile.configuration(k, M, rv, c, _diff_profile_nfw, amplitude=M, normalisation=float(g['rhom']),
+                                            mass_tracer=True)
+            pg = halo.profile.configuration(k, M, rv, c, _diff_profile_gas)
+            for name, pr in (('nfw', pm), ('gas', pg)):
+                np.testing.assert_allclose(pr.Uk, g['%s_%s_Uk' % (tag, name)], rtol=1e-11)
+                np.testing.assert_allclose(pr.Wk, g['%s_%s_Wk' % (tag, name)], rtol=1e-11)
+                np.testing.assert_allclose(pr.amplitude, g['%s_%s_amp' % (tag, name)], rtol=1e-12)
+    finally:
+        halo.win_integration = 'romb'
+    with pytest.raises(ValueError):
+        halo.win_integration = 'bogus'
+        try:
+            halo.profile.configuration(k, M, rv, c, _diff_profile_gas)
+        finally:
+            halo.win_integration = 'romb'
+    # through power_spectrum against the oracle
+    cs = _synthetic_case(16, 32, z=0.3)
+    om = orc.make_model(cs['z'], cs['Om_m'], Dv=cs['Dv'], dc=cs['dc'])
+    hmod = halo.model(cs['z'], cs['Om_m'], Dv=cs['Dv'], dc=cs['dc'])
+    rv2, c2 = orc.virial_radius(cs['M'], om.Om_m, om.Dv), orc.concentration(cs['M'], om.z)
+    op = {'m': orc.configuration_profile(cs['k'], cs['M'], rv2, c2, _diff_profile_nfw, amplitude=cs['M'],
+                                         normalisation=om.rhom, mass_tracer=True),
+          'x': orc.configuration_profile(cs['k'], cs['M'], rv2, c2, _diff_profile_gas)}
+    gp = {'m': halo.profile.configuration(cs['k'], cs['M'], rv2, c2, _diff_profile_nfw, amplitude=cs['M'],
+                                          normalisation=hmod.rhom, mass_tracer=True),
+          'x': halo.profile.configuration(cs['k'], cs['M'], rv2, c2, _diff_profile_gas)}
+    want = orc.power_spectrum(om, cs['k'], cs['Pk_lin'], cs['M'], cs['sigmaM'], op)
+    got = hmod.power_spectrum(cs['k'], cs['Pk_lin'], cs['M'], cs['sigmaM'], gp)
+    for t in range(3):
+        for key in want[t]:
+            assert_spectra_close(got[t][key], want[t][key], rtol=RTOL, what='config %s term %d' % (key, t))

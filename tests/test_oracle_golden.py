@@ -209,3 +209,30 @@ def test_power_beta_nl():
         orc.DO_I11, orc.DO_I12_I21 = True, True
     with pytest.raises(ValueError):
         orc.power_spectrum(hm, g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs, beta=g['beta'], simple_twohalo=True)
+
+
+def _diff_profile_nfw(r, M, rv, c):
+    rs = rv/c
+    return M*(r/rs**2)/(1.+r/rs)**2/(np.log(1.+c)-c/(1.+c))
+
+
+def _diff_profile_gas(r, M, rv, c):
+    return 1e-3*M**0.8*4.*np.pi*r**2/(1.+(r/(0.3*rv))**2)**1.2
+
+
+def test_configuration_profiles():
+    """profile.configuration with the sample-based integrators (pyhalomodel.py:886-961)."""
+    g = load_golden('configuration.npz')
+    k, M, rv, c = g['k'], g['M'], g['rv'], g['c']
+    try:
+        for tag in ('trapezoid', 'simps', 'romb'):
+            orc.WIN_INTEGRATION = tag
+            pm = orc.configuration_profile(k, M, rv, c, _diff_profile_nfw, amplitude=M, normalisation=float(g['rhom']),
+                                           mass_tracer=True)
+            pg = orc.configuration_profile(k, M, rv, c, _diff_profile_gas)
+            for name, pr in (('nfw', pm), ('gas', pg)):
+                np.testing.assert_allclose(pr.Uk, g['%s_%s_Uk' % (tag, name)], rtol=1e-13)
+                np.testing.assert_allclose(pr.Wk, g['%s_%s_Wk' % (tag, name)], rtol=1e-13)
+                np.testing.assert_allclose(pr.amplitude, g['%s_%s_amp' % (tag, name)], rtol=1e-13)
+    finally:
+        orc.WIN_INTEGRATION = 'romb'
