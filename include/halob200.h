@@ -134,6 +134,11 @@ int hm_average(const hm_model_desc* model_host, const double* M_dev, const doubl
 int hm_average_batch(const hm_model_desc* models_dev, const double* M_dev, const double* sigma_dev, int32_t nM,
                      int32_t n_samples, int32_t models_per_sample, const double* f_dev, double* out_dev, void* stream);
 
+/* out[j][k] = sum_m w[j][m] grid[k][m]: weighted row sums of one (k,M) grid for nw weight vectors (used by
+ * model.cross_halo_spectrum, pyhalomodel.py:573-704).  grid_dev: [nk][nM]; w_dev: [nw][nM]; out_dev: [nw][nk]. */
+int hm_weighted_rowsum(const double* grid_dev, const double* w_dev, int32_t nk, int32_t nM, int32_t nw,
+                       double* out_dev, void* stream);
+
 /* ---- the hot path: model.power_spectrum (pyhalomodel.py:361-513, beta=None) --------------------------------
  * out_dev: [B][S][3][nk] with S = P(P+1)/2 unique pairs ordered (0,0),(0,1),..,(0,P-1),(1,1),.. and the three
  * terms ordered (Pk_2h, Pk_1h, Pk_hm).  lowmass_dev (optional, [B]) receives A so the caller can raise the

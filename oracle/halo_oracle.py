@@ -426,6 +426,40 @@ def _two_halo(hm, Pk_lin, M, nu, Wu, Wv, mass_u, mass_v, A, beta=None):
     return (Iu*Iv+I_NL)*Pk_lin
 
 
+def cross_halo_spectrum(hm: HaloModel, k, Pk_lin, M, sigmaM, profiles: dict, M_halo, beta=None, simple_twohalo=False,
+                        k_trunc=None):
+    """pyhalomodel.py:573-704: each tracer crossed with haloes of mass M_halo."""
+    if simple_twohalo and (beta is not None):
+        raise ValueError('A simple two-halo term is not compatible with non-linear halo bias')
+    if not is_increasing(M):
+        raise ValueError('Halo mass array must be increasing monotonically')
+    nu = peak_height(hm, sigmaM)
+    g, b = mass_function_nu(hm, nu), linear_bias_nu(hm, nu)
+    A = 1.-_integrate.trapezoid(g*b, nu)                                              # :624-625
+    nu_halo = _interp1d(np.log(M), nu, kind='cubic')(np.log(M_halo))                   # :631-632
+    b_halo = linear_bias_nu(hm, nu_halo)
+    P2, P1, PH = {}, {}, {}
+    for name, prof in profiles.items():
+        W_halo = np.array([_interp1d(np.log(M), prof.Wk[ik, :], kind='cubic')(np.log(M_halo)) for ik in range(len(k))])
+        p2h, p1h = np.zeros_like(k), np.zeros_like(k)
+        for ik in range(len(k)):
+            Wrow = prof.amplitude/prof.normalisation if simple_twohalo else prof.Wk[ik, :]
+            Iu = _two_halo_integral(hm, M, nu, Wrow, prof.mass_tracer, A)              # :688
+            I_NL = 0.
+            if beta is not None:                                                       # :691-704
+                integral = np.trapezoid(beta[ik, :]*prof.Wk[ik, :]*g*b/M, nu)
+                if prof.mass_tracer:
+                    integral += A*beta[ik, 0]*prof.Wk[ik, 0]/M[0]
+                I_NL = b_halo*integral*hm.rhom
+            p2h[ik] = (b_halo*Iu+I_NL)*Pk_lin[ik]                                      # :689
+            p1h[ik] = W_halo[ik]                                                       # :662
+        if k_trunc is not None:
+            p1h *= 1.-np.exp(-(k/k_trunc)**2)
+        P2[name], P1[name] = p2h.copy(), p1h.copy()
+        PH[name] = P2[name]+P1[name]
+    return P2, P1, PH
+
+
 def power_spectrum(hm: HaloModel, k, Pk_lin, M, sigmaM, profiles: dict, beta=None, simple_twohalo=False,
                    subtract_shotnoise=True, correct_discrete=True, k_trunc=None):
     """pyhalomodel.py:361-513.  Returns (Pk_2h, Pk_1h, Pk_hm) dictionaries keyed 'u-v'

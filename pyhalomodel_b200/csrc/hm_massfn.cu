@@ -89,3 +89,30 @@ extern "C" int hm_average_batch(const hm_model_desc* models_dev, const double* M
   HM_LAUNCH_CHECK();
   return HM_OK;
 }
+
+// Generic weighted row sums: out[j][k] = sum_m w[j][m] * grid[k][m]  (the building block of the halo-model mass
+// integrals once the trapezoid rule and the mass function are folded into w; used by cross_halo_spectrum,
+// pyhalomodel.py:573-704).  One CTA per grid row, fixed-order reduction.
+__global__ void __launch_bounds__(256) hm_rowsum_kernel(const double* __restrict__ grid, const double* __restrict__ w,
+                                                        int nk, int nM, int nw, double* __restrict__ out) {
+  __shared__ double scratch[32];
+  const int ik = blockIdx.x;
+  const double* row = grid + (size_t)ik * nM;
+  for (int j = 0; j < nw; ++j) {
+    double acc = 0.;
+    for (int m = threadIdx.x; m < nM; m += blockDim.x) acc = fma(w[(size_t)j * nM + m], row[m], acc);
+    const double tot = hm_block_sum(acc, scratch);
+    if (threadIdx.x == 0) out[(size_t)j * nk + ik] = tot;
+  }
+}
+
+extern "C" int hm_weighted_rowsum(const double* grid_dev, const double* w_dev, int32_t nk, int32_t nM, int32_t nw,
+                                  double* out_dev, void* stream) {
+  int rc = hm_check_device();
+  if (rc) return rc;
+  HM_REQUIRE(grid_dev && w_dev && out_dev, "NULL pointer");
+  HM_REQUIRE(nk > 0 && nM > 0 && nw > 0, "bad sizes");
+  hm_rowsum_kernel<<<nk, 256, 0, (cudaStream_t)stream>>>(grid_dev, w_dev, nk, nM, nw, out_dev);
+  HM_LAUNCH_CHECK();
+  return HM_OK;
+}

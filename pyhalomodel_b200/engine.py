@@ -127,6 +127,17 @@ def average_batch(models_dev, M, sigma, funcs, models_per_sample=1):
     return out
 
 
+def weighted_rowsum(grid, w):
+    """grid [nk, nM], w [nw, nM] -> [nw, nk] with out[j, k] = sum_m w[j, m] grid[k, m]."""
+    grid, w = to_dev(grid), to_dev(w)
+    if w.dim() == 1:
+        w = w[None, :]
+    nk, nM = grid.shape
+    out = torch.empty((w.shape[0], nk), dtype=F64, device=grid.device)
+    check(lib().hm_weighted_rowsum(_ptr(grid), _ptr(w), nk, nM, w.shape[0], _ptr(out), _stream()))
+    return out
+
+
 def sici(x):
     x = to_dev(x)
     si, ci = torch.empty_like(x), torch.empty_like(x)

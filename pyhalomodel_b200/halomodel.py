@@ -230,6 +230,16 @@ class model():
         out = engine.average(self.descriptor(), M, sigmaM, func)
         return out[0] if _wants_device(M, sigmaM, func) else float(out[0].item())
 
+    def cross_halo_spectrum(self, k, Pk_lin, M, sigmaM, profiles: dict, M_halo: float, beta=None, simple_twohalo=False,
+                            k_trunc=None, verbose=False) -> tuple:
+        '''
+        Power spectrum of each tracer crossed with haloes of one mass M_halo (pyhalomodel.py:573-677): dictionaries
+        keyed by the profile names.  beta is beta_NL(k, M) at M_halo.  The mass integrals and the cubic
+        interpolation in ln M are weighted row sums of the (k, M) grids on the device.
+        '''
+        return _cross_halo_spectrum(self, k, Pk_lin, M, sigmaM, profiles, M_halo, beta=beta,
+                                    simple_twohalo=simple_twohalo, k_trunc=k_trunc, verbose=verbose)
+
     # -- the hot path ---------------------------------------------------------------------------------------
     def power_spectrum(self, k, Pk_lin, M, sigmaM, profiles: dict, beta=None, simple_twohalo=False,
                        subtract_shotnoise=True, correct_discrete=True, k_trunc=None, verbose=False) -> tuple:
@@ -303,6 +313,14 @@ class model():
         return ordered
 
 
+def _cubic_interp_weights(x, x0):
+    """Weights L_m with interp1d(x, y, kind='cubic')(x0) = sum_m L_m y_m: scipy's cubic interp1d is the not-a-knot
+    interpolating spline (make_interp_spline, k=3), which is linear in y, so one solve against the identity gives
+    the weights for every row of a (k, M) grid at once (pyhalomodel.py:631-639)."""
+    from scipy.interpolate import make_interp_spline
+    return np.asarray(make_interp_spline(x, np.eye(len(x)), k=3)(x0), dtype=float)
+
+
 def _sample_rule_weights(scheme, nr):
     """Weights per unit spacing of the sample-based rules of scipy.integrate the reference selects with
     `win_integration` (pyhalomodel.py:938-948): every one is linear in the samples."""
@@ -324,6 +342,70 @@ def _sample_rule_weights(scheme, nr):
         eye = np.eye(nr)
         return np.array([romb(eye[i], dx=1.) for i in range(nr)])
     raise ValueError('Halo window function integration method not recognised')
+
+
+def _cross_halo_spectrum(self, k, Pk_lin, M, sigmaM, profiles, M_halo, beta=None, simple_twohalo=False,
+                         k_trunc=None, verbose=False):
+    if simple_twohalo and (beta is not None):
+        raise ValueError('A simple two-halo term is not compatible with non-linear halo bias')
+    Mh = engine.to_host(M) if isinstance(M, torch.Tensor) else np.asarray(M, dtype=float)
+    kh = engine.to_host(k) if isinstance(k, torch.Tensor) else np.asarray(k, dtype=float)
+    if not util.is_array_monotonic(Mh):
+        raise ValueError('Halo mass array must be increasing monotonically')
+    if not isinstance(profiles, dict):
+        raise TypeError('profiles must be a dictionary')
+    for prof in profiles.values():
+        if np.shape(kh) != np.shape(prof.k) or (kh != prof.k).all():
+            raise ValueError('k arrays must all be identical to those in profiles')
+        if np.shape(Mh) != np.shape(prof.M) or (Mh != prof.M).all():
+            raise ValueError('Mass arrays must be identical to those in profiles')
+    on_dev = _wants_device(k, Pk_lin, M, sigmaM)
+    Md, sig, Pk, kd = engine.to_dev(M), engine.to_dev(sigmaM), engine.to_dev(Pk_lin), engine.to_dev(k)
+    nu = self.dc/sig
+    g, b = engine.massfn_nu(self.descriptor(), nu)
+    tw = torch.empty_like(nu)                     # trapezoid rule in nu as weights (pyhalomodel.py:27)
+    tw[1:-1] = 0.5*(nu[2:]-nu[:-2])
+    tw[0], tw[-1] = 0.5*(nu[1]-nu[0]), 0.5*(nu[-1]-nu[-2])
+    A = 1.-float(torch.sum(tw*(g*b)).item())      # note: trapezoid here, not quad (pyhalomodel.py:624-625)
+    L = engine.to_dev(_cubic_interp_weights(np.log(Mh), np.log(M_halo)))     # cubic interpolation in ln M (:631-639)
+    nu_halo = torch.sum(L*nu).reshape(1)
+    _, b_halo = engine.massfn_nu(self.descriptor(), nu_halo, want_g=False)
+    b_halo = b_halo[0]
+    w2 = tw*(b*g)/Md
+    damp = (1.-torch.exp(-(kd/k_trunc)**2)) if k_trunc is not None else None
+    betad = engine.to_dev(beta) if beta is not None else None
+    out2, out1, outh = {}, {}, {}
+    for name, prof in profiles.items():
+        amp = prof._amplitude
+        norm = float(prof.normalisation)
+        if prof._mode == _lib.GRID_UK:
+            cW, gridW = amp/norm, prof._grid
+        else:
+            cW, gridW = torch.ones_like(Md), (prof._grid if prof._mode == _lib.GRID_WK else prof._wk)
+        e = w2*cW
+        if prof.mass_tracer:
+            e = e.clone()
+            e[0] = e[0]+(A/Md[0])*cW[0]                                     # A W(k, M0)/M0 (:541-542)
+        sums = engine.weighted_rowsum(gridW, torch.stack([e, L*cW]))        # I_u(k)/rhom and W(k, M_halo)
+        if simple_twohalo:                                                 # (:648-650)
+            Iu = self.rhom*(torch.sum(w2*(amp/norm))+(A*(amp[0]/norm)/Md[0] if prof.mass_tracer else 0.))
+            Iu = Iu.expand(kd.shape[0])
+        else:
+            Iu = sums[0]*self.rhom
+        I_NL = 0.
+        if betad is not None:                                              # _I_beta_hu (:691-704)
+            wb = betad*(gridW*cW[None, :])*(w2[None, :])                    # beta W g b/M with trapezoid weights
+            integral = torch.sum(wb, dim=1)
+            if prof.mass_tracer:
+                integral = integral+A*betad[:, 0]*(gridW[:, 0]*cW[0])/Md[0]
+            I_NL = b_halo*integral*self.rhom
+        p2h = (b_halo*Iu+I_NL)*Pk                                           # (:689)
+        p1h = sums[1].clone()                                               # the profile at M = M_halo (:662)
+        if damp is not None:
+            p1h = p1h*damp
+        out2[name], out1[name] = _give_back(p2h, on_dev), _give_back(p1h, on_dev)
+        outh[name] = out2[name]+out1[name]
+    return out2, out1, outh
 
 
 def _split3(block, on_dev):

@@ -324,6 +324,31 @@ def golden_configuration():
     save('configuration.npz', **out)
 
 
+def golden_cross_halo():
+    """model.cross_halo_spectrum (pyhalomodel.py:573-704): tracer x halo-of-mass-M_h spectra for m + g + p, with and
+    without beta_NL(k, M), k_trunc and the simple two-halo option."""
+    nk, nM = 18, 64
+    k, M = syn.k_grid(nk, 1e-2, 5.), syn.M_grid(nM, 1e10, 1e16)
+    Om_m, z = 0.29, 0.35
+    Plin0 = syn.LinearSpectrum(Om_m, 0.7, 0.96, 0.8)
+    dc, Dv = dcDv(z, Om_m)
+    hmod = ref.model(z, Om_m, name=SHORT['Tinker2010'], Dv=Dv, dc=dc)
+    sig, R = sigma_of_M(hmod, M, Plin0, z)
+    Pk = Plin0(k, z)
+    profs, extra = build_profiles(hmod, k, M, sig, z, hod=syn.zheng_defaults(), with_pressure=True)
+    beta = synthetic_beta(k, M)[:, :, nM//3]          # beta_NL(k, M) at the halo mass
+    out = dict(k=k, M=M, Pk_lin=Pk, sigmaM=sig, z=np.array(z), Om_m=np.array(Om_m), dcDv=np.array([dc, Dv]),
+               rho_g=extra['rho_g'], beta=beta, M_halo=np.array([3.3e12, 2.1e14]))
+    for ih, Mh in enumerate(out['M_halo']):
+        for tag, kw in (('plain', {}), ('beta', dict(beta=beta)), ('ktrunc', dict(k_trunc=0.2)), ('simple', dict(simple_twohalo=True))):
+            with warnings.catch_warnings():
+                warnings.simplefilter('ignore')
+                P2, P1, PH = hmod.cross_halo_spectrum(k, Pk, M, sig, profs, Mh, **kw)
+            for name in ('m', 'g', 'p'):
+                out['h%d_%s_%s' % (ih, tag, name)] = np.array([P2[name], P1[name], PH[name]])
+    save('cross_halo.npz', **out)
+
+
 if __name__ == '__main__':
     golden_massfn()
     golden_windows()
@@ -334,3 +359,4 @@ if __name__ == '__main__':
     golden_power_c2_small()
     golden_power_beta()
     golden_configuration()
+    golden_cross_halo()

@@ -465,3 +465,23 @@ def test_configuration_profiles_golden(halo):
     for t in range(3):
         for key in want[t]:
             assert_spectra_close(got[t][key], want[t][key], rtol=RTOL, what='config %s term %d' % (key, t))
+
+
+def test_cross_halo_spectrum_golden(halo):
+    """model.cross_halo_spectrum (tracer x halo of mass M_h, pyhalomodel.py:573-704) against the live-reference golden."""
+    from test_oracle_golden import CROSS_VARIANTS
+    g = load_golden('cross_halo.npz')
+    dc, Dv = g['dcDv']
+    hmod = halo.model(float(g['z']), float(g['Om_m']), name=orc.TINKER10, Dv=Dv, dc=dc)
+    profs = _profiles(halo, hmod, g, hod=syn.zheng_defaults(), pressure=True)
+    for ih, Mh in enumerate(g['M_halo']):
+        for tag, kw in CROSS_VARIANTS:
+            kw = dict(beta=g['beta']) if kw == 'beta' else kw
+            out = hmod.cross_halo_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs, float(Mh), **kw)
+            assert list(out[0].keys()) == ['m', 'g', 'p']
+            for name in ('m', 'g', 'p'):
+                for t in range(3):
+                    assert_spectra_close(out[t][name], g['h%d_%s_%s' % (ih, tag, name)][t], rtol=RTOL,
+                                         what='cross %s %s %d' % (tag, name, t))
+    with pytest.raises(ValueError):
+        hmod.cross_halo_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs, 1e13, beta=g['beta'], simple_twohalo=True)

@@ -236,3 +236,22 @@ def test_configuration_profiles():
                 np.testing.assert_allclose(pr.amplitude, g['%s_%s_amp' % (tag, name)], rtol=1e-13)
     finally:
         orc.WIN_INTEGRATION = 'romb'
+
+
+CROSS_VARIANTS = (('plain', {}), ('beta', 'beta'), ('ktrunc', dict(k_trunc=0.2)), ('simple', dict(simple_twohalo=True)))
+
+
+def test_cross_halo_spectrum():
+    """model.cross_halo_spectrum (pyhalomodel.py:573-704)."""
+    g = load_golden('cross_halo.npz')
+    dc, Dv = g['dcDv']
+    hm = orc.make_model(float(g['z']), float(g['Om_m']), name=orc.TINKER10, Dv=Dv, dc=dc)
+    profs = _profiles(hm, g, hod=syn.zheng_defaults(), pressure=True)
+    for ih, Mh in enumerate(g['M_halo']):
+        for tag, kw in CROSS_VARIANTS:
+            kw = dict(beta=g['beta']) if kw == 'beta' else kw
+            out = orc.cross_halo_spectrum(hm, g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs, Mh, **kw)
+            for name in ('m', 'g', 'p'):
+                for t in range(3):
+                    assert_spectra_close(out[t][name], g['h%d_%s_%s' % (ih, tag, name)][t], rtol=1e-12,
+                                         what='cross %s %s %d' % (tag, name, t))
