@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
 // wavenumber): one CTA per (model, k), a warp per matrix row, the P vectors a_v staged in shared memory.
 // ---------------------------------------------------------------------------------------------------------------
 struct hm_beta_args {
-  int nk, nM, nMp, F, do_I11, do_I12_I21;
+  int nk, nM, nMp, F, do_I11, do_I12_I21, vec2;
   const double* M;
   const double* beta;                // [G][nk][nM][nM]
   const double* gridW[HM_MAXP];
@@ -571,10 +571,33 @@ __global__ void __launch_bounds__(256) hm_beta2h_kernel(const hm_beta_args a) {
     double y[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) y[p] = 0.;
-    for (int c = lane; c < a.nM; c += 32) {
-      const double bv = hm_ldg_stream1(row + c);
+    if (a.vec2) {        // even nM, 16-byte aligned rows: 8 independent 16-byte streaming loads in flight per lane
+      const int npair = a.nM >> 1;
+      for (int c0 = lane; c0 < npair; c0 += 32 * 8) {
+        double2 bv[8];
 #pragma unroll
-      for (int p = 0; p < P; ++p) y[p] = fma(bv, av[(size_t)p * a.nMp + c], y[p]);
+        for (int j = 0; j < 8; ++j) {
+          const int c = c0 + 32 * j;
+          bv[j] = (c < npair) ? hm_ldg_stream2(row + 2 * c) : make_double2(0., 0.);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = c0 + 32 * j;
+          if (c < npair) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+              const double2 avv = *reinterpret_cast<const double2*>(av + (size_t)p * a.nMp + 2 * c);
+              y[p] = fma(bv[j].x, avv.x, fma(bv[j].y, avv.y, y[p]));
+            }
+          }
+        }
+      }
+    } else {
+      for (int c = lane; c < a.nM; c += 32) {
+        const double bv = hm_ldg_stream1(row + c);
+#pragma unroll
+        for (int p = 0; p < P; ++p) y[p] = fma(bv, av[(size_t)p * a.nMp + c], y[p]);
+      }
     }
 #pragma unroll
     for (int p = 0; p < P; ++p) y[p] = hm_warp_sum(y[p]);        // every lane holds y_p[m1] = beta[m1,:] . a_p
@@ -901,6 +924,7 @@ extern "C" int hm_mass_quadrature_stages(const hm_problem* pr, double* out_dev, 
   hm_beta_args bt;
   bt.nk = pr->nk; bt.nM = pr->nM; bt.nMp = L.nMp; bt.F = pr->models_per_sample;
   bt.do_I11 = pr->beta_do_I11; bt.do_I12_I21 = pr->beta_do_I12_I21; bt.M = pr->M_dev; bt.beta = pr->beta_dev;
+  bt.vec2 = (pr->nM % 2 == 0) && !((uintptr_t)pr->beta_dev & 15);
   for (int p = 0; p < HM_MAXP; ++p) { bt.gridW[p] = a.gridW[p]; bt.mass[p] = (p < L.P) ? pr->tracers[p].mass_tracer : 0; }
   bt.weights = a.weights; bt.scal = e.scal; bt.inl = (double*)ws + L.inl_offset;
   for (int p = 0; p < HM_MAXP; ++p) e.discrete[p] = (p < L.P) ? pr->tracers[p].discrete_tracer : 0;
