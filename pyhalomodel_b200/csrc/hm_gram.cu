@@ -300,8 +300,8 @@ __device__ __forceinline__ void hm_gram_flush(double (&acc)[RK][2][4][2], double
   }
 
 // ---- named barriers between the two warp roles (ids 1..4; 0 is __syncthreads) ---------------------------------
-#define HM_GBAR_FULL 1      // + buf: prep warps arrive, MMA warps wait
-#define HM_GBAR_EMPTY 3     // + buf: MMA warps arrive, prep warps wait
+#define HM_GBAR_FULL 1      // + buf (0..2): prep warps arrive, MMA warps wait
+#define HM_GBAR_EMPTY 4     // + buf (0..2): MMA warps arrive, prep warps wait
 #define HM_GTHREADS (64 * HM_GWARPS)
 __device__ __forceinline__ void hm_bar_sync(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(HM_GTHREADS) : "memory");
@@ -330,9 +330,8 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
   constexpr int PT = 8 * NBT;
   constexpr size_t tile_doubles = (size_t)RK * PT * HM_GLD;
   constexpr int NDV = NBT * RK * 2;                     // diagonal sums per prep warp (<= 32)
-  double* Ys = gsm;                                     // [2][RK][PT][HM_GLD]  W tiles
-  double* w1s = Ys + 2 * tile_doubles;                  // [2][HM_GMCH]
-  double* sdiag = w1s + 2 * HM_GMCH;                    // [HM_GWARPS][NDV][33]  per-lane diagonal accumulators
+  double* Ys = gsm;                                     // [3][RK][PT][HM_GLD]  W tiles (raw grid rows until scaled)
+  double* w1s = Ys + 3 * tile_doubles;                  // [3][HM_GMCH]
   const int P = a.P;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform: role dispatch does not diverge
@@ -341,8 +340,6 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
   const long long it0 = (long long)blockIdx.x * per;
   const long long it1 = (it0 + per < a.nitems) ? it0 + per : a.nitems;
   if (it0 >= it1) return;
-  for (int i = tid; i < HM_GWARPS * NDV * 33; i += blockDim.x) sdiag[i] = 0.;
-  __syncthreads();
 
   hm_gram_cursor cur;
   cur.item = (int)it0; cur.ch = 0;
@@ -350,50 +347,82 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
 
   if (warp >= HM_GWARPS) {
     // =============================== prep warps ===============================
+    // cp.async (LDGSTS) streams the raw tracer rows of chunk n+1 into its W-tile buffer while chunk n is scaled in
+    // place: no registers are held by loads in flight, so a whole 64 KB chunk per SM is always on its way.
     const int pw = warp - HM_GWARPS;                    // owns tracers pw, pw+8, ...
-    double* myd = sdiag + (size_t)pw * NDV * 33 + lane;
     const double2 zero = make_double2(0., 0.);
+    double vals[32];                                    // diagonal sums of the current item (per lane)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) vals[i] = 0.;
+
+    auto issue = [&](const hm_gram_cursor& c, int buf) {
+      const int m = c.mbeg + c.ch * HM_GMCH + 2 * lane;
+      const bool in = m < c.mend;
+      const int mc = in ? m : 0;                        // keep the (unread) source address inside the row
+      const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(Ys + (size_t)buf * tile_doubles + 2 * lane);
+#pragma unroll
+      for (int r = 0; r < RK; ++r) {
+        const int row = (c.row0 + r < a.nk) ? c.row0 + r : a.nk - 1;         // clamp: duplicates are never written
+        const size_t off = ((size_t)c.smp * a.nk + row) * (size_t)a.nM + mc;
+#pragma unroll
+        for (int t = 0; t < NBT; ++t) {
+          const int p = pw + 8 * t;
+          const bool on = in && p < P;
+          const double* src = a.grid[on ? p : 0] + off;
+          const uint32_t dst = dst0 + (uint32_t)(((size_t)r * PT + p) * HM_GLD * sizeof(double));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(on ? 16 : 0) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    hm_gram_cursor fill = cur;                          // `fill` runs one chunk ahead of `cur`
+    issue(fill, 0);
+    bool more = hm_gram_advance(fill, it1);
+    if (more && fill.ch == 0) hm_gram_decode<RK>(fill, a);
     int n = 0;
     while (true) {
-      const int buf = n & 1;
+      const int buf = n % 3;
+      if (more) {                                       // prefetch chunk n+1 into its buffer once the MMA warps are
+        const int nb = (n + 1) % 3;                     // done with chunk n-2, which used it
+        if (n + 1 >= 3) hm_bar_sync(HM_GBAR_EMPTY + nb);
+        issue(fill, nb);
+      }
       const int m = cur.mbeg + cur.ch * HM_GMCH + 2 * lane;
       const bool in = m < cur.mend;                     // nM and MP are even: a lane's two masses are in or out together
       const double* __restrict__ gw = a.gw + (size_t)cur.b * a.gw_stride;
-      size_t rowoff[RK];
-#pragma unroll
-      for (int r = 0; r < RK; ++r) {
-        const int row = (cur.row0 + r < a.nk) ? cur.row0 + r : a.nk - 1;     // clamp: duplicates are never written
-        rowoff[r] = ((size_t)cur.smp * a.nk + row) * (size_t)a.nM + m;
-      }
       const double2 w2v = in ? *reinterpret_cast<const double2*>(gw + (size_t)a.nMp + m) : zero;
       const double2 w1v = (pw == 0 && in) ? *reinterpret_cast<const double2*>(gw + m) : zero;
       double* Y = Ys + (size_t)buf * tile_doubles + 2 * lane;
-      constexpr int TH = (NBT + 1) / 2;                 // tracers per half: bounds the registers held by loads
+      constexpr int TH = (NBT + 1) / 2;                 // tracers per half: bounds the registers held by c_p, d_p
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        double2 x[TH][RK], cc[TH], dd[TH];
+        double2 cc[TH], dd[TH];
 #pragma unroll
         for (int tt = 0; tt < TH; ++tt) {
           const int t = half * TH + tt, p = pw + 8 * t;
           const bool on = in && t < NBT && p < P;
           cc[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + p) * a.nMp + m) : zero;
           dd[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + P + p) * a.nMp + m) : zero;
-#pragma unroll
-          for (int r = 0; r < RK; ++r) x[tt][r] = on ? hm_ldg_stream2(a.grid[p] + rowoff[r]) : zero;
         }
-        if (half == 0 && n >= 2) hm_bar_sync(HM_GBAR_EMPTY + buf);        // MMA warps are done with this buffer
+        if (half == 0) {                                // my copies of chunk n have landed (n+1 may still fly)
+          if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+          else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
 #pragma unroll
         for (int tt = 0; tt < TH; ++tt) {
           const int t = half * TH + tt, p = pw + 8 * t;
           if (t < NBT) {
 #pragma unroll
             for (int r = 0; r < RK; ++r) {
-              const double2 xv = x[tt][r];
+              double2* cell = reinterpret_cast<double2*>(Y + ((size_t)r * PT + p) * HM_GLD);
+              const double2 xv = *cell;                 // raw grid values (zero-filled where off)
               const double2 y = make_double2(cc[tt].x * xv.x, cc[tt].y * xv.y);
-              *reinterpret_cast<double2*>(Y + ((size_t)r * PT + p) * HM_GLD) = y;
-              double* dv = myd + (size_t)((t * RK + r) * 2) * 33;
-              dv[0] += fma(w2v.x, y.x, w2v.y * y.y);                                 // sum_m w2 W_p   (:539)
-              dv[33] += fma(dd[tt].x * xv.x, xv.x, (dd[tt].y * xv.y) * xv.y);          // sum_m d_p U^2  (:475-477)
+              *cell = y;                                // W = c_p * grid, in place
+              if ((t * RK + r) * 2 + 1 < 32) {
+                vals[(t * RK + r) * 2] += fma(w2v.x, y.x, w2v.y * y.y);                          // sum_m w2 W_p   (:539)
+                vals[(t * RK + r) * 2 + 1] += fma(dd[tt].x * xv.x, xv.x, (dd[tt].y * xv.y) * xv.y);   // sum_m d_p U^2  (:475-477)
+              }
             }
           }
         }
@@ -403,26 +432,23 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
       hm_bar_arrive(HM_GBAR_FULL + buf);
 
       if (cur.ch + 1 == cur.nch_item) {                 // item finished: reduce and write my tracers' diagonal sums
-        __syncwarp();
         const int part = cur.item % a.nparts;
         double* dst = a.partial + ((size_t)cur.b * a.nparts + part) * (size_t)a.NW * a.nk;
-        if (lane < NDV) {
-          const double* row = sdiag + ((size_t)pw * NDV + lane) * 33;
-          double tot = 0.;
-#pragma unroll 8
-          for (int l = 0; l < 32; ++l) tot += row[l];                        // fixed order => reproducible
-          const int t = lane / (2 * RK), r = (lane >> 1) % RK, kind = lane & 1, p = pw + 8 * t;
-          if (p < P && cur.row0 + r < a.nk) dst[(size_t)(kind * P + p) * a.nk + cur.row0 + r] = tot;
-        }
-        __syncwarp();
+        const double tot = hm_warp_transpose_sum32(vals, lane);          // lane j now holds value j of this warp
+        const int t = lane / (2 * RK), r = (lane >> 1) % RK, kind = lane & 1, p = pw + 8 * t;
+        if (lane < NDV && p < P && cur.row0 + r < a.nk) dst[(size_t)(kind * P + p) * a.nk + cur.row0 + r] = tot;
 #pragma unroll
-        for (int v = 0; v < NDV; ++v) myd[(size_t)v * 33] = 0.;
-        __syncwarp();
+        for (int i = 0; i < 32; ++i) vals[i] = 0.;
       }
       ++n;
       const int prev_item = cur.item;
       if (!hm_gram_advance(cur, it1)) break;
       if (cur.item != prev_item) hm_gram_decode<RK>(cur, a);
+      if (more) {
+        const int pf = fill.item;
+        more = hm_gram_advance(fill, it1);
+        if (more && fill.item != pf) hm_gram_decode<RK>(fill, a);
+      }
     }
     return;
   }
@@ -438,7 +464,7 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
   const int fr = lane >> 2, fk = lane & 3;
   int n = 0;
   while (true) {
-    const int buf = n & 1;
+    const int buf = n % 3;
     hm_bar_sync(HM_GBAR_FULL + buf);                    // the W tile of this chunk is staged
     {
       const double* Yt = Ys + (size_t)buf * tile_doubles;
@@ -601,8 +627,7 @@ extern "C" int hm_gram_power_spectrum(const hm_gram_problem* pr, double* out_dev
   g.gw = wsd; g.partial = wsd + L.partial_offset;
   // the kernel is instantiated for block grids of 2, 4 and 8 (16, 32, 64 tracer rows); pad up to the next one
   const int NBT = (L.NB <= 2) ? 2 : (L.NB <= 4) ? 4 : 8;
-  const size_t smem = (2 * (size_t)L.RK * (8 * NBT) * HM_GLD + 2 * HM_GMCH
-                       + (size_t)HM_GWARPS * (NBT * L.RK * 2) * 33) * sizeof(double);
+  const size_t smem = (3 * (size_t)L.RK * (8 * NBT) * HM_GLD + 3 * HM_GMCH) * sizeof(double);
   static bool configured = false;
   if (!configured) {
     HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
