@@ -9,11 +9,12 @@
 //
 //   hm_gram_weights_kernel  w1, w2, per-tracer c_p (W = c_p*grid) and d_p (auto one-halo weight) per mass; A
 //   hm_gram_scalars_kernel  shot noise and simple-two-halo integrals per (tracer, model)
-//   hm_gram_kernel<RK>      CTA = (model, RK wavenumbers, mass part).  Per 64-mass chunk: (1) all warps load the
-//                           tracer rows with 16-byte streaming loads, scale them to W, store the W tile to shared
-//                           memory and accumulate the diagonal work (two-halo sums sum_m w2 W_p and auto one-halo
-//                           sums sum_m d_p grid_p^2) with a transposing shuffle reduction; (2) each warp runs DMMA
-//                           over its share of the 8x8 upper-triangle fragments.  Two CTAs per SM overlap (1) and (2).
+//   hm_gram_tracer_kernel   c_p and d_p per (tracer, mass)
+//   hm_gram_kernel<RK,NBT>  persistent warp-specialised CTA per SM over (model, RK wavenumbers, mass part) items:
+//                           prep warps stream the tracer rows of the next 64-mass chunk with cp.async into one of
+//                           three W-tile buffers, scale them in place to W and keep the diagonal work (two-halo
+//                           sums sum_m w2 W_p, auto one-halo sums sum_m d_p grid_p^2) in registers; MMA warps run
+//                           DMMA over statically owned 8x8 upper-triangle fragments; named barriers hand tiles over.
 //   hm_gram_epilogue_kernel adds the mass parts and finishes P_2h, P_1h, P_hm for every unique pair (:456-501)
 //
 // The diagonal (auto) terms are NOT Gram entries: they use Uk, amplitude, variance (pyhalomodel.py:465-477).

@@ -1,6 +1,6 @@
-// hm_quad.cu -- the hot path of model.power_spectrum (pyhalomodel.py:361-513, beta=None) as three kernels:
+// hm_quad.cu -- the hot path of model.power_spectrum (pyhalomodel.py:361-513) as a short kernel pipeline:
 //
-//   hm_weights_kernel      (mass-chunk, model) CTAs: nu = dc/sigma, g(nu), b(nu), trapezoid-in-nu weights, the
+//   hm_weights_kernel      (256-mass chunk, model) CTAs: nu = dc/sigma, g(nu), b(nu), trapezoid-in-nu weights, the
 //                          low-mass correction A, and from those the P+S per-mass weight vectors that turn every
 //                          integral of the reference into a plain weighted row sum over M:
 //                            I_u(k)  = rhom * sum_m  e_u[m]  * G_u[k,m]                  (:535-544, incl. A W(k,M0)/M0)
@@ -8,17 +8,19 @@
 //                            P1h_uv  = rhom * sum_m  q_uv[m] * G_u[k,m] * G_v[k,m]       (:479)
 //                          where G_u is the single grid a Fourier profile was built from (Uk, or Wk when
 //                          amplitude=None; :874-881), so each (k,M) grid is read from HBM exactly once.
-//   hm_quad_stream_kernel  the HBM-bound kernel.  Persistent CTAs (one per SM); a producer warp feeds a shared-memory
-//                          ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of R-row x 512-mass
-//                          tiles of every tracer grid; 8 consumer warps keep the weights of their two mass columns
-//                          in registers, accumulate R*(P+S) partial sums, reduce them with a transposing
-//                          warp-shuffle network and one shared-memory pass, and write per-mass-slice row sums.
+//   hm_quad_stream_kernel  the HBM-bound kernel.  Persistent CTAs (one per SM); a producer warp feeds a 6-stage
+//                          shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of
+//                          R-row x 512-mass tiles of every tracer grid; 8 independent consumer warps keep the
+//                          weights of their two mass columns in registers, accumulate R*(P+S) sums, reduce them
+//                          over the warp with a transposing shuffle network and store the warp's partial row sums
+//                          (no CTA-wide synchronisation).  FM = 5 fuses the five mass functions of one sample.
 //   hm_quad_kernel         fallback of the same arithmetic with plain (scalar or 16-byte) loads for odd nM,
 //                          unaligned grids or profiles with separate Uk/Wk grids.
-//   hm_epilogue_kernel     sums the mass slices in fixed order and forms P_2h = I_u I_v P_lin, the
+//   hm_beta2h_kernel       optional non-linear halo bias: I_NL = rhom^2 a_u^T beta_k a_v + edge terms (:546-571)
+//   hm_epilogue_kernel     adds the mass parts in fixed order and forms P_2h = (I_u I_v + I_NL) P_lin, the
 //                          discrete/shot-noise/k_trunc fix-ups and P_hm (:456-501).
 //
-// Algorithmic bytes per launch of the streaming kernel: 8*(G*P*nk*nM + B*(P+S)*nM + B*nslices*(P+S)*nk).
+// Algorithmic bytes per launch of the streaming kernel: 8*(G*P*nk*nM + B*(P+S)*nM).
 #include "hm_common.cuh"
 
 #define HM_MAXP HM_MAX_TRACERS
