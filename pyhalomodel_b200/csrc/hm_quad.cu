@@ -47,12 +47,13 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
 // ---------------------------------------------------------------------------------------------------------------
 #define HM_NSCAL 12
 #define HM_WCHUNK 256        // masses per CTA of the weights kernel
-#define HM_MC 512            // masses per slice of the streaming kernel (256 consumer threads x double2)
+#define HM_MC 512            // masses per slice of the streaming kernel per pair of columns a consumer thread owns
+                             // (256 consumer threads x double2); slices are HM_MC or 2*HM_MC wide
 #define HM_CONSUMER_WARPS 8
 #define HM_STREAM_THREADS (32 * (HM_CONSUMER_WARPS + 1))
 
 struct hm_layout {
-  int P, S, NW, nMp, nchunks, nslices, nparts;
+  int P, S, NW, nMp, nchunks, nslices, nparts, MC;
   bool stream;
   size_t B, scal_offset, cpart_offset, partial_offset, inl_offset, total_bytes;
 };
@@ -74,7 +75,10 @@ static hm_layout hm_make_layout(const hm_problem* pr) {
   L.nMp = (pr->nM + 1) & ~1;
   L.nchunks = (L.nMp + HM_WCHUNK - 1) / HM_WCHUNK;
   L.stream = hm_can_stream(pr);
-  L.nslices = L.stream ? (pr->nM + HM_MC - 1) / HM_MC : 1;
+  // wide slices (4 mass columns per consumer thread) halve the partial sums and the reductions per byte; they fit
+  // the register budget up to 3 tracers and are used when the mass axis is long enough to fill them
+  L.MC = (pr->nM >= 2 * HM_MC && L.P <= 3 && pr->models_per_sample != 5) ? 2 * HM_MC : HM_MC;
+  L.nslices = L.stream ? (pr->nM + L.MC - 1) / L.MC : 1;
   L.nparts = L.stream ? L.nslices * HM_CONSUMER_WARPS : 1;
   L.B = (size_t)pr->n_samples * (size_t)pr->models_per_sample;
   auto align = [](size_t x) { return (x + 31) & ~(size_t)31; };
@@ -204,7 +208,7 @@ __global__ void __launch_bounds__(HM_WCHUNK) hm_weights_kernel(const hm_weights_
 // Shared pieces of the two quadrature kernels
 // ---------------------------------------------------------------------------------------------------------------
 struct hm_quad_args {
-  int nk, nM, nMp, F, B, ntiles, nslices, nparts;
+  int nk, nM, nMp, F, B, ntiles, nslices, nparts, MC;
   long long nitems;
   const double* gridW[HM_MAXP];      // two-halo / cross source
   const double* gridU[HM_MAXP];      // auto one-halo source (== gridW unless HM_GRID_SEPARATE)
@@ -357,13 +361,14 @@ __device__ __forceinline__ void hm_bulk_g2s(uint32_t dst, const void* src, uint3
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <int P, int R>
+template <int P, int R, int H>      // H = pairs of mass columns per consumer thread (slice width H * HM_MC)
 struct hm_stream_cfg {
   static constexpr int S = P * (P + 1) / 2;
   static constexpr int NW = P + S;
   static constexpr int NV = R * NW;
   static constexpr int NG = (NV + 31) / 32;
-  static constexpr int STAGE_DOUBLES = R * P * HM_MC;
+  static constexpr int MC = H * HM_MC;
+  static constexpr int STAGE_DOUBLES = R * P * MC;
   static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
   static constexpr int BUDGET = 226 * 1024 - 256;
   static constexpr int NS = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
@@ -391,10 +396,11 @@ struct hm_item_cursor {
 // FM > 1: the FM models of one sample (e.g. the five mass functions evaluated on one cosmology) share its grids.
 // An item is then (sample, slice, tile): the tile is read from HBM ONCE and accumulated against FM weight sets
 // held in registers (BASELINE config 3), instead of once per model.
-template <int P, int R, int FM>
+template <int P, int R, int FM, int H>
+// 9 warps: one SM sub-partition (16K registers) hosts three of them, hence at most 168 registers per thread
 __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(const hm_quad_args a) {
-  using C = hm_stream_cfg<P, R>;
-  constexpr int NW = C::NW, NG = C::NG, NS = C::NS;
+  using C = hm_stream_cfg<P, R, H>;
+  constexpr int NW = C::NW, NS = C::NS, MC = C::MC;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* ring = reinterpret_cast<double*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)NS * C::STAGE_DOUBLES);    // full[NS], empty[NS]
@@ -425,8 +431,8 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
       int s = 0;
       uint32_t parity = 0;
       for (int n = 0; n < nloc; ++n) {
-        const int smp = (FM > 1) ? cur.b : cur.b / a.F, m0 = cur.slice * HM_MC, row0 = cur.tile * R;
-        const int cols = (a.nM - m0 < HM_MC) ? a.nM - m0 : HM_MC;
+        const int smp = (FM > 1) ? cur.b : cur.b / a.F, m0 = cur.slice * MC, row0 = cur.tile * R;
+        const int cols = (a.nM - m0 < MC) ? a.nM - m0 : MC;
         const uint32_t bytes = (uint32_t)cols * 8u;
         hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);        // slot drained by all consumer warps
         hm_mbar_arrive_expect_tx(bar_full + 8 * s, bytes * (uint32_t)(R * P));
@@ -437,7 +443,7 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
           const size_t off = ((size_t)smp * a.nk + row) * (size_t)a.nM + m0;
 #pragma unroll
           for (int p = 0; p < P; ++p)
-            hm_bulk_g2s(dst0 + (uint32_t)((r * P + p) * HM_MC * 8), a.gridW[p] + off, bytes, bar_full + 8 * s);
+            hm_bulk_g2s(dst0 + (uint32_t)((r * P + p) * MC * 8), a.gridW[p] + off, bytes, bar_full + 8 * s);
         }
         cur.next(a.nslices, a.ntiles);
         if (++s == NS) { s = 0; parity ^= 1u; }
@@ -446,53 +452,62 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
     return;
   }
 
-  // ---------------- consumers: 8 independent warps, 64 mass columns per warp, 2 per thread -----------------
-  // No CTA-wide synchronisation: every warp reduces its own 64 columns and writes its own partial row sums;
+  // ------- consumers: 8 independent warps, 64*H mass columns per warp, H column pairs per thread ------------
+  // No CTA-wide synchronisation: every warp reduces its own columns and writes its own partial row sums;
   // the epilogue kernel adds the parts in fixed order.
-  double wv[FM][2][NW];
+  double wv[FM][H][2][NW];
   int cur_b = -1, cur_slice = -1;
   int s = 0;
   uint32_t parity = 0;
   for (int n = 0; n < nloc; ++n) {
-    const int m = cur.slice * HM_MC + 2 * tid, row0 = cur.tile * R;
-    const bool active = m < a.nM;
-    if (cur.b != cur_b || cur.slice != cur_slice) {   // weights of my two columns stay in registers for the slice
+    const int m0 = cur.slice * MC + 2 * tid, row0 = cur.tile * R;      // my pair h covers masses m0 + h*HM_MC + {0,1}
+    if (cur.b != cur_b || cur.slice != cur_slice) {   // weights of my columns stay in registers for the slice
       cur_b = cur.b; cur_slice = cur.slice;
 #pragma unroll
-      for (int f = 0; f < FM; ++f) {
-        const double* __restrict__ w = a.weights + ((size_t)cur.b * FM + f) * NW * a.nMp + m;
+      for (int f = 0; f < FM; ++f)
 #pragma unroll
-        for (int i = 0; i < NW; ++i) {
-          const double2 t = active ? *reinterpret_cast<const double2*>(w + (size_t)i * a.nMp) : make_double2(0., 0.);
-          wv[f][0][i] = t.x; wv[f][1][i] = t.y;
+        for (int h = 0; h < H; ++h) {
+          const int m = m0 + h * HM_MC;
+          const double* __restrict__ w = a.weights + ((size_t)cur.b * FM + f) * NW * a.nMp + m;
+#pragma unroll
+          for (int i = 0; i < NW; ++i) {
+            const double2 t = (m < a.nM) ? *reinterpret_cast<const double2*>(w + (size_t)i * a.nMp) : make_double2(0., 0.);
+            wv[f][h][0][i] = t.x; wv[f][h][1][i] = t.y;
+          }
         }
-      }
     }
-    hm_mbar_wait(bar_full + 8 * s, parity);                  // TMA bytes have landed
-    const double* st = ring + (size_t)s * C::STAGE_DOUBLES + 2 * tid;
-    double x[2][R][P];
-    const double xu[1][1] = {{0.}};
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        const double2 t = active ? *reinterpret_cast<const double2*>(st + (r * P + p) * HM_MC) : make_double2(0., 0.);
-        x[0][r][p] = t.x; x[1][r][p] = t.y;
-      }
-    __syncwarp();
-    if (lane == 0) hm_mbar_arrive(bar_empty + 8 * s);        // values are in registers: release the slot early
-
-    // all FM*R*NW sums of this tile go through ONE transposing reduction (lane j ends up with value j)
     constexpr int NVF = FM * R * NW, NGF = (NVF + 31) / 32;
-    const int nvalid = ((a.nk - row0 < R) ? a.nk - row0 : R) * NW;
     double acc[NGF * 32];
 #pragma unroll
     for (int i = 0; i < NGF * 32; ++i) acc[i] = 0.;
+    const double xu[1][1] = {{0.}};
+    hm_mbar_wait(bar_full + 8 * s, parity);                  // TMA bytes have landed
+    const double* st = ring + (size_t)s * C::STAGE_DOUBLES + 2 * tid;
 #pragma unroll
-    for (int f = 0; f < FM; ++f) {
-      hm_accumulate<P, R, false>(acc + f * R * NW, wv[f][0], x[0], xu);
-      hm_accumulate<P, R, false>(acc + f * R * NW, wv[f][1], x[1], xu);
+    for (int h = 0; h < H; ++h) {
+      const bool active = m0 + h * HM_MC < a.nM;
+      double x[2][R][P];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          const double2 t = active ? *reinterpret_cast<const double2*>(st + (r * P + p) * MC + h * HM_MC)
+                                   : make_double2(0., 0.);
+          x[0][r][p] = t.x; x[1][r][p] = t.y;
+        }
+      if (h == H - 1) {                                      // all my values are in registers: release the slot early
+        __syncwarp();
+        if (lane == 0) hm_mbar_arrive(bar_empty + 8 * s);
+      }
+#pragma unroll
+      for (int f = 0; f < FM; ++f) {
+        hm_accumulate<P, R, false>(acc + f * R * NW, wv[f][h][0], x[0], xu);
+        hm_accumulate<P, R, false>(acc + f * R * NW, wv[f][h][1], x[1], xu);
+      }
     }
+
+    // all FM*R*NW sums of this tile go through ONE transposing reduction (lane j ends up with value j)
+    const int nvalid = ((a.nk - row0 < R) ? a.nk - row0 : R) * NW;
 #pragma unroll
     for (int g = 0; g < NGF; ++g) {
       double v[32];
@@ -852,12 +867,12 @@ static int hm_launch_fallback(hm_quad_args& a, bool vec2, bool sep, cudaStream_t
   return HM_OK;
 }
 
-template <int P, int R, int FM>
+template <int P, int R, int FM, int H>
 static int hm_launch_stream_fm(hm_quad_args& a, cudaStream_t st) {
-  using C = hm_stream_cfg<P, R>;
+  using C = hm_stream_cfg<P, R, H>;
   static bool configured = false;
   if (!configured) {
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_quad_stream_kernel<P, R, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_quad_stream_kernel<P, R, FM, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM_BYTES));
     configured = true;
   }
@@ -865,7 +880,7 @@ static int hm_launch_stream_fm(hm_quad_args& a, cudaStream_t st) {
   a.nitems = (long long)(a.B / FM) * a.nslices * a.ntiles;     // FM > 1: items enumerate samples, not models
   long long grid = hm_num_sms();
   if (grid > a.nitems) grid = a.nitems;
-  hm_quad_stream_kernel<P, R, FM><<<(int)grid, HM_STREAM_THREADS, C::SMEM_BYTES, st>>>(a);
+  hm_quad_stream_kernel<P, R, FM, H><<<(int)grid, HM_STREAM_THREADS, C::SMEM_BYTES, st>>>(a);
   HM_LAUNCH_CHECK();
   return HM_OK;
 }
@@ -875,9 +890,12 @@ static int hm_launch_stream(hm_quad_args& a, cudaStream_t st) {
   // the fused multi-family variant holds F weight sets in registers: instantiated where they fit (P <= 2, F = 5:
   // the five mass functions of BASELINE config 3); other combinations read the shared grids once per model
   if constexpr (P <= 2) {
-    if (a.F == 5) return hm_launch_stream_fm<P, (P == 1 ? 3 : 1), 5>(a, st);   // 30 / 25 sums: one reduction
+    if (a.F == 5) return hm_launch_stream_fm<P, (P == 1 ? 3 : 1), 5, 1>(a, st);   // 30 / 25 sums: one reduction
   }
-  return hm_launch_stream_fm<P, R, 1>(a, st);
+  if constexpr (P <= 3) {
+    if (a.MC == 2 * HM_MC) return hm_launch_stream_fm<P, R, 1, 2>(a, st);
+  }
+  return hm_launch_stream_fm<P, R, 1, 1>(a, st);
 }
 
 template <int P>
@@ -903,7 +921,7 @@ extern "C" int hm_mass_quadrature_stages(const hm_problem* pr, double* out_dev, 
   if ((rc = hm_check_workspace("hm_mass_quadrature", L, ws, ws_bytes))) return rc;
   hm_quad_args a;
   a.nk = pr->nk; a.nM = pr->nM; a.nMp = L.nMp; a.F = pr->models_per_sample; a.B = (int)L.B; a.nslices = L.nslices;
-  a.nparts = L.nparts;
+  a.nparts = L.nparts; a.MC = L.MC;
   bool sep = false, aligned = (pr->nM % 2 == 0);
   for (int p = 0; p < HM_MAXP; ++p) {
     const bool on = p < L.P;
