@@ -43,7 +43,7 @@ def parse():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--batch', type=int, default=32, help='models per GPU per step')
+    ap.add_argument('--batch', type=int, default=64, help='models per GPU per step')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-models', type=int, default=16, help='models in the bounded CPU-baseline sample')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
@@ -137,7 +137,7 @@ def run_reference(args, rank):
                                   sample='%d config-2 models per step, one per process, oracle.power_spectrum '
                                          '(numpy/scipy port of pyhalomodel.py:361-544)' % per_step),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -181,8 +181,24 @@ def pinned_numpy(arr):
     return a, t
 
 
+_STDOUT_FD = None
+
+
+def emit(line):
+    """Write the one JSON line to the process's original stdout."""
+    data = (json.dumps(line)+'\n').encode()
+    sys.stdout.flush()
+    os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, data)
+
+
 def main():
     args = parse()
+    # stdout carries the JSON line and nothing else: libraries that print to file descriptor 1 (NCCL's version
+    # banner, for one) are sent to stderr, and the line is written to the saved descriptor at the end
+    global _STDOUT_FD
+    sys.stdout.flush()
+    _STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     if args.impl == 'reference':
@@ -194,7 +210,11 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        # gloo carries the control plane (barriers, max over ranks of the timings); the NCCL communicator is created
+        # lazily by the first CUDA collective, which is the all-gather that checks the fused gather AFTER all the
+        # timed regions.  Measured on this stack (tools/dev_multi_probe.py): once an NCCL communicator exists in the
+        # process, the streaming kernel runs 6 % slower (262 -> 277 us), whatever NCCL's transport settings.
+        dist.init_process_group('cpu:gloo,cuda:nccl')
     import pyhalomodel_b200.pyhalomodel as halo
     from pyhalomodel_b200 import engine, workloads
 
@@ -221,10 +241,19 @@ def main():
         else:
             pipe.submit()
 
+    token = torch.zeros(1, dtype=torch.float64)
+
     def barrier():
-        if world > 1:
-            dist.barrier()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.all_reduce(token)           # CPU tensor: gloo
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # ---- HBM-resident throughput ------------------------------------------------------------------------------
     for _ in range(W):
@@ -244,26 +273,9 @@ def main():
     e1.record()                  # (the barrier below completes the gather: all peer stores have landed on rank 0)
     barrier()
     t1 = time.perf_counter()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
     value = world*B*S*K/(ms_total*1e-3)
-
-    gather_ok = None
-    if world > 1:                # check the fused gather against the NCCL baseline (outside the timed region)
-        mine = plan.run()[0].clone()
-        torch.cuda.synchronize()
-        ref_all = sweep.gather_spectra(mine, world*B)
-        if rank == 0:
-            got = peer.local[:, (K-1) % peer.slots].reshape(ref_all.shape)
-            gather_ok = bool(torch.equal(got, ref_all))
-            if not gather_ok:
-                bad = (got != ref_all)
-                print('gather mismatch: %d of %d elements; per rank %s; first slots equal %s' % (
-                    int(bad.sum()), bad.numel(), [int(b.sum()) for b in bad.reshape(world, -1)],
-                    [bool(torch.equal(peer.local[:, i].reshape(ref_all.shape), ref_all)) for i in range(peer.slots)]),
-                    file=sys.stderr)
+    gathered = peer.local[:, (K-1) % peer.slots].clone() if (world > 1 and rank == 0) else None
 
     # ---- roofline of the dominant kernel (the streaming mass-quadrature kernel alone), CUDA events on the
     # launching stream; the weights and epilogue kernels are timed the same way for the step breakdown ----------
@@ -298,7 +310,7 @@ def main():
         tj = json.load(open(tpath))
         if tj.get('batch') == B:
             traffic = tj.get('dram_bytes_per_launch')
-    roofline = dict(bound='hbm', kernel='hm_quad_stream_kernel<3,3,1>', achieved=achieved, peak=peak, unit='GB/s',
+    roofline = dict(bound='hbm', kernel='hm_quad_stream_kernel<3,3,1,2>', achieved=achieved, peak=peak, unit='GB/s',
                     frac=achieved/peak, traffic=traffic, algorithmic_bytes_per_launch=alg_bytes,
                     kernel_ms=quad_ms, epilogue_kernel_ms=epi_ms, weights_kernel_ms=weights_ms,
                     step_algorithmic_bytes=plan.algorithmic_bytes(),
@@ -345,13 +357,25 @@ def main():
     ee1.record()
     barrier()
     e2e_wall = time.perf_counter()-tt0
-    e2e_ms = torch.tensor([max(ee0.elapsed_time(ee1), 1e3*e2e_wall)], dtype=torch.float64, device='cuda')
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e = dict(value=world*n_e2e*S*e2e_steps/(float(e2e_ms.item())*1e-3), unit=UNIT,
+    e2e_ms = max_over_ranks(max(ee0.elapsed_time(ee1), 1e3*e2e_wall))
+    e2e = dict(value=world*n_e2e*S*e2e_steps/(e2e_ms*1e-3), unit=UNIT,
                h2d_bytes_per_step=h2d_model*n_e2e, d2h_bytes_per_step=d2h_model*n_e2e,
                models_per_step=n_e2e, steps=e2e_steps,
                path='profile.Fourier(host numpy) x3 + model.power_spectrum -> numpy, per model')
+
+    # ---- the fused gather against the NCCL baseline (first NCCL collective of the process, after all timing) ---
+    gather_ok = None
+    if world > 1:
+        mine = plan.run()[0].clone()
+        torch.cuda.synchronize()
+        ref_all = sweep.gather_spectra(mine, world*B)
+        if rank == 0:
+            got = gathered.reshape(ref_all.shape)
+            gather_ok = bool(torch.equal(got, ref_all))
+            if not gather_ok:
+                bad = (got != ref_all)
+                print('gather mismatch: %d of %d elements; per rank %s' % (
+                    int(bad.sum()), bad.numel(), [int(b.sum()) for b in bad.reshape(world, -1)]), file=sys.stderr)
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------------------
     cpu = None
@@ -360,7 +384,11 @@ def main():
         cpu = cpu_baseline_serial(cases)
         # parity spot check of what was just timed: GPU batch sample 0 vs the oracle on the same inputs
         _, ref0 = _oracle_one(cases[0])
-        cpu['parity_mm_k0'] = abs(float(plan.out[0, 0, 2, 0].item())/ref0-1.)
+        out0 = plan.run()[0]
+        torch.cuda.synchronize()
+        cpu['parity_mm_k0'] = abs(float(out0[0, 0, 2, 0].item())/ref0-1.)
+        if not cpu['parity_mm_k0'] < 1e-10:
+            raise SystemExit('bench: GPU spectrum differs from the oracle on the timed inputs (rel %.3e)' % cpu['parity_mm_k0'])
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total/K,
@@ -370,7 +398,7 @@ def main():
                                 % (B*len(TRACERS)*NK*NM*8/1e6), collective=('gather to rank 0 fused into the epilogue kernel (peer stores over NVLink into a symmetric buffer); '
                                             'verified against NCCL all_gather: %s' % gather_ok) if world > 1 else 'none'),
                     clocks=clocks, e2e=e2e, gpu_launches=3*K, roofline=roofline, cpu_baseline=cpu)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
