@@ -51,10 +51,15 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
                              // (256 consumer threads x double2); slices are HM_MC or 2*HM_MC wide
 #define HM_CONSUMER_WARPS 8
 #define HM_STREAM_THREADS (32 * (HM_CONSUMER_WARPS + 1))
+#define HM_ROWS_RG 1         // row-per-lane kernel: groups of 64 rows per item ...
+#define HM_ROWS_CS 64        // ... and mass columns per stage
+#define HM_ROWS_CG (HM_CONSUMER_WARPS / HM_ROWS_RG)
+#define HM_ROWS_PW 4         // ... fed by this many producer warps
+#define HM_ROWS_THREADS (32 * (HM_CONSUMER_WARPS + HM_ROWS_PW))
 
 struct hm_layout {
   int P, S, NW, nMp, nchunks, nslices, nparts, MC;
-  bool stream;
+  bool stream, rows;
   size_t B, scal_offset, cpart_offset, partial_offset, inl_offset, total_bytes;
 };
 
@@ -80,6 +85,10 @@ static hm_layout hm_make_layout(const hm_problem* pr) {
   L.MC = (pr->nM >= 2 * HM_MC && L.P <= 3 && pr->models_per_sample != 5) ? 2 * HM_MC : HM_MC;
   L.nslices = L.stream ? (pr->nM + L.MC - 1) / L.MC : 1;
   L.nparts = L.stream ? L.nslices * HM_CONSUMER_WARPS : 1;
+  // five mass functions per sample on one or two tracers (BASELINE config 3): the row-per-lane kernel reads the
+  // shared grids once for all five and leaves one part per column group of warps
+  L.rows = L.stream && pr->models_per_sample == 5 && L.P <= 2;
+  if (L.rows) { L.nslices = 1; L.nparts = HM_ROWS_CG; }
   L.B = (size_t)pr->n_samples * (size_t)pr->models_per_sample;
   auto align = [](size_t x) { return (x + 31) & ~(size_t)31; };
   L.scal_offset = align(L.B * (size_t)L.NW * (size_t)L.nMp);
@@ -361,6 +370,14 @@ __device__ __forceinline__ void hm_bulk_g2s(uint32_t dst, const void* src, uint3
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// 16-byte LDGSTS (global -> shared without registers, L2 only) and its completion on an mbarrier
+__device__ __forceinline__ void hm_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void hm_cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 template <int P, int R, int H>      // H = pairs of mass columns per consumer thread (slice width H * HM_MC)
 struct hm_stream_cfg {
   static constexpr int S = P * (P + 1) / 2;
@@ -523,6 +540,201 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
     }
     cur.next(a.nslices, a.ntiles);
     if (++s == NS) { s = 0; parity ^= 1u; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row-per-lane streaming kernel for sweeps that evaluate FM models (mass functions) on the grids of one sample.
+//
+// With FM*(P+S) = 25 sums per grid row and only 16 bytes of grid per (k, M) point, the column-per-lane kernel above
+// drowns in its warp reductions (one 32-value shuffle network per 50 FMAs; ncu: 423 instructions per warp tile,
+// FP64 pipe 29 %).  Here a lane owns two wavenumber rows (lane and lane + 32 of a 64-row group) for the whole mass
+// axis, so its FM*(P+S) sums per row stay in registers from the first mass to the last and nothing is ever
+// reduced across lanes.  The weights of a mass column are the same for every lane: they ride in the ring next to
+// the grid tile (cp.async copies of the same [model][i][m] vectors the other kernels use) and are read with broadcast
+// 16-byte shared-memory loads, one load feeding four FMAs (two rows x two columns).  The grid rows of a stage are
+// padded by 16 bytes so that the eight lanes of a quarter warp hit eight different 16-byte bank groups.
+// An item is (sample, 64*RG-row tile); the 8 consumer warps split into RG row groups x CG column groups, and every
+// warp writes its sums once per item: partial[model][cg][row][i], combined by the epilogue in fixed order.
+// ---------------------------------------------------------------------------------------------------------------
+template <int P, int FM, int RG, int CS>
+struct hm_rows_cfg {
+  static constexpr int S = P * (P + 1) / 2;
+  static constexpr int NW = P + S;
+  static constexpr int NV = FM * NW;                          // sums per grid row
+  static constexpr int CG = HM_CONSUMER_WARPS / RG;           // column groups of warps = mass parts
+  static constexpr int CW = CS / CG;                          // columns per warp per stage
+  static constexpr int RT = 64 * RG;                          // rows per item
+  static constexpr int ROWB = CS * 8 + 16;                    // padded pitch of a grid row in the ring
+  static constexpr int DATA_BYTES = RT * P * ROWB;
+  static constexpr int W_BYTES = NV * CS * 8;
+  static constexpr int STAGE_BYTES = ((DATA_BYTES + W_BYTES + 127) / 128) * 128;
+  static constexpr int BUDGET = 226 * 1024 - 256;
+  static constexpr int NS = (BUDGET / STAGE_BYTES) > 4 ? 4 : (BUDGET / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = NS * STAGE_BYTES + 256;
+  static_assert(CW >= 2 && CW % 2 == 0, "a warp works on pairs of columns");
+  static_assert(NS >= 2, "the ring needs two stages");
+};
+
+template <int P, int FM, int RG, int CS>
+__global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const hm_quad_args a) {
+  using C = hm_rows_cfg<P, FM, RG, CS>;
+  constexpr int NW = C::NW, NV = C::NV, NS = C::NS, RT = C::RT, ROWB = C::ROWB;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * C::STAGE_BYTES);   // full[NS], empty[NS]
+  const uint32_t ring = hm_smem_addr(smem_raw);
+  const uint32_t bar_full = hm_smem_addr(bars), bar_empty = hm_smem_addr(bars + NS);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      hm_mbar_init(bar_full + 8 * s, 32 * HM_ROWS_PW);    // every producer lane (cp.async arrive, .noinc)
+      hm_mbar_init(bar_empty + 8 * s, HM_CONSUMER_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // contiguous range of (sample, row tile) items for this CTA; every item walks the whole mass axis
+  const long long per = (a.nitems + gridDim.x - 1) / gridDim.x;
+  const long long it0 = (long long)blockIdx.x * per;
+  const long long it1 = (it0 + per < a.nitems) ? it0 + per : a.nitems;
+  if (it0 >= it1) return;
+  const int nstages = (a.nM + CS - 1) / CS;
+  int smp = (int)(it0 / a.ntiles), tile = (int)(it0 - (long long)smp * a.ntiles);
+  int s = 0;
+  uint32_t parity = 0;
+
+  if (warp >= HM_CONSUMER_WARPS) {
+    // ---- producer warps: one 16-byte cp.async per lane and row (LDGSTS: a whole 512-byte row segment per warp
+    // instruction, landing at the padded pitch); the lanes' copies complete on the stage's mbarrier.  Producer warp
+    // pw moves rows pw, pw + PW, ... ; addresses are base + constant * stride so that the copies issue back to back.
+    // (153 separate 512-byte TMA bulk copies per stage serialise on the SM's one TMA unit: 654 us per launch.) ----
+    static_assert(CS == 64, "one warp instruction moves one row segment of 64 columns");
+    static_assert(RT % HM_ROWS_PW == 0, "rows split evenly over the producer warps");
+    constexpr int PW = HM_ROWS_PW;
+    const int pw = warp - HM_CONSUMER_WARPS;
+    const int nk = a.nk, nM = a.nM, ntiles = a.ntiles;
+    const uint32_t rowstep = (uint32_t)nM * 8u * PW, wstep = (uint32_t)a.nMp * 8u * PW;
+    for (long long it = it0; it < it1; ++it) {
+      const int row0 = tile * RT;
+      const bool full_tile = row0 + RT <= nk;
+      const char* gsrc[P];
+#pragma unroll
+      for (int p = 0; p < P; ++p)
+        gsrc[p] = reinterpret_cast<const char*>(a.gridW[p] + ((size_t)smp * nk + row0 + (full_tile ? pw : 0)) * (size_t)nM + 2 * lane);
+      const char* wsrc = reinterpret_cast<const char*>(a.weights + ((size_t)smp * NV + pw) * (size_t)a.nMp + 2 * lane);
+      for (int st = 0; st < nstages; ++st) {
+        const int m0 = st * CS;
+        const bool on = 2 * lane < nM - m0;
+        if (lane == 0) hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);      // slot drained by all consumer warps
+        __syncwarp();
+        const uint32_t dst0 = ring + (uint32_t)s * C::STAGE_BYTES + 16u * lane + (uint32_t)pw * ROWB;
+        if (on) {
+          if (full_tile) {
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+#pragma unroll
+              for (int i = 0; i < RT / PW; ++i)
+                hm_cp_async16(dst0 + (uint32_t)(p * RT + PW * i) * ROWB, gsrc[p] + (size_t)m0 * 8 + (size_t)((uint32_t)i * rowstep));
+          } else {                                            // last tile of a ragged k axis: clamp (never written)
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+#pragma unroll 4
+              for (int i = 0; i < RT / PW; ++i) {
+                const int r = (row0 + pw + PW * i < nk) ? pw + PW * i : nk - 1 - row0;
+                hm_cp_async16(dst0 + (uint32_t)(p * RT + PW * i) * ROWB, gsrc[p] + ((size_t)r * nM + m0) * 8);
+              }
+          }
+          const uint32_t wdst = ring + (uint32_t)s * C::STAGE_BYTES + C::DATA_BYTES + 16u * lane + (uint32_t)pw * (CS * 8);
+#pragma unroll
+          for (int i = 0; i < (NV + PW - 1) / PW; ++i)
+            if (pw + PW * i < NV)
+              hm_cp_async16(wdst + (uint32_t)(PW * i) * (CS * 8), wsrc + (size_t)m0 * 8 + (size_t)((uint32_t)i * wstep));
+        }
+        hm_cp_async_mbar_arrive(bar_full + 8 * s);                        // fires when my copies have landed
+        if (++s == NS) { s = 0; parity ^= 1u; }
+      }
+      if (++tile == ntiles) { tile = 0; ++smp; }
+    }
+    return;
+  }
+
+  // ------------------------------------------- consumer warps --------------------------------------------------
+  const int rg = warp % RG, cg = warp / RG;
+  const int cbeg = cg * C::CW;
+  const uint32_t my_row = (uint32_t)(rg * 64 + lane) * ROWB;          // my first row inside a tracer's block of rows
+  for (long long it = it0; it < it1; ++it) {
+    double acc[2][NV];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int j = 0; j < NV; ++j) acc[r][j] = 0.;
+    for (int st = 0; st < nstages; ++st) {
+      const int cols = (a.nM - st * CS < CS) ? a.nM - st * CS : CS;
+      const int cend = (cbeg + C::CW < cols) ? cbeg + C::CW : cols;
+      const unsigned char* stage = smem_raw + (size_t)s * C::STAGE_BYTES;
+      const unsigned char* wsm = stage + C::DATA_BYTES;
+      hm_mbar_wait(bar_full + 8 * s, parity);                 // TMA bytes have landed
+#pragma unroll 1
+      for (int c = cbeg; c < cend; c += 2) {
+        double2 x[2][P];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int p = 0; p < P; ++p)
+            x[r][p] = *reinterpret_cast<const double2*>(stage + my_row + (uint32_t)(p * RT + r * 32) * ROWB + c * 8);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+          // basis value i of my two rows and two columns: G_p, G_p^2, G_u G_v in the order of the weight vectors
+          double2 v[2];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            if (i < P) {
+              v[r] = x[r][i];
+            } else if (i < 2 * P) {
+              v[r] = make_double2(x[r][i - P].x * x[r][i - P].x, x[r][i - P].y * x[r][i - P].y);
+            } else {
+              int idx = 2 * P, uu = 0, vv = 1;
+#pragma unroll
+              for (int u = 0; u < P; ++u)
+#pragma unroll
+                for (int w = u + 1; w < P; ++w) {
+                  if (idx == i) { uu = u; vv = w; }
+                  ++idx;
+                }
+              v[r] = make_double2(x[r][uu].x * x[r][vv].x, x[r][uu].y * x[r][vv].y);
+            }
+          }
+#pragma unroll
+          for (int f = 0; f < FM; ++f) {
+            const double2 w2 = *reinterpret_cast<const double2*>(wsm + ((f * NW + i) * CS + c) * 8);   // broadcast
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              acc[r][f * NW + i] = fma(w2.x, v[r].x, acc[r][f * NW + i]);
+              acc[r][f * NW + i] = fma(w2.y, v[r].y, acc[r][f * NW + i]);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) hm_mbar_arrive(bar_empty + 8 * s);       // my reads of the slot are done
+      if (++s == NS) { s = 0; parity ^= 1u; }
+    }
+    // my two rows of this item: sums over the columns of my group, one part per column group
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int row = tile * RT + rg * 64 + r * 32 + lane;
+      if (row < a.nk) {
+#pragma unroll
+        for (int f = 0; f < FM; ++f) {
+          double* dst = a.partial + ((((size_t)smp * FM + f) * a.nparts + cg) * a.nk + row) * NW;
+#pragma unroll
+          for (int i = 0; i < NW; ++i) dst[i] = acc[r][f * NW + i];
+        }
+      }
+    }
+    if (++tile == a.ntiles) { tile = 0; ++smp; }
   }
 }
 
@@ -885,12 +1097,30 @@ static int hm_launch_stream_fm(hm_quad_args& a, cudaStream_t st) {
   return HM_OK;
 }
 
+template <int P, int FM>
+static int hm_launch_rows(hm_quad_args& a, cudaStream_t st) {
+  using C = hm_rows_cfg<P, FM, HM_ROWS_RG, HM_ROWS_CS>;
+  static bool configured = false;
+  if (!configured) {
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_quad_rows_kernel<P, FM, HM_ROWS_RG, HM_ROWS_CS>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    configured = true;
+  }
+  a.ntiles = (a.nk + C::RT - 1) / C::RT;
+  a.nitems = (long long)(a.B / FM) * a.ntiles;                 // items enumerate (sample, row tile)
+  long long grid = hm_num_sms();
+  if (grid > a.nitems) grid = a.nitems;
+  hm_quad_rows_kernel<P, FM, HM_ROWS_RG, HM_ROWS_CS><<<(int)grid, HM_ROWS_THREADS, C::SMEM_BYTES, st>>>(a);
+  HM_LAUNCH_CHECK();
+  return HM_OK;
+}
+
 template <int P, int R>
 static int hm_launch_stream(hm_quad_args& a, cudaStream_t st) {
   // the fused multi-family variant holds F weight sets in registers: instantiated where they fit (P <= 2, F = 5:
   // the five mass functions of BASELINE config 3); other combinations read the shared grids once per model
   if constexpr (P <= 2) {
-    if (a.F == 5) return hm_launch_stream_fm<P, (P == 1 ? 3 : 1), 5, 1>(a, st);   // 30 / 25 sums: one reduction
+    if (a.F == 5) return hm_launch_rows<P, 5>(a, st);         // must agree with hm_layout.rows
   }
   if constexpr (P <= 3) {
     if (a.MC == 2 * HM_MC) return hm_launch_stream_fm<P, R, 1, 2>(a, st);
