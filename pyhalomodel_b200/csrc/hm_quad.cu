@@ -52,7 +52,7 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
 #define HM_CONSUMER_WARPS 8
 #define HM_STREAM_THREADS (32 * (HM_CONSUMER_WARPS + 1))
 #define HM_ROWS_RG 1         // row-per-lane kernel: groups of 64 rows per item ...
-#define HM_ROWS_CS 64        // ... and mass columns per stage
+#define HM_ROWS_CS 32        // ... and mass columns per stage
 #define HM_ROWS_CG (HM_CONSUMER_WARPS / HM_ROWS_RG)
 #define HM_ROWS_PW 4         // ... fed by this many producer warps
 #define HM_ROWS_THREADS (32 * (HM_CONSUMER_WARPS + HM_ROWS_PW))
@@ -555,7 +555,9 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
 // 16-byte shared-memory loads, one load feeding four FMAs (two rows x two columns).  The grid rows of a stage are
 // padded by 16 bytes so that the eight lanes of a quarter warp hit eight different 16-byte bank groups.
 // An item is (sample, 64*RG-row tile); the 8 consumer warps split into RG row groups x CG column groups, and every
-// warp writes its sums once per item: partial[model][cg][row][i], combined by the epilogue in fixed order.
+// warp writes its sums once per item: partial[model][cg][i][row], combined by the epilogue in fixed order.
+// Items are dealt round-robin (CTA c takes c, c + grid, ...), so the row tiles of one sample run at the same time
+// on neighbouring SMs and its weight vectors come from DRAM once and from L2 for the other tiles.
 // ---------------------------------------------------------------------------------------------------------------
 template <int P, int FM, int RG, int CS>
 struct hm_rows_cfg {
@@ -570,7 +572,7 @@ struct hm_rows_cfg {
   static constexpr int W_BYTES = NV * CS * 8;
   static constexpr int STAGE_BYTES = ((DATA_BYTES + W_BYTES + 127) / 128) * 128;
   static constexpr int BUDGET = 226 * 1024 - 256;
-  static constexpr int NS = (BUDGET / STAGE_BYTES) > 4 ? 4 : (BUDGET / STAGE_BYTES);
+  static constexpr int NS = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
   static constexpr int SMEM_BYTES = NS * STAGE_BYTES + 256;
   static_assert(CW >= 2 && CW % 2 == 0, "a warp works on pairs of columns");
   static_assert(NS >= 2, "the ring needs two stages");
@@ -595,11 +597,9 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
   }
   __syncthreads();
 
-  // contiguous range of (sample, row tile) items for this CTA; every item walks the whole mass axis
-  const long long per = (a.nitems + gridDim.x - 1) / gridDim.x;
-  const long long it0 = (long long)blockIdx.x * per;
-  const long long it1 = (it0 + per < a.nitems) ? it0 + per : a.nitems;
-  if (it0 >= it1) return;
+  // (sample, row tile) items dealt round-robin over the CTAs; every item walks the whole mass axis
+  const long long it0 = blockIdx.x, it1 = a.nitems;
+  const int istep = gridDim.x, step_smp = istep / a.ntiles, step_tile = istep - step_smp * a.ntiles;
   const int nstages = (a.nM + CS - 1) / CS;
   int smp = (int)(it0 / a.ntiles), tile = (int)(it0 - (long long)smp * a.ntiles);
   int s = 0;
@@ -610,52 +610,58 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
     // instruction, landing at the padded pitch); the lanes' copies complete on the stage's mbarrier.  Producer warp
     // pw moves rows pw, pw + PW, ... ; addresses are base + constant * stride so that the copies issue back to back.
     // (153 separate 512-byte TMA bulk copies per stage serialise on the SM's one TMA unit: 654 us per launch.) ----
-    static_assert(CS == 64, "one warp instruction moves one row segment of 64 columns");
-    static_assert(RT % HM_ROWS_PW == 0, "rows split evenly over the producer warps");
     constexpr int PW = HM_ROWS_PW;
+    constexpr int LPR = CS / 2;                 // lanes per row segment (16 bytes each)
+    constexpr int RPI = 32 / LPR;               // rows per warp instruction
+    static_assert(LPR == 32 || LPR == 16, "a warp instruction moves one or two whole row segments");
+    static_assert(RT % (PW * RPI) == 0, "rows split evenly over the producer warps");
     const int pw = warp - HM_CONSUMER_WARPS;
+    const int lrow = lane / LPR, lcol = 2 * (lane % LPR);          // my row inside an instruction, my first column
     const int nk = a.nk, nM = a.nM, ntiles = a.ntiles;
-    const uint32_t rowstep = (uint32_t)nM * 8u * PW, wstep = (uint32_t)a.nMp * 8u * PW;
-    for (long long it = it0; it < it1; ++it) {
+    const uint32_t rowstep = (uint32_t)nM * 8u * (PW * RPI), wstep = (uint32_t)a.nMp * 8u * (PW * RPI);
+    const int r_first = pw * RPI + lrow;                           // my rows: r_first + PW*RPI*i
+    for (long long it = it0; it < it1; it += istep) {
       const int row0 = tile * RT;
       const bool full_tile = row0 + RT <= nk;
       const char* gsrc[P];
 #pragma unroll
       for (int p = 0; p < P; ++p)
-        gsrc[p] = reinterpret_cast<const char*>(a.gridW[p] + ((size_t)smp * nk + row0 + (full_tile ? pw : 0)) * (size_t)nM + 2 * lane);
-      const char* wsrc = reinterpret_cast<const char*>(a.weights + ((size_t)smp * NV + pw) * (size_t)a.nMp + 2 * lane);
+        gsrc[p] = reinterpret_cast<const char*>(a.gridW[p] + ((size_t)smp * nk + row0 + (full_tile ? r_first : 0)) * (size_t)nM + lcol);
+      const char* wsrc = reinterpret_cast<const char*>(a.weights + ((size_t)smp * NV + (r_first < NV ? r_first : 0)) * (size_t)a.nMp + lcol);
       for (int st = 0; st < nstages; ++st) {
         const int m0 = st * CS;
-        const bool on = 2 * lane < nM - m0;
+        const bool on = lcol < nM - m0;
         if (lane == 0) hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);      // slot drained by all consumer warps
         __syncwarp();
-        const uint32_t dst0 = ring + (uint32_t)s * C::STAGE_BYTES + 16u * lane + (uint32_t)pw * ROWB;
+        const uint32_t dst0 = ring + (uint32_t)s * C::STAGE_BYTES + 8u * lcol + (uint32_t)r_first * ROWB;
         if (on) {
           if (full_tile) {
 #pragma unroll
             for (int p = 0; p < P; ++p)
 #pragma unroll
-              for (int i = 0; i < RT / PW; ++i)
-                hm_cp_async16(dst0 + (uint32_t)(p * RT + PW * i) * ROWB, gsrc[p] + (size_t)m0 * 8 + (size_t)((uint32_t)i * rowstep));
+              for (int i = 0; i < RT / (PW * RPI); ++i)
+                hm_cp_async16(dst0 + (uint32_t)(p * RT + PW * RPI * i) * ROWB,
+                              gsrc[p] + (size_t)m0 * 8 + (size_t)((uint32_t)i * rowstep));
           } else {                                            // last tile of a ragged k axis: clamp (never written)
 #pragma unroll
             for (int p = 0; p < P; ++p)
 #pragma unroll 4
-              for (int i = 0; i < RT / PW; ++i) {
-                const int r = (row0 + pw + PW * i < nk) ? pw + PW * i : nk - 1 - row0;
-                hm_cp_async16(dst0 + (uint32_t)(p * RT + PW * i) * ROWB, gsrc[p] + ((size_t)r * nM + m0) * 8);
+              for (int i = 0; i < RT / (PW * RPI); ++i) {
+                const int r = (row0 + r_first + PW * RPI * i < nk) ? r_first + PW * RPI * i : nk - 1 - row0;
+                hm_cp_async16(dst0 + (uint32_t)(p * RT + PW * RPI * i) * ROWB, gsrc[p] + ((size_t)r * nM + m0) * 8);
               }
           }
-          const uint32_t wdst = ring + (uint32_t)s * C::STAGE_BYTES + C::DATA_BYTES + 16u * lane + (uint32_t)pw * (CS * 8);
+          const uint32_t wdst = ring + (uint32_t)s * C::STAGE_BYTES + C::DATA_BYTES + 8u * lcol + (uint32_t)r_first * (CS * 8);
 #pragma unroll
-          for (int i = 0; i < (NV + PW - 1) / PW; ++i)
-            if (pw + PW * i < NV)
-              hm_cp_async16(wdst + (uint32_t)(PW * i) * (CS * 8), wsrc + (size_t)m0 * 8 + (size_t)((uint32_t)i * wstep));
+          for (int i = 0; i < (NV + PW * RPI - 1) / (PW * RPI); ++i)
+            if (r_first + PW * RPI * i < NV)
+              hm_cp_async16(wdst + (uint32_t)(PW * RPI * i) * (CS * 8), wsrc + (size_t)m0 * 8 + (size_t)((uint32_t)i * wstep));
         }
         hm_cp_async_mbar_arrive(bar_full + 8 * s);                        // fires when my copies have landed
         if (++s == NS) { s = 0; parity ^= 1u; }
       }
-      if (++tile == ntiles) { tile = 0; ++smp; }
+      smp += step_smp; tile += step_tile;
+      if (tile >= ntiles) { tile -= ntiles; ++smp; }
     }
     return;
   }
@@ -664,7 +670,7 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
   const int rg = warp % RG, cg = warp / RG;
   const int cbeg = cg * C::CW;
   const uint32_t my_row = (uint32_t)(rg * 64 + lane) * ROWB;          // my first row inside a tracer's block of rows
-  for (long long it = it0; it < it1; ++it) {
+  for (long long it = it0; it < it1; it += istep) {
     double acc[2][NV];
 #pragma unroll
     for (int r = 0; r < 2; ++r)
@@ -728,13 +734,14 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
       if (row < a.nk) {
 #pragma unroll
         for (int f = 0; f < FM; ++f) {
-          double* dst = a.partial + ((((size_t)smp * FM + f) * a.nparts + cg) * a.nk + row) * NW;
+          double* dst = a.partial + (((size_t)smp * FM + f) * a.nparts + cg) * NW * (size_t)a.nk + row;
 #pragma unroll
-          for (int i = 0; i < NW; ++i) dst[i] = acc[r][f * NW + i];
+          for (int i = 0; i < NW; ++i) dst[(size_t)i * a.nk] = acc[r][f * NW + i];     // [i][row]: coalesced over lanes
         }
       }
     }
-    if (++tile == a.ntiles) { tile = 0; ++smp; }
+    smp += step_smp; tile += step_tile;
+    if (tile >= a.ntiles) { tile -= a.ntiles; ++smp; }
   }
 }
 
@@ -890,6 +897,7 @@ static int hm_launch_beta(const hm_beta_args& a, int B, cudaStream_t st) {
 struct hm_epi_args {
   int nk, B, F, P, NW, S, nparts, nchunks;
   int simple_twohalo, subtract_shotnoise, correct_discrete, fence_out;
+  int rows_layout;           // partial is [B][nparts][NW][nk] (row-per-lane kernel) instead of [B][nparts][nk][NW]
   double k_trunc;
   const double* k;
   const double* Pk_lin;      // [G][nk]
@@ -922,12 +930,13 @@ __global__ void __launch_bounds__(256) hm_epilogue_kernel(const hm_epi_args a) {
   double f[NW];
 #pragma unroll
   for (int i = 0; i < NW; ++i) f[i] = 0.;
+  const int rs = a.rows_layout ? 1 : NW, is = a.rows_layout ? a.nk : 1;     // strides of a row and of a value
   if (row < a.nk) {
 #pragma unroll 4
     for (int j = pg; j < a.nparts; j += PG) {
-      const double* pp = a.partial + (((size_t)b * a.nparts + j) * a.nk + row) * NW;
+      const double* pp = a.partial + ((size_t)b * a.nparts + j) * a.nk * NW + (size_t)row * rs;
 #pragma unroll
-      for (int i = 0; i < NW; ++i) f[i] += pp[i];
+      for (int i = 0; i < NW; ++i) f[i] += pp[(size_t)i * is];
     }
   }
 #pragma unroll
@@ -1165,7 +1174,7 @@ extern "C" int hm_mass_quadrature_stages(const hm_problem* pr, double* out_dev, 
   a.partial = (double*)ws + L.partial_offset;
   hm_epi_args e;
   e.nk = pr->nk; e.B = (int)L.B; e.F = pr->models_per_sample; e.P = L.P; e.NW = L.NW; e.S = L.S;
-  e.nparts = L.nparts; e.nchunks = L.nchunks;
+  e.nparts = L.nparts; e.nchunks = L.nchunks; e.rows_layout = L.rows;
   e.simple_twohalo = pr->simple_twohalo; e.subtract_shotnoise = pr->subtract_shotnoise;
   e.correct_discrete = pr->correct_discrete; e.k_trunc = pr->k_trunc; e.k = pr->k_dev; e.Pk_lin = pr->Pk_lin_dev;
   e.fence_out = pr->output_is_peer;
