@@ -86,9 +86,9 @@ static hm_layout hm_make_layout(const hm_problem* pr) {
   L.nslices = L.stream ? (pr->nM + L.MC - 1) / L.MC : 1;
   L.nparts = L.stream ? L.nslices * HM_CONSUMER_WARPS : 1;
   // five mass functions per sample on one or two tracers (BASELINE config 3): the row-per-lane kernel reads the
-  // shared grids once for all five and leaves one part per column group of warps
+  // shared grids once for all five and combines its column groups itself (one part)
   L.rows = L.stream && pr->models_per_sample == 5 && L.P <= 2;
-  if (L.rows) { L.nslices = 1; L.nparts = HM_ROWS_CG; }
+  if (L.rows) { L.nslices = 1; L.nparts = 1; }
   L.B = (size_t)pr->n_samples * (size_t)pr->models_per_sample;
   auto align = [](size_t x) { return (x + 31) & ~(size_t)31; };
   L.scal_offset = align(L.B * (size_t)L.NW * (size_t)L.nMp);
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
 // 16-byte shared-memory loads, one load feeding four FMAs (two rows x two columns).  The grid rows of a stage are
 // padded by 16 bytes so that the eight lanes of a quarter warp hit eight different 16-byte bank groups.
 // An item is (sample, 64*RG-row tile); the 8 consumer warps split into RG row groups x CG column groups, and every
-// warp writes its sums once per item: partial[model][cg][i][row], combined by the epilogue in fixed order.
+// warps add their sums in shared memory in warp order at the end of the item: partial[model][i][row], one part.
 // Items are dealt round-robin (CTA c takes c, c + grid, ...), so the row tiles of one sample run at the same time
 // on neighbouring SMs and its weight vectors come from DRAM once and from L2 for the other tiles.
 // ---------------------------------------------------------------------------------------------------------------
@@ -571,9 +571,11 @@ struct hm_rows_cfg {
   static constexpr int DATA_BYTES = RT * P * ROWB;
   static constexpr int W_BYTES = NV * CS * 8;
   static constexpr int STAGE_BYTES = ((DATA_BYTES + W_BYTES + 127) / 128) * 128;
-  static constexpr int BUDGET = 226 * 1024 - 256;
+  static constexpr int COMB_BYTES = RT * NV * 8;              // the item's sums, combined over the column groups
+  static constexpr int BUDGET = 226 * 1024 - 256 - COMB_BYTES;
   static constexpr int NS = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = NS * STAGE_BYTES + 256;
+  static constexpr int SMEM_BYTES = NS * STAGE_BYTES + COMB_BYTES + 256;
+  static_assert(RG == 1, "the in-kernel combine assumes that all consumer warps share the item's 64 rows");
   static_assert(CW >= 2 && CW % 2 == 0, "a warp works on pairs of columns");
   static_assert(NS >= 2, "the ring needs two stages");
 };
@@ -583,7 +585,8 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
   using C = hm_rows_cfg<P, FM, RG, CS>;
   constexpr int NW = C::NW, NV = C::NV, NS = C::NS, RT = C::RT, ROWB = C::ROWB;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * C::STAGE_BYTES);   // full[NS], empty[NS]
+  double* comb = reinterpret_cast<double*>(smem_raw + (size_t)NS * C::STAGE_BYTES);        // [NV][64 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * C::STAGE_BYTES + C::COMB_BYTES);   // full[NS], empty[NS]
   const uint32_t ring = hm_smem_addr(smem_raw);
   const uint32_t bar_full = hm_smem_addr(bars), bar_empty = hm_smem_addr(bars + NS);
 
@@ -727,19 +730,27 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
       if (lane == 0) hm_mbar_arrive(bar_empty + 8 * s);       // my reads of the slot are done
       if (++s == NS) { s = 0; parity ^= 1u; }
     }
-    // my two rows of this item: sums over the columns of my group, one part per column group
+    // combine the column groups in shared memory in warp order (a fixed summation order), then store the item's
+    // RT x NV sums once: partial[model][i][row], coalesced over rows
+#pragma unroll 1
+    for (int w = 0; w < HM_CONSUMER_WARPS; ++w) {
+      if (warp == w) {
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int row = tile * RT + rg * 64 + r * 32 + lane;
-      if (row < a.nk) {
+        for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int f = 0; f < FM; ++f) {
-          double* dst = a.partial + (((size_t)smp * FM + f) * a.nparts + cg) * NW * (size_t)a.nk + row;
-#pragma unroll
-          for (int i = 0; i < NW; ++i) dst[(size_t)i * a.nk] = acc[r][f * NW + i];     // [i][row]: coalesced over lanes
-        }
+          for (int j = 0; j < NV; ++j) {
+            double* c = comb + j * 64 + r * 32 + lane;
+            *c = (w == 0) ? acc[r][j] : *c + acc[r][j];
+          }
       }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
+    for (int idx = tid; idx < 64 * NV; idx += 32 * HM_CONSUMER_WARPS) {
+      const int j = idx >> 6, row = tile * RT + (idx & 63);
+      const int f = j / NW, i = j - f * NW;
+      if (row < a.nk) a.partial[(((size_t)smp * FM + f) * NW + i) * (size_t)a.nk + row] = comb[idx];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");               // comb is free for the next item
     smp += step_smp; tile += step_tile;
     if (tile >= a.ntiles) { tile -= a.ntiles; ++smp; }
   }
