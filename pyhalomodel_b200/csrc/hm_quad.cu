@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(HM_WCHUNK) hm_weights_kernel(const hm_weights_
   // one reduction phase for all 17 sums: warp butterflies, then a fixed-order sum over the 8 warps
 #pragma unroll
   for (int i = 0; i < NRED; ++i) {
-    const double t = hm_warp_sum(red[i]);
+    const bool used = (i == 2 * HM_MAXP) ? (chunk == 0) : ((i & (HM_MAXP - 1)) < a.P);   // the others are zero
+    const double t = used ? hm_warp_sum(red[i]) : 0.;
     if (lane == 0) sred[warp][i] = t;
   }
   __syncthreads();
