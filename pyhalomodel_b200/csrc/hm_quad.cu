@@ -13,7 +13,10 @@
 //                          R-row x 512-mass tiles of every tracer grid; 8 independent consumer warps keep the
 //                          weights of their two mass columns in registers, accumulate R*(P+S) sums, reduce them
 //                          over the warp with a transposing shuffle network and store the warp's partial row sums
-//                          (no CTA-wide synchronisation).  FM = 5 fuses the five mass functions of one sample.
+//                          (no CTA-wide synchronisation).
+//   hm_quad_rows_kernel    sweeps with five models per sample (one or two tracers): a lane owns two wavenumber
+//                          rows for the whole mass axis, the weights are broadcast from shared memory, and
+//                          nothing is reduced across lanes (see the comment above the kernel).
 //   hm_quad_kernel         fallback of the same arithmetic with plain (scalar or 16-byte) loads for odd nM,
 //                          unaligned grids or profiles with separate Uk/Wk grids.
 //   hm_beta2h_kernel       optional non-linear halo bias: I_NL = rhom^2 a_u^T beta_k a_v + edge terms (:546-571)

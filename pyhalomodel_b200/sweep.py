@@ -140,6 +140,28 @@ class ShardedSweep:
         out, _ = self.plan.run()
         return out
 
+    def run_to_root(self, root=0):
+        """Like run(), but with the gather fused into the epilogue kernel: every rank's spectra are stored straight
+        into the root's memory over NVLink (PeerGatherBuffer), no collective kernel runs, and only the root gets
+        the [n_samples*F, S, 3, nk] result (the other ranks get None).  CUDA only; uneven shards are padded."""
+        if self.plan is None:
+            raise RuntimeError('empty shard: more ranks than samples')
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world == 1:
+            return self.run_local()
+        rank = dist.get_rank(self.group)
+        bounds = shard_bounds(self.n_samples, world)
+        nmax = max(b-a for a, b in bounds)
+        tail = tuple(self.plan.out.shape[1:])
+        if getattr(self, '_peer', None) is None or self._peer.root != root:
+            self._peer = PeerGatherBuffer((nmax*self.F,)+tail, 1, root=root, group=self.group)
+        n_mine = (self.hi-self.lo)*self.F
+        self.plan.run(out=self._peer.slot(0)[:n_mine], peer=True)
+        local = self._peer.finish()
+        if rank != root:
+            return None
+        return torch.cat([local[r, 0, :(b-a)*self.F] for r, (a, b) in enumerate(bounds)], dim=0)
+
     def run(self):
         out = self.run_local()
         if out is None:
