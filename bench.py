@@ -310,7 +310,7 @@ def main():
         tj = json.load(open(tpath))
         if tj.get('batch') == B:
             traffic = tj.get('dram_bytes_per_launch')
-    roofline = dict(bound='hbm', kernel='hm_quad_stream_kernel<3,3,1,2>', achieved=achieved, peak=peak, unit='GB/s',
+    roofline = dict(bound='hbm', kernel='hm_quad_stream_kernel<3,3,2>', achieved=achieved, peak=peak, unit='GB/s',
                     frac=achieved/peak, traffic=traffic, algorithmic_bytes_per_launch=alg_bytes,
                     kernel_ms=quad_ms, epilogue_kernel_ms=epi_ms, weights_kernel_ms=weights_ms,
                     step_algorithmic_bytes=plan.algorithmic_bytes(),

@@ -414,10 +414,7 @@ struct hm_item_cursor {
   }
 };
 
-// FM > 1: the FM models of one sample (e.g. the five mass functions evaluated on one cosmology) share its grids.
-// An item is then (sample, slice, tile): the tile is read from HBM ONCE and accumulated against FM weight sets
-// held in registers (BASELINE config 3), instead of once per model.
-template <int P, int R, int FM, int H>
+template <int P, int R, int H>
 // 9 warps: one SM sub-partition (16K registers) hosts three of them, hence at most 168 registers per thread
 __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(const hm_quad_args a) {
   using C = hm_stream_cfg<P, R, H>;
@@ -452,7 +449,7 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
       int s = 0;
       uint32_t parity = 0;
       for (int n = 0; n < nloc; ++n) {
-        const int smp = (FM > 1) ? cur.b : cur.b / a.F, m0 = cur.slice * MC, row0 = cur.tile * R;
+        const int smp = cur.b / a.F, m0 = cur.slice * MC, row0 = cur.tile * R;
         const int cols = (a.nM - m0 < MC) ? a.nM - m0 : MC;
         const uint32_t bytes = (uint32_t)cols * 8u;
         hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);        // slot drained by all consumer warps
@@ -476,7 +473,7 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
   // ------- consumers: 8 independent warps, 64*H mass columns per warp, H column pairs per thread ------------
   // No CTA-wide synchronisation: every warp reduces its own columns and writes its own partial row sums;
   // the epilogue kernel adds the parts in fixed order.
-  double wv[FM][H][2][NW];
+  double wv[H][2][NW];
   int cur_b = -1, cur_slice = -1;
   int s = 0;
   uint32_t parity = 0;
@@ -485,19 +482,17 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
     if (cur.b != cur_b || cur.slice != cur_slice) {   // weights of my columns stay in registers for the slice
       cur_b = cur.b; cur_slice = cur.slice;
 #pragma unroll
-      for (int f = 0; f < FM; ++f)
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
+      for (int h = 0; h < H; ++h) {
           const int m = m0 + h * HM_MC;
-          const double* __restrict__ w = a.weights + ((size_t)cur.b * FM + f) * NW * a.nMp + m;
+          const double* __restrict__ w = a.weights + (size_t)cur.b * NW * a.nMp + m;
 #pragma unroll
           for (int i = 0; i < NW; ++i) {
             const double2 t = (m < a.nM) ? *reinterpret_cast<const double2*>(w + (size_t)i * a.nMp) : make_double2(0., 0.);
-            wv[f][h][0][i] = t.x; wv[f][h][1][i] = t.y;
+            wv[h][0][i] = t.x; wv[h][1][i] = t.y;
           }
         }
     }
-    constexpr int NVF = FM * R * NW, NGF = (NVF + 31) / 32;
+    constexpr int NVF = R * NW, NGF = (NVF + 31) / 32;
     double acc[NGF * 32];
 #pragma unroll
     for (int i = 0; i < NGF * 32; ++i) acc[i] = 0.;
@@ -520,14 +515,11 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
         __syncwarp();
         if (lane == 0) hm_mbar_arrive(bar_empty + 8 * s);
       }
-#pragma unroll
-      for (int f = 0; f < FM; ++f) {
-        hm_accumulate<P, R, false>(acc + f * R * NW, wv[f][h][0], x[0], xu);
-        hm_accumulate<P, R, false>(acc + f * R * NW, wv[f][h][1], x[1], xu);
-      }
+      hm_accumulate<P, R, false>(acc, wv[h][0], x[0], xu);
+      hm_accumulate<P, R, false>(acc, wv[h][1], x[1], xu);
     }
 
-    // all FM*R*NW sums of this tile go through ONE transposing reduction (lane j ends up with value j)
+    // all R*NW sums of this tile go through ONE transposing reduction (lane j ends up with value j)
     const int nvalid = ((a.nk - row0 < R) ? a.nk - row0 : R) * NW;
 #pragma unroll
     for (int g = 0; g < NGF; ++g) {
@@ -535,10 +527,10 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] = acc[g * 32 + i];
       const double t = hm_warp_transpose_sum32(v, lane);
-      const int idx = g * 32 + lane, f = idx / (R * NW), rem = idx - f * (R * NW);
-      if (f < FM && rem < nvalid) {
+      const int rem = g * 32 + lane;
+      if (rem < nvalid) {
         // partial[model][slice*8 + warp][row0 + r][i]: the R*NW values of a tile are contiguous -> coalesced store
-        const size_t model = (size_t)cur.b * FM + f;
+        const size_t model = (size_t)cur.b;
         a.partial[((model * a.nparts + cur.slice * HM_CONSUMER_WARPS + warp) * a.nk + row0) * NW + rem] = t;
       }
     }
@@ -1103,20 +1095,20 @@ static int hm_launch_fallback(hm_quad_args& a, bool vec2, bool sep, cudaStream_t
   return HM_OK;
 }
 
-template <int P, int R, int FM, int H>
-static int hm_launch_stream_fm(hm_quad_args& a, cudaStream_t st) {
+template <int P, int R, int H>
+static int hm_launch_stream_h(hm_quad_args& a, cudaStream_t st) {
   using C = hm_stream_cfg<P, R, H>;
   static bool configured = false;
   if (!configured) {
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_quad_stream_kernel<P, R, FM, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_quad_stream_kernel<P, R, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM_BYTES));
     configured = true;
   }
   a.ntiles = (a.nk + R - 1) / R;
-  a.nitems = (long long)(a.B / FM) * a.nslices * a.ntiles;     // FM > 1: items enumerate samples, not models
+  a.nitems = (long long)a.B * a.nslices * a.ntiles;
   long long grid = hm_num_sms();
   if (grid > a.nitems) grid = a.nitems;
-  hm_quad_stream_kernel<P, R, FM, H><<<(int)grid, HM_STREAM_THREADS, C::SMEM_BYTES, st>>>(a);
+  hm_quad_stream_kernel<P, R, H><<<(int)grid, HM_STREAM_THREADS, C::SMEM_BYTES, st>>>(a);
   HM_LAUNCH_CHECK();
   return HM_OK;
 }
@@ -1141,15 +1133,15 @@ static int hm_launch_rows(hm_quad_args& a, cudaStream_t st) {
 
 template <int P, int R>
 static int hm_launch_stream(hm_quad_args& a, cudaStream_t st) {
-  // the fused multi-family variant holds F weight sets in registers: instantiated where they fit (P <= 2, F = 5:
-  // the five mass functions of BASELINE config 3); other combinations read the shared grids once per model
+  // five models per sample on one or two tracers (the five mass functions of BASELINE config 3) take the
+  // row-per-lane kernel, which reads the shared grids once; other combinations read them once per model
   if constexpr (P <= 2) {
     if (a.F == 5) return hm_launch_rows<P, 5>(a, st);         // must agree with hm_layout.rows
   }
   if constexpr (P <= 3) {
-    if (a.MC == 2 * HM_MC) return hm_launch_stream_fm<P, R, 1, 2>(a, st);
+    if (a.MC == 2 * HM_MC) return hm_launch_stream_h<P, R, 2>(a, st);
   }
-  return hm_launch_stream_fm<P, R, 1, 1>(a, st);
+  return hm_launch_stream_h<P, R, 1>(a, st);
 }
 
 template <int P>
