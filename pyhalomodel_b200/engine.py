@@ -347,7 +347,9 @@ class PipelinedPlans:
         self.n = 0
         self.forked = False
 
-    def submit(self, out=None, peer=False):
+    def submit(self, out=None, peer=False, then=None):
+        """Enqueue one step; `then(out, lowmass)`, if given, is called with the step's stream current (e.g. to
+        enqueue a copy of the spectra behind the epilogue kernel)."""
         main = torch.cuda.current_stream()
         if not self.forked:
             for st in self.streams:
@@ -356,6 +358,8 @@ class PipelinedPlans:
         i = self.n & 1
         with torch.cuda.stream(self.streams[i]):
             res = self.plans[i].run(out=out, peer=peer)
+            if then is not None:
+                then(*res)
         self.n += 1
         return res
 
