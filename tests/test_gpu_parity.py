@@ -354,6 +354,27 @@ def test_batched_plan_equals_single_models(halo, names, with_gal, shape):
                     assert np.array_equal(out[b, s, t], single[t][key]), (b, key, t)
 
 
+def test_fused_sweep_many_items_vs_per_family_plans(halo):
+    """More (sample, row tile) items than SMs, so every CTA of the row-per-lane sweep kernel walks several items
+    (round-robin item stepping, ring wrap-around across items, ragged last row tile and mass stage): the five
+    families in one fused plan against five single-family plans that take the per-model streaming kernel."""
+    from pyhalomodel_b200 import engine, workloads
+    G, nk, nM = 170, 150, 206
+    batch = workloads.build(G, nk, nM, ('m', 'g'), syn.FAMILY_NAMES, seed=11, fiducial_first=False)
+    F = len(syn.FAMILY_NAMES)
+    fused, A5 = batch.plan().run()
+    fused, A5 = fused.cpu().numpy().reshape(G, F, 3, 3, nk), A5.cpu().numpy().reshape(G, F)
+    for f in range(F):
+        tracers = [engine.Tracer(t.grid, t.amplitude, engine.to_dev(t.normalisation)[f::F].contiguous(),
+                                 variance=t.variance, mode=t.mode, mass_tracer=t.mass_tracer,
+                                 discrete_tracer=t.discrete_tracer) for t in batch.tracers]
+        models = [m.descriptor() for m in batch.models[f::F]]
+        single, A1 = engine.PowerSpectrumPlan(batch.k, batch.Pk_lin, batch.M, batch.sigma, tracers, models).run()
+        np.testing.assert_allclose(fused[:, f], single.cpu().numpy(), rtol=1e-12, atol=0., err_msg=syn.FAMILY_NAMES[f])
+        np.testing.assert_array_equal(A5[:, f], A1.cpu().numpy())
+    assert np.isfinite(fused).all()
+
+
 def test_error_behaviour(halo):
     g = load_golden('power_c1.npz')
     hmod = halo.model(0., 0.3, name=orc.ST99, Dv=330.)
