@@ -53,23 +53,31 @@ def parse():
 # ---------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference algorithm (oracle/halo_oracle.py)
 # ---------------------------------------------------------------------------------------------------------------
-def _oracle_inputs(seed, n):
-    """Host-only construction of n config-2 models (no GPU needed): the same recipe as workloads.build."""
-    from oracle import halo_oracle as orc
+def _oracle_params(seed, n):
+    """The (cosmology, HOD) draws of n config-2 models: the same recipe as workloads.build."""
     from pyhalomodel_b200 import synthetic as syn
     rng = np.random.default_rng(seed)
-    k, M = syn.k_grid(NK), syn.M_grid(NM)
-    kg, dlnk = syn.sigma_k_grid()
-    cases = []
+    out = []
     for i in range(n):
         cs = dict(Om_m=0.3, sigma8=0.8, ns=0.96, h=0.7, z=0.) if i == 0 else syn.draw_cosmology(rng)
         hod = syn.zheng_defaults() if i == 0 else syn.draw_hod(rng)
-        P0 = syn.LinearSpectrum(cs['Om_m'], cs['h'], cs['ns'], cs['sigma8'])
-        Omz = syn.Om_m_of_z(cs['z'], cs['Om_m'])
-        dc, Dv = orc.dc_nakamura_suto(Omz), orc.Dv_bryan_norman(Omz)
-        sig = syn.sigmaR_numpy(orc.lagrangian_radius(M, cs['Om_m']), P0(kg, cs['z']), kg, dlnk)
-        cases.append(dict(k=k, M=M, Pk=P0(k, cs['z']), sig=sig, z=cs['z'], Om_m=cs['Om_m'], dc=dc, Dv=Dv, hod=hod))
-    return cases
+        out.append((cs, hod))
+    return out
+
+
+def _oracle_case(param):
+    """Host-only construction of the inputs of one config-2 model (no GPU needed); sigma(M) takes ~15 s of numpy, so
+    the reference arm builds its cases in parallel, outside the timed region."""
+    from oracle import halo_oracle as orc
+    from pyhalomodel_b200 import synthetic as syn
+    cs, hod = param
+    k, M = syn.k_grid(NK), syn.M_grid(NM)
+    kg, dlnk = syn.sigma_k_grid()
+    P0 = syn.LinearSpectrum(cs['Om_m'], cs['h'], cs['ns'], cs['sigma8'])
+    Omz = syn.Om_m_of_z(cs['z'], cs['Om_m'])
+    dc, Dv = orc.dc_nakamura_suto(Omz), orc.Dv_bryan_norman(Omz)
+    sig = syn.sigmaR_numpy(orc.lagrangian_radius(M, cs['Om_m']), P0(kg, cs['z']), kg, dlnk)
+    return dict(k=k, M=M, Pk=P0(k, cs['z']), sig=sig, z=cs['z'], Om_m=cs['Om_m'], dc=dc, Dv=Dv, hod=hod)
 
 
 def _oracle_one(case):
@@ -118,10 +126,10 @@ def run_reference(args, rank):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
     per_step = cores
-    cases = _oracle_inputs(1234, per_step)
     ctx = mp.get_context('fork')
     times = []
     with ctx.Pool(cores) as pool:
+        cases = pool.map(_oracle_case, _oracle_params(1234, per_step))     # inputs: built in parallel, not timed
         for step in range(args.warmup+args.steps):
             t0 = time.perf_counter()
             pool.map(_oracle_one, cases)
