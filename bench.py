@@ -235,7 +235,7 @@ def main():
     # kernel: its output pointer is this rank's slot of a symmetric buffer that lives on rank 0, so the spectra are
     # stored over NVLink as they are produced (sweep.PeerGatherBuffer).  The NCCL all-gather is the baseline it is
     # checked against after the timed region.
-    peer = sweep.PeerGatherBuffer(plan.out.shape, max(K, W)) if world > 1 else None
+    peer = sweep.PeerGatherBuffer(plan.out.shape, min(max(K, W), 32)) if world > 1 else None     # ring of result slots
     step_no = [0]
 
     # consecutive steps are software-pipelined over two CUDA streams (double-buffered plans): the weights and

@@ -120,3 +120,19 @@ def test_model_constants_and_errors():
         halo.pyhalomodel.HOD_mean(M, method='nope')
     with pytest.raises(ValueError):
         halo.pyhalomodel.concentration(M, 0., halo_definition='nope')
+
+
+def test_integration_stub_matches_the_abi():
+    """The ctypes structures shown to a maintainer in INTEGRATION.md have the layout of the shipped binding."""
+    import ctypes as C
+    from pyhalomodel_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, 'INTEGRATION.md')).read()
+    code = text[text.index('class ModelDesc(C.Structure):'):text.index('lib.hm_power_spectrum_workspace.restype')]
+    ns = {'C': C}
+    exec(code, ns)
+    for name in ('ModelDesc', 'Tracer', 'Problem'):
+        stub, real = ns[name], getattr(_lib, name)
+        assert C.sizeof(stub) == C.sizeof(real), name
+        assert [(f[0], getattr(stub, f[0]).offset) for f in stub._fields_] == \
+               [(f[0], getattr(real, f[0]).offset) for f in real._fields_], name
