@@ -56,7 +56,6 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
 #define HM_STREAM_THREADS (32 * (HM_CONSUMER_WARPS + 1))
 #define HM_ROWS_RG 1         // row-per-lane kernel: groups of 64 rows per item ...
 #define HM_ROWS_CS 32        // ... and mass columns per stage
-#define HM_ROWS_CG (HM_CONSUMER_WARPS / HM_ROWS_RG)
 #define HM_ROWS_PW 4         // ... fed by this many producer warps
 #define HM_ROWS_THREADS (32 * (HM_CONSUMER_WARPS + HM_ROWS_PW))
 
@@ -582,10 +581,11 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
   uint32_t parity = 0;
 
   if (warp >= HM_CONSUMER_WARPS) {
-    // ---- producer warps: one 16-byte cp.async per lane and row (LDGSTS: a whole 512-byte row segment per warp
-    // instruction, landing at the padded pitch); the lanes' copies complete on the stage's mbarrier.  Producer warp
-    // pw moves rows pw, pw + PW, ... ; addresses are base + constant * stride so that the copies issue back to back.
-    // (153 separate 512-byte TMA bulk copies per stage serialise on the SM's one TMA unit: 654 us per launch.) ----
+    // ---- producer warps: one 16-byte cp.async per lane (LDGSTS: a warp instruction moves the 256-byte segments of
+    // two rows, landing at the padded pitch); the lanes' copies complete on the stage's mbarrier.  Producer warp pw
+    // moves row pairs pw, pw + PW, ... ; addresses are base + constant * stride so that the copies issue back to
+    // back.  (One TMA bulk copy per row segment -- 153 small copies per stage -- serialises on the SM's TMA unit:
+    // 654 us per launch against 240 us this way.) ----
     constexpr int PW = HM_ROWS_PW;
     constexpr int LPR = CS / 2;                 // lanes per row segment (16 bytes each)
     constexpr int RPI = 32 / LPR;               // rows per warp instruction
@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
       const int cend = (cbeg + C::CW < cols) ? cbeg + C::CW : cols;
       const unsigned char* stage = smem_raw + (size_t)s * C::STAGE_BYTES;
       const unsigned char* wsm = stage + C::DATA_BYTES;
-      hm_mbar_wait(bar_full + 8 * s, parity);                 // TMA bytes have landed
+      hm_mbar_wait(bar_full + 8 * s, parity);                 // every producer lane's copies have landed
 #pragma unroll 1
       for (int c = cbeg; c < cend; c += 2) {
         double2 x[2][P];
