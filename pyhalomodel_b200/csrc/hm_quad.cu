@@ -8,12 +8,12 @@
 //                            P1h_uv  = rhom * sum_m  q_uv[m] * G_u[k,m] * G_v[k,m]       (:479)
 //                          where G_u is the single grid a Fourier profile was built from (Uk, or Wk when
 //                          amplitude=None; :874-881), so each (k,M) grid is read from HBM exactly once.
-//   hm_quad_stream_kernel  the HBM-bound kernel.  Persistent CTAs (one per SM); a producer warp feeds a 6-stage
-//                          shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx) of
-//                          R-row x 512-mass tiles of every tracer grid; 8 independent consumer warps keep the
-//                          weights of their two mass columns in registers, accumulate R*(P+S) sums, reduce them
-//                          over the warp with a transposing shuffle network and store the warp's partial row sums
-//                          (no CTA-wide synchronisation).
+//   hm_quad_stream_kernel  the HBM-bound kernel.  Persistent CTAs (one per SM); a producer warp feeds a shared-
+//                          memory ring (221 KB: 6 stages, or 3 of twice the width) with TMA bulk copies
+//                          (cp.async.bulk + mbarrier complete_tx) of R-row x 512*H-mass tiles of every tracer
+//                          grid; 8 independent consumer warps keep the weights of their 2*H mass columns in
+//                          registers, accumulate R*(P+S) sums, reduce them over the warp with a transposing
+//                          shuffle network and store the warp's partial row sums (no CTA-wide synchronisation).
 //   hm_quad_rows_kernel    sweeps with five models per sample (one or two tracers): a lane owns two wavenumber
 //                          rows for the whole mass axis, the weights are broadcast from shared memory, and
 //                          nothing is reduced across lanes (see the comment above the kernel).
