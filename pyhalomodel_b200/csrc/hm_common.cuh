@@ -48,6 +48,19 @@ static inline int hm_num_sms() {
   return sms;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: remember on which devices of this
+// process a kernel has been configured (a repeated call from a racing thread is harmless)
+struct hm_once_per_device {
+  unsigned long long mask = 0ull;
+  bool needed() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) return true;
+    if ((mask >> dev) & 1ull) return false;
+    mask |= 1ull << dev;
+    return true;
+  }
+};
+
 // ---- streaming loads: (k,M) grids are read exactly once, keep them out of L1 ---------------------------------
 __device__ __forceinline__ double2 hm_ldg_stream2(const double* p) {
   double2 v;

@@ -629,12 +629,11 @@ extern "C" int hm_gram_power_spectrum(const hm_gram_problem* pr, double* out_dev
   // the kernel is instantiated for block grids of 2, 4 and 8 (16, 32, 64 tracer rows); pad up to the next one
   const int NBT = (L.NB <= 2) ? 2 : (L.NB <= 4) ? 4 : 8;
   const size_t smem = (3 * (size_t)L.RK * (8 * NBT) * HM_GLD + 3 * HM_GMCH) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  static hm_once_per_device once;
+  if (once.needed()) {
     HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    configured = true;
   }
   g.nitems = (long long)L.B * L.ntiles * L.nparts;
   HM_REQUIRE(g.nitems < (1LL << 31), "too many work items for one launch");

@@ -861,10 +861,9 @@ __global__ void __launch_bounds__(256) hm_beta2h_kernel(const hm_beta_args a) {
 template <int P>
 static int hm_launch_beta(const hm_beta_args& a, int B, cudaStream_t st) {
   const size_t smem = ((size_t)P * a.nMp + 8 * (P * (P + 1) / 2 + P)) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
+  static hm_once_per_device once;
+  if (once.needed()) {
     HM_CUDA_TRY(cudaFuncSetAttribute(hm_beta2h_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
   }
   if (smem > 200 * 1024) {
     hm_set_error("beta_NL: %d tracers x %d masses do not fit in shared memory", P, a.nM);
@@ -1075,11 +1074,10 @@ static int hm_launch_fallback(hm_quad_args& a, bool vec2, bool sep, cudaStream_t
 template <int P, int R, int H>
 static int hm_launch_stream_h(hm_quad_args& a, cudaStream_t st) {
   using C = hm_stream_cfg<P, R, H>;
-  static bool configured = false;
-  if (!configured) {
+  static hm_once_per_device once;
+  if (once.needed()) {
     HM_CUDA_TRY(cudaFuncSetAttribute(hm_quad_stream_kernel<P, R, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM_BYTES));
-    configured = true;
   }
   a.ntiles = (a.nk + R - 1) / R;
   a.nitems = (long long)a.B * a.nslices * a.ntiles;
@@ -1093,11 +1091,10 @@ static int hm_launch_stream_h(hm_quad_args& a, cudaStream_t st) {
 template <int P, int FM>
 static int hm_launch_rows(hm_quad_args& a, cudaStream_t st) {
   using C = hm_rows_cfg<P, FM, HM_ROWS_RG, HM_ROWS_CS>;
-  static bool configured = false;
-  if (!configured) {
+  static hm_once_per_device once;
+  if (once.needed()) {
     HM_CUDA_TRY(cudaFuncSetAttribute(hm_quad_rows_kernel<P, FM, HM_ROWS_RG, HM_ROWS_CS>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    configured = true;
   }
   a.ntiles = (a.nk + C::RT - 1) / C::RT;
   a.nitems = (long long)(a.B / FM) * a.ntiles;                 // items enumerate (sample, row tile)
