@@ -349,7 +349,51 @@ def golden_cross_halo():
     save('cross_halo.npz', **out)
 
 
+def golden_power_many():
+    """Many tracers (BASELINE config 4 in small): matter + 12 HOD galaxy samples with NFW profiles, 91 unique
+    pairs on 24 k x 96 M, Tinker10.  Pins the oracle's pair loop for a tracer count that takes the Gram path."""
+    nk, nM, ngal = 24, 96, 12
+    k, M = syn.k_grid(nk), syn.M_grid(nM, 1e10, 1e16)
+    Om_m, z = 0.31, 0.25
+    Plin0 = syn.LinearSpectrum(Om_m, 0.69, 0.965, 0.81)
+    dc, Dv = dcDv(z, Om_m)
+    hmod = ref.model(z, Om_m, name=SHORT['Tinker2010'], Dv=Dv, dc=dc)
+    sig, R = sigma_of_M(hmod, M, Plin0, z)
+    Pk = Plin0(k, z)
+    rv = hmod.virial_radius(M)
+    c = ref.concentration(M, z, halo_definition='Mvir')
+    Unfw = ref.window_function(k, rv, c, profile='NFW')
+    rng = np.random.default_rng(44)
+    profs = {'m': ref.matter_profile(k, M, rv, c, Om_m)}
+    hods, rho = [], []
+    for i in range(ngal):
+        hod = syn.draw_hod(rng)
+        Nc, Ns = ref.HOD_mean(M, method='Zheng et al. (2005)', **hod)
+        Vc, Vs, _ = ref.HOD_variance(Nc, Ns)
+        rho_g = hmod.average(M, sig, Nc+Ns)
+        profs['g%d' % i] = ref.profile.Fourier(k, M, Unfw, amplitude=Nc+Ns, normalisation=rho_g, variance=Vc+Vs,
+                                               discrete_tracer=True)
+        hods.append([hod[x] for x in ('Mmin', 'sigma', 'M0', 'M1', 'alpha')])
+        rho.append(rho_g)
+    names = list(profs.keys())
+    out = dict(k=k, M=M, Pk_lin=Pk, sigmaM=sig, z=np.array(z), Om_m=np.array(Om_m), dcDv=np.array([dc, Dv]),
+               hods=np.array(hods), rho_g=np.array(rho))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        P2, P1, PH = hmod.power_spectrum(k, Pk, M, sig, profs)
+    for iu, u in enumerate(names):          # unique pairs only (the lower triangle aliases them)
+        for v in names[iu:]:
+            key = u+'-'+v
+            out['P_'+key] = np.array([P2[key], P1[key], PH[key]])
+    assert PH['g3-m'] is PH['m-g3']
+    save('power_many.npz', **out)
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1:                   # e.g. `make_golden.py power_many`: regenerate one fixture only
+        for name in sys.argv[1:]:
+            globals()['golden_'+name]()
+        sys.exit(0)
     golden_massfn()
     golden_windows()
     golden_sigma()
@@ -360,3 +404,4 @@ if __name__ == '__main__':
     golden_power_beta()
     golden_configuration()
     golden_cross_halo()
+    golden_power_many()

@@ -164,6 +164,36 @@ def test_power_flags_and_aliasing():
         orc.power_spectrum(hm, g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs, correct_discrete=False)
 
 
+def test_power_many_tracers():
+    """Matter + 12 HOD samples (91 unique pairs): the oracle's pair loop at a tracer count that takes the Gram path on
+    the GPU, pinned to the live reference."""
+    g = load_golden('power_many.npz')
+    dc, Dv = g['dcDv']
+    k, M, sig = g['k'], g['M'], g['sigmaM']
+    hm = orc.make_model(float(g['z']), float(g['Om_m']), name=orc.TINKER10, Dv=Dv, dc=dc)
+    rv, c = orc.virial_radius(M, hm.Om_m, hm.Dv), orc.concentration(M, hm.z, halo_definition='Mvir')
+    Unfw = orc.window_nfw(k, rv, c)
+    profs = {'m': orc.matter_profile(k, M, rv, c, hm.Om_m)}
+    for i, row in enumerate(g['hods']):
+        hod = dict(zip(('Mmin', 'sigma', 'M0', 'M1', 'alpha'), row))
+        Nc, Ns = orc.hod_mean(M, **hod)
+        Vc, Vs, _ = orc.hod_variance(Nc, Ns)
+        rho_g = orc.average(hm, M, sig, Nc+Ns)
+        np.testing.assert_allclose(rho_g, g['rho_g'][i], rtol=TIGHT)
+        profs['g%d' % i] = orc.Profile.Fourier(k, M, Unfw, amplitude=Nc+Ns, normalisation=rho_g, variance=Vc+Vs,
+                                               discrete_tracer=True)
+    P2, P1, PH = orc.power_spectrum(hm, k, g['Pk_lin'], M, sig, profs)
+    names = list(profs.keys())
+    assert len(names) == 13
+    for iu, u in enumerate(names):
+        for v in names[iu:]:
+            key = u+'-'+v
+            want = g['P_'+key]
+            for got, ref_row in zip((P2[key], P1[key], PH[key]), want):
+                np.testing.assert_allclose(got, ref_row, rtol=1e-13, atol=0., err_msg=key)
+    assert PH['g3-m'] is PH['m-g3']
+
+
 def test_power_c2_small_and_average():
     g = load_golden('power_c2_small.npz')
     dc, Dv = g['dcDv']
