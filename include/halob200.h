@@ -139,6 +139,26 @@ int hm_average_batch(const hm_model_desc* models_dev, const double* M_dev, const
 int hm_weighted_rowsum(const double* grid_dev, const double* w_dev, int32_t nk, int32_t nM, int32_t nw,
                        double* out_dev, void* stream);
 
+/* M^2 n(M)/rhobar and n(M) (model.multiplicity_function / mass_function, pyhalomodel.py:286-315, with the three-point
+ * derivative of ln sigma against ln R of utility.derivative_from_samples, utility.py:15-35).  F_dev / n_dev: [nM],
+ * either may be NULL. */
+int hm_multiplicity_function(const hm_model_desc* model_host, const double* M_dev, const double* sigma_dev,
+                             int32_t nM, double* F_dev, double* n_dev, void* stream);
+
+/* Every tracer crossed with haloes of one mass M_h (model.cross_halo_spectrum, pyhalomodel.py:573-704).
+ * tracers: HOST array [n_tracers] (device pointers inside; grids [nk][nM], amplitudes [nM]); normalisation_host:
+ * [n_tracers]; interp_weights_dev: [nM] weights L with f(M_h) = sum_m L[m] f(M[m]) (the reference's cubic
+ * interpolation in ln M, :631-639, is linear in the samples); beta_dev: [nk][nM] beta_NL(k, M) at M_h or NULL;
+ * k_trunc <= 0 means None.  out_dev: [n_tracers][3][nk] (2h, 1h, hm).  halo_bias_nu_dev (optional, [3]) receives
+ * A, nu(M_h), b(M_h).  Workspace: hm_cross_halo_workspace(nM) bytes. */
+size_t hm_cross_halo_workspace(int32_t nM);
+int hm_cross_halo_spectrum(const hm_model_desc* model_host, const double* k_dev, const double* Pk_lin_dev,
+                           const double* M_dev, const double* sigma_dev, int32_t nk, int32_t nM,
+                           const hm_tracer* tracers, const double* normalisation_host, int32_t n_tracers,
+                           const double* interp_weights_dev, const double* beta_dev, int32_t simple_twohalo,
+                           double k_trunc, double* out_dev, double* halo_bias_nu_dev, void* workspace_dev,
+                           size_t workspace_bytes, void* stream);
+
 /* ---- the hot path: model.power_spectrum (pyhalomodel.py:361-513, beta=None) --------------------------------
  * out_dev: [B][S][3][nk] with S = P(P+1)/2 unique pairs ordered (0,0),(0,1),..,(0,P-1),(1,1),.. and the three
  * terms ordered (Pk_2h, Pk_1h, Pk_hm).  lowmass_dev (optional, [B]) receives A so the caller can raise the

@@ -191,6 +191,34 @@ def low_mass_correction(hm: HaloModel, nu0):
     return 1.-_integrate.quad(lambda x: mass_function_nu(hm, x)*linear_bias_nu(hm, x), nu0, np.inf)[0]
 
 
+def derivative_from_samples(x, xs, fs):
+    """Derivative at x of the quadratic through the three samples around it, utility.py:15-35 (scipy's `lagrange`
+    polynomial in the monomial basis, differentiated: the reference's own arithmetic)."""
+    from scipy.interpolate import lagrange
+    ix = int(np.abs(xs-x).argmin())               # utility.find_closest_index_value, utility.py:50-56
+    if ix == 0:
+        imin, imax = (0, 1) if x < xs[0] else (0, 2)
+    elif ix == len(xs)-1:
+        nx = len(xs)
+        imin, imax = (nx-2, nx-1) if x > xs[-1] else (nx-3, nx-1)
+    else:
+        imin, imax = ix-1, ix+1
+    return lagrange(xs[imin:imax+1], fs[imin:imax+1]).deriv()(x)
+
+
+def multiplicity_function(hm: HaloModel, M, sigmaM):
+    """M^2 n(M)/rhobar = g(nu) dnu/dlnM, pyhalomodel.py:298-315"""
+    nu = peak_height(hm, sigmaM)
+    logR, logsig = np.log(lagrangian_radius(M, hm.Om_m)), np.log(sigmaM)
+    deriv = np.array([2.*derivative_from_samples(x, logR, logsig) for x in logR])
+    return mass_function_nu(hm, nu)*(-(nu/6.)*deriv)
+
+
+def mass_function(hm: HaloModel, M, sigmaM):
+    """n(M) = F rhom/M^2, pyhalomodel.py:286-296"""
+    return multiplicity_function(hm, M, sigmaM)*hm.rhom/M**2
+
+
 def is_increasing(x):
     """utility.py:63-67"""
     return np.all(np.diff(x) > 0.)

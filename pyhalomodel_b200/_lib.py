@@ -62,6 +62,13 @@ _SIGNATURES = {
                              C.c_void_p, C.c_void_p]),
     'hm_average_batch': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_void_p]),
+    'hm_multiplicity_function': (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
+    'hm_cross_halo_workspace': (C.c_size_t, [C.c_int32]),
+    'hm_cross_halo_spectrum': (C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                        C.c_int32, C.POINTER(Tracer), C.POINTER(C.c_double), C.c_int32, C.c_void_p,
+                                        C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.c_void_p]),
     'hm_weighted_rowsum': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     'hm_power_spectrum_workspace': (C.c_size_t, [C.POINTER(Problem)]),
     'hm_power_spectrum': (C.c_int, [C.POINTER(Problem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

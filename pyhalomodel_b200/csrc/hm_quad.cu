@@ -24,6 +24,8 @@
 //                          discrete/shot-noise/k_trunc fix-ups and P_hm (:456-501).
 //
 // Algorithmic bytes per launch of the streaming kernel: 8*(G*P*nk*nM + B*(P+S)*nM).
+#include <cuda.h>      // CUtensorMap: types only, the encoder is fetched through cudaGetDriverEntryPoint
+
 #include "hm_common.cuh"
 
 #define HM_MAXP HM_MAX_TRACERS
@@ -44,7 +46,8 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
 //   weights [B][NW][nMp]            per-mass weight vectors
 //   scal    [B][HM_NSCAL]           A, rhom, w2[0], -, c_p[0] (8): the last two feed the beta_NL edge terms
 //   inl     [B][S][nk]              non-linear-bias two-halo term I_NL (only when beta is given)
-//   cpart   [B][nchunks][2*HM_MAXP] per-mass-chunk partial sums of the shot-noise and simple-two-halo integrals
+//   cpart   [B][nchunks+1][2*HM_MAXP] per-mass-chunk partial sums of the shot-noise and simple-two-halo integrals
+//                                   (last slot: the low-mass term of the latter); only written when flags need them
 //   partial [B][nparts][nk][NW]     partial row sums over mass sub-ranges written by the quadrature kernel
 //                                   (streaming kernel: one part per consumer warp per 512-mass slice)
 // ---------------------------------------------------------------------------------------------------------------
@@ -54,10 +57,9 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
                              // (256 consumer threads x double2); slices are HM_MC or 2*HM_MC wide
 #define HM_CONSUMER_WARPS 8
 #define HM_STREAM_THREADS (32 * (HM_CONSUMER_WARPS + 1))
-#define HM_ROWS_RG 1         // row-per-lane kernel: groups of 64 rows per item ...
-#define HM_ROWS_CS 32        // ... and mass columns per stage
-#define HM_ROWS_PW 4         // ... fed by this many producer warps
-#define HM_ROWS_THREADS (32 * (HM_CONSUMER_WARPS + HM_ROWS_PW))
+#define HM_ROWS_CS 32        // row-per-lane kernel: mass columns per stage (four per consumer warp)
+#define HM_ROWS_THREADS (32 * (HM_CONSUMER_WARPS + 1))
+#define HM_ROWS_MAXF 5       // ... for 2..5 models per sample on one or two tracers
 
 struct hm_layout {
   int P, S, NW, nMp, nchunks, nslices, nparts, MC;
@@ -74,6 +76,12 @@ static bool hm_can_stream(const hm_problem* pr) {
   return true;
 }
 
+// The shot-noise integral only enters a discrete auto spectrum when exactly one of correct_discrete /
+// subtract_shotnoise is set (:484-491), the k-independent two-halo integral only with simple_twohalo (:442-446).
+static bool hm_needs_cpart(const hm_problem* pr) {
+  return pr->simple_twohalo || ((pr->correct_discrete != 0) != (pr->subtract_shotnoise != 0));
+}
+
 static hm_layout hm_make_layout(const hm_problem* pr) {
   hm_layout L;
   L.P = pr->n_tracers;
@@ -84,18 +92,18 @@ static hm_layout hm_make_layout(const hm_problem* pr) {
   L.stream = hm_can_stream(pr);
   // wide slices (4 mass columns per consumer thread) halve the partial sums and the reductions per byte; they fit
   // the register budget up to 3 tracers and are used when the mass axis is long enough to fill them
-  L.MC = (pr->nM >= 2 * HM_MC && L.P <= 3 && pr->models_per_sample != 5) ? 2 * HM_MC : HM_MC;
+  // two to five mass functions per sample on one or two tracers (BASELINE config 3 has five): the row-per-lane
+  // kernel reads the shared grids once for all of them and combines its column groups itself (one part)
+  L.rows = L.stream && pr->models_per_sample >= 2 && pr->models_per_sample <= HM_ROWS_MAXF && L.P <= 2;
+  L.MC = (pr->nM >= 2 * HM_MC && L.P <= 3 && !L.rows) ? 2 * HM_MC : HM_MC;
   L.nslices = L.stream ? (pr->nM + L.MC - 1) / L.MC : 1;
   L.nparts = L.stream ? L.nslices * HM_CONSUMER_WARPS : 1;
-  // five mass functions per sample on one or two tracers (BASELINE config 3): the row-per-lane kernel reads the
-  // shared grids once for all five and combines its column groups itself (one part)
-  L.rows = L.stream && pr->models_per_sample == 5 && L.P <= 2;
   if (L.rows) { L.nslices = 1; L.nparts = 1; }
   L.B = (size_t)pr->n_samples * (size_t)pr->models_per_sample;
   auto align = [](size_t x) { return (x + 31) & ~(size_t)31; };
   L.scal_offset = align(L.B * (size_t)L.NW * (size_t)L.nMp);
   L.cpart_offset = align(L.scal_offset + L.B * HM_NSCAL);
-  L.partial_offset = align(L.cpart_offset + L.B * (size_t)L.nchunks * 2 * HM_MAXP);
+  L.partial_offset = align(L.cpart_offset + L.B * (size_t)(L.nchunks + 1) * 2 * HM_MAXP);
   L.inl_offset = align(L.partial_offset + L.B * (size_t)L.nparts * L.NW * (size_t)pr->nk);
   L.total_bytes = (L.inl_offset + (pr->beta_dev ? L.B * (size_t)L.S * pr->nk : 0)) * sizeof(double);
   return L;
@@ -115,104 +123,175 @@ struct hm_weights_args {
   int mode[HM_MAXP], mass[HM_MAXP], discrete[HM_MAXP];
   double* weights;
   double* scal;
-  double* cpart;
+  double* cpart;                     // [B][nchunks + 1][2*HM_MAXP], written only by hm_weights_kernel<true>
   double* lowmass;                   // optional [B]
 };
 
+// grid (nchunks + 1, G): CTA (chunk, s) builds the weight vectors of 256 masses for ALL F models of sample s -- the
+// loads of sigma, M, amplitudes and variances and (when the models share delta_c) the three divisions behind nu are
+// shared by the F mass functions -- and CTA (nchunks, s) integrates the low-mass correction A of each model
+// (pyhalomodel.py:413-414) and owns everything that needs it: e_p[0] with the A W(k,M0)/M0 term, the scalars, A.
+// RED: also reduce the shot-noise and simple-two-halo integrals (:423-426, :442-446); only non-default flags read
+// them (hm_epilogue_kernel), so the default path skips the 16 block reductions per model altogether.
+template <bool RED>
 __global__ void __launch_bounds__(HM_WCHUNK) hm_weights_kernel(const hm_weights_args a) {
-  constexpr int NRED = 2 * HM_MAXP + 1;                 // shot noise [8], simple two-halo [8], low-mass integral
+  constexpr int NRED = 2 * HM_MAXP;                     // shot noise [8], simple two-halo [8]
   __shared__ double sred[HM_WCHUNK / 32][NRED];
-  __shared__ double stot[NRED];
-  __shared__ double s_an0[HM_MAXP];
-  const int b = blockIdx.y, chunk = blockIdx.x;
+  __shared__ double sA[HM_WCHUNK / 32];
+  const int s = blockIdx.y, chunk = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int s = b / a.F;
-  const hm_model_desc d = a.models ? a.models[b] : a.single;
   const double* sig = a.sigma + (size_t)s * a.nM;
   const double M0 = a.M[0];
 
-  double red[NRED];
+  if (chunk == a.nchunks) {
+    // ---- low-mass CTA: A = 1 - int g b dnu from nu[0] by composite Gauss-Legendre, one node per thread, summed
+    // in a fixed order (warp butterflies, then the warps in order) ----
+    for (int f = 0; f < a.F; ++f) {
+      const int b = s * a.F + f;
+      const hm_model_desc d = a.models ? a.models[b] : a.single;
+      const double part = hm_warp_sum(hm_lowmass_node(d, d.dc / sig[0], tid));
+      __syncthreads();                                  // sA is free again
+      if (lane == 0) sA[warp] = part;
+      __syncthreads();
+      if (tid == 0) {
+        double tot = 0.;
 #pragma unroll
-  for (int i = 0; i < NRED; ++i) red[i] = 0.;
-  // A = 1 - int g b dnu from nu[0] (pyhalomodel.py:413-414): one Gauss-Legendre node per thread, chunk 0 only
-  if (chunk == 0) red[2 * HM_MAXP] = hm_lowmass_node(d, d.dc / sig[0], tid);
-
-  double* wout = a.weights + (size_t)b * a.NW * a.nMp;
-  const int m = chunk * HM_WCHUNK + tid;
-  double cW[HM_MAXP], w2_plain = 0.;
-#pragma unroll
-  for (int p = 0; p < HM_MAXP; ++p) cW[p] = 0.;
-  if (m < a.nMp && m >= a.nM) {   // padding column
-    for (int i = 0; i < a.NW; ++i) wout[(size_t)i * a.nMp + m] = 0.;
-  } else if (m < a.nM) {
-    const double nu = d.dc / sig[m];
-    const double nu_hi = (m + 1 < a.nM) ? d.dc / sig[m + 1] : nu;
-    const double nu_lo = (m > 0) ? d.dc / sig[m - 1] : nu;
-    const double tw = 0.5 * (nu_hi - nu_lo);   // trapezoid rule in nu as a weight (scipy trapezoid, :27)
-    const double g = hm_g_nu(d, nu);
-    const double bg = hm_b_nu(d, nu) * g;
-    const double Mm = a.M[m];
-    const double w1 = tw * (g / Mm);           // one-halo weight  (:530)
-    w2_plain = tw * (bg / Mm);                 // two-halo weight  (:539); the low-mass term is patched in below
-#pragma unroll
-    for (int p = 0; p < HM_MAXP; ++p) {
-      if (p < a.P) {
-        const double amp = a.amplitude[p][(size_t)s * a.amp_stride[p] + m];
-        const double norm = a.norm[p][b];
-        // <N(N-1)> or <N^2> plus variance (:466-473); no FMA contraction so exact zeros stay exact
-        double fac = (a.correct_discrete && a.discrete[p]) ? __dmul_rn(amp, __dadd_rn(amp, -1.)) : __dmul_rn(amp, amp);
-        if (a.variance[p]) fac = __dadd_rn(fac, a.variance[p][(size_t)s * a.nM + m]);
-        const double an = amp / norm;
-        double uS;   // U/normalisation = uS * grid
-        if (a.mode[p] == HM_GRID_UK) { cW[p] = an; uS = 1. / norm; }
-        else if (a.mode[p] == HM_GRID_WK) { cW[p] = 1.; uS = 1. / (amp * norm); }
-        else { cW[p] = 1.; uS = 1. / norm; }
-        wout[(size_t)p * a.nMp + m] = w2_plain * cW[p];                                  // e_p
-        wout[(size_t)(a.P + p) * a.nMp + m] = __dmul_rn(__dmul_rn(w1, fac), uS * uS);     // d_p
-        red[p] = w1 * (amp / (norm * norm));                                             // shot noise integrand (:425)
-        red[HM_MAXP + p] = w2_plain * an;                                                // simple two-halo (:442-446)
-        if (m == 0) s_an0[p] = an;
+        for (int w = 0; w < HM_WCHUNK / 32; ++w) tot += sA[w];
+        const double A = 1. - tot;
+        const double Aterm = A / M0;                    // multiplies W(k, M[0]) for mass tracers (:541-542)
+        const double nu = d.dc / sig[0], nu_hi = d.dc / sig[1];
+        const double tw = 0.5 * (nu_hi - nu);
+        const double w2_plain = tw * (hm_b_nu(d, nu) * hm_g_nu(d, nu) / M0);
+        double* wout = a.weights + (size_t)b * a.NW * a.nMp;
+        double* sc = a.scal + (size_t)b * HM_NSCAL;
+        double* cp = a.cpart + ((size_t)b * (a.nchunks + 1) + a.nchunks) * 2 * HM_MAXP;
+        for (int p = 0; p < HM_MAXP; ++p) {
+          double cW = 0., low = 0.;
+          if (p < a.P) {
+            const double an = a.amplitude[p][(size_t)s * a.amp_stride[p]] / a.norm[p][b];
+            cW = (a.mode[p] == HM_GRID_UK) ? an : 1.;
+            wout[(size_t)p * a.nMp] = a.mass[p] ? (w2_plain + Aterm) * cW : w2_plain * cW;   // e_p[0]
+            if (a.mass[p]) low = Aterm * an;
+          }
+          sc[4 + p] = cW;                               // w2[0] and c_p[0]: edge terms of the beta_NL integral
+          if (RED) { cp[p] = 0.; cp[HM_MAXP + p] = low; }
+        }
+        sc[0] = A;
+        sc[1] = d.rhom;
+        sc[2] = w2_plain;
+        if (a.lowmass) a.lowmass[b] = A;
       }
     }
-    int idx = 2 * a.P;
-    for (int u = 0; u < a.P; ++u)
-      for (int v = u + 1; v < a.P; ++v) wout[(size_t)(idx++) * a.nMp + m] = w1 * cW[u] * cW[v];   // q_uv
+    return;
   }
 
-  // one reduction phase for all 17 sums: warp butterflies, then a fixed-order sum over the 8 warps
+  // per-model constants of a group of up to 8 models: parameter logarithms and reciprocal normalisations, computed
+  // once per CTA instead of once per thread
+  struct fam_consts { hm_family_consts c; double rnorm[HM_MAXP]; };
+  __shared__ fam_consts sfc[8];
+
+  const int m = chunk * HM_WCHUNK + tid;
+  const bool live = m < a.nM;
+  const bool pad = !live && m < a.nMp;                  // padding column: zero weights
+  double sg = 1., sg_hi = 1., sg_lo = 1., rM = 1.;
+  double amp[HM_MAXP], var[HM_MAXP];
 #pragma unroll
-  for (int i = 0; i < NRED; ++i) {
-    const bool used = (i == 2 * HM_MAXP) ? (chunk == 0) : ((i & (HM_MAXP - 1)) < a.P);   // the others are zero
-    const double t = used ? hm_warp_sum(red[i]) : 0.;
-    if (lane == 0) sred[warp][i] = t;
-  }
-  __syncthreads();
-  if (tid < NRED) {
-    double t = 0.;
-#pragma unroll
-    for (int w = 0; w < HM_WCHUNK / 32; ++w) t += sred[w][tid];
-    stot[tid] = t;
-  }
-  __syncthreads();
-  const double A = 1. - stot[2 * HM_MAXP];
-  const double Aterm = A / M0;   // multiplies W(k, M[0]) for mass tracers (:541-542)
-  double* cp = a.cpart + ((size_t)b * a.nchunks + chunk) * 2 * HM_MAXP;
-  if (tid < a.P) {
-    cp[tid] = a.discrete[tid] ? stot[tid] : 0.;
-    const double low = (chunk == 0 && a.mass[tid]) ? Aterm * s_an0[tid] : 0.;
-    cp[HM_MAXP + tid] = stot[HM_MAXP + tid] + low;
-  }
-  if (chunk == 0 && tid == 0) {
+  for (int p = 0; p < HM_MAXP; ++p) amp[p] = var[p] = 0.;
+  if (live) {
+    sg = sig[m];
+    sg_hi = (m + 1 < a.nM) ? sig[m + 1] : sg;
+    sg_lo = (m > 0) ? sig[m - 1] : sg;
+    rM = 1. / a.M[m];
 #pragma unroll
     for (int p = 0; p < HM_MAXP; ++p)
-      if (p < a.P && a.mass[p]) wout[(size_t)p * a.nMp] = (w2_plain + Aterm) * cW[p];     // e_p[0] with the low-mass term
-    double* sc = a.scal + (size_t)b * HM_NSCAL;
-    sc[0] = A;
-    sc[1] = d.rhom;
-    sc[2] = w2_plain;                                   // w2[0] and c_p[0]: edge terms of the beta_NL integral
+      if (p < a.P) {
+        amp[p] = a.amplitude[p][(size_t)s * a.amp_stride[p] + m];
+        if (a.variance[p]) var[p] = a.variance[p][(size_t)s * a.nM + m];
+      }
+  }
+  double dc_prev = 0., nu = 0., lnnu = 0., tw = 0.;
+#pragma unroll 1
+  for (int f = 0; f < a.F; ++f) {
+    const int b = s * a.F + f;
+    const hm_model_desc d = a.models ? a.models[b] : a.single;
+    if ((f & 7) == 0) {
+      __syncthreads();                                  // the previous group is done with sfc
+      if (tid < 8 && f + tid < a.F) {
+        const hm_model_desc dm = a.models ? a.models[b + tid] : a.single;
+        sfc[tid].c = hm_make_family_consts(dm);
+        for (int p = 0; p < HM_MAXP; ++p) sfc[tid].rnorm[p] = (p < a.P) ? 1. / a.norm[p][b + tid] : 0.;
+      }
+      __syncthreads();
+    }
+    const fam_consts& fc = sfc[f & 7];
+    double* wout = a.weights + (size_t)b * a.NW * a.nMp;
+    double red[NRED];
 #pragma unroll
-    for (int p = 0; p < HM_MAXP; ++p) sc[4 + p] = cW[p];
-    if (a.lowmass) a.lowmass[b] = A;
+    for (int i = 0; i < NRED; ++i) red[i] = 0.;
+    if (pad) {
+      for (int i = 0; i < a.NW; ++i) wout[(size_t)i * a.nMp + m] = 0.;
+    } else if (live) {
+      if (f == 0 || d.dc != dc_prev) {                  // models of one sample usually share delta_c
+        nu = d.dc / sg;
+        const double nu_hi = (m + 1 < a.nM) ? d.dc / sg_hi : nu;
+        const double nu_lo = (m > 0) ? d.dc / sg_lo : nu;
+        tw = 0.5 * (nu_hi - nu_lo);                     // trapezoid rule in nu as a weight (scipy trapezoid, :27)
+        lnnu = log(nu);
+        dc_prev = d.dc;
+      }
+      double g, bg;
+      hm_gb_nu_shared(d, fc.c, nu, lnnu, g, bg);
+      const double w1 = tw * (g * rM);                  // one-halo weight  (:530)
+      const double w2_plain = tw * (bg * rM);           // two-halo weight  (:539)
+      double cW[HM_MAXP];
+#pragma unroll
+      for (int p = 0; p < HM_MAXP; ++p) {
+        cW[p] = 0.;
+        if (p < a.P) {
+          const double rnorm = fc.rnorm[p];
+          // <N(N-1)> or <N^2> plus variance (:466-473); no FMA contraction so exact zeros stay exact
+          double fac = (a.correct_discrete && a.discrete[p]) ? __dmul_rn(amp[p], __dadd_rn(amp[p], -1.))
+                                                             : __dmul_rn(amp[p], amp[p]);
+          if (a.variance[p]) fac = __dadd_rn(fac, var[p]);
+          const double an = amp[p] * rnorm;
+          double uS;   // U/normalisation = uS * grid
+          if (a.mode[p] == HM_GRID_UK) { cW[p] = an; uS = rnorm; }
+          else if (a.mode[p] == HM_GRID_WK) { cW[p] = 1.; uS = rnorm / amp[p]; }
+          else { cW[p] = 1.; uS = rnorm; }
+          if (m != 0) wout[(size_t)p * a.nMp + m] = w2_plain * cW[p];                      // e_p (e_p[0]: low-mass CTA)
+          wout[(size_t)(a.P + p) * a.nMp + m] = __dmul_rn(__dmul_rn(w1, fac), uS * uS);     // d_p
+          if (RED) {
+            red[p] = w1 * (an * rnorm);                                                    // shot noise integrand (:425)
+            red[HM_MAXP + p] = w2_plain * an;                                              // simple two-halo (:442-446)
+          }
+        }
+      }
+      int idx = 2 * a.P;
+#pragma unroll
+      for (int u = 0; u < HM_MAXP; ++u)
+#pragma unroll
+        for (int v = u + 1; v < HM_MAXP; ++v)
+          if (v < a.P) wout[(size_t)(idx++) * a.nMp + m] = w1 * cW[u] * cW[v];                     // q_uv
+    }
+    if (RED) {
+      // one reduction phase for the 16 sums: warp butterflies, then a fixed-order sum over the 8 warps
+#pragma unroll
+      for (int i = 0; i < NRED; ++i) {
+        const bool used = (i & (HM_MAXP - 1)) < a.P;    // the others are zero
+        const double t = used ? hm_warp_sum(red[i]) : 0.;
+        if (lane == 0) sred[warp][i] = t;
+      }
+      __syncthreads();
+      if (tid < NRED) {
+        double t = 0.;
+#pragma unroll
+        for (int w = 0; w < HM_WCHUNK / 32; ++w) t += sred[w][tid];
+        const int p = tid & (HM_MAXP - 1);
+        double* cp = a.cpart + ((size_t)b * (a.nchunks + 1) + chunk) * 2 * HM_MAXP;
+        cp[tid] = (tid >= HM_MAXP || (p < a.P && a.discrete[p])) ? t : 0.;
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -516,156 +595,151 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Row-per-lane streaming kernel for sweeps that evaluate FM models (mass functions) on the grids of one sample.
+// Row-per-lane streaming kernel for sweeps that evaluate FM = 2..5 models (mass functions) on the grids of one sample.
 //
 // With FM*(P+S) = 25 sums per grid row and only 16 bytes of grid per (k, M) point, the column-per-lane kernel above
 // drowns in its warp reductions (one 32-value shuffle network per 50 FMAs; ncu: 423 instructions per warp tile,
-// FP64 pipe 29 %).  Here a lane owns two wavenumber rows (lane and lane + 32 of a 64-row group) for the whole mass
+// FP64 pipe 29 %).  Here a lane owns two wavenumber rows (lane and lane + 32 of a 64-row tile) for the whole mass
 // axis, so its FM*(P+S) sums per row stay in registers from the first mass to the last and nothing is ever
 // reduced across lanes.  The weights of a mass column are the same for every lane: they ride in the ring next to
-// the grid tile (cp.async copies of the same [model][i][m] vectors the other kernels use) and are read with broadcast
-// 16-byte shared-memory loads, one load feeding four FMAs (two rows x two columns).  The grid rows of a stage are
-// padded by 16 bytes so that the eight lanes of a quarter warp hit eight different 16-byte bank groups.
-// An item is (sample, 64*RG-row tile); the 8 consumer warps split into RG row groups x CG column groups, and every
-// warps add their sums in shared memory in warp order at the end of the item: partial[model][i][row], one part.
-// Items are dealt round-robin (CTA c takes c, c + grid, ...), so the row tiles of one sample run at the same time
-// on neighbouring SMs and its weight vectors come from DRAM once and from L2 for the other tiles.
+// the grid tile and are read with broadcast 16-byte shared-memory loads, one load feeding four FMAs (two rows x two
+// columns).
+//
+// Feeding: ONE producer lane drives the TMA unit with 2-D tensor-map copies (cp.async.bulk.tensor.2d, SASS UTMALDG):
+// per 32-column stage one 64-row x 16-column box per tracer and half stage (128-byte rows, SWIZZLE_128B: the
+// eight lanes of a quarter warp read eight different 16-byte bank groups without padding) plus one FM*(P+S) x 32 box of
+// the weight vectors; ragged mass and wavenumber edges are zero-filled by the TMA unit.  (Round 1 fed this ring with
+// four warps of LDGSTS copies after 153 one-dimensional bulk copies per stage had serialised on the TMA unit.)
+//
+// An item is (sample, 64-row tile); the 8 consumer warps own 4 of a stage's 32 columns each and add their sums at the
+// end of the item in a binary tree through shared memory (warp w+4 -> w, w+2 -> w, 1 -> 0: a fixed summation order).
+// The hand-overs of the tree are mbarrier pairs per writer, so a warp that has handed its sums over starts the next
+// item's stages at once while the others are still adding: the combine overlaps the streaming.  Items are dealt
+// round-robin (CTA c takes c, c + grid, ...), so the row tiles of one sample run at the same time on neighbouring
+// SMs and its weight vectors come from DRAM once and from L2 for the other tiles.
 // ---------------------------------------------------------------------------------------------------------------
-template <int P, int FM, int RG, int CS>
+__device__ __forceinline__ void hm_tma_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+template <int P, int FM>
 struct hm_rows_cfg {
   static constexpr int S = P * (P + 1) / 2;
   static constexpr int NW = P + S;
   static constexpr int NV = FM * NW;                          // sums per grid row
-  static constexpr int CG = HM_CONSUMER_WARPS / RG;           // column groups of warps = mass parts
-  static constexpr int CW = CS / CG;                          // columns per warp per stage
-  static constexpr int RT = 64 * RG;                          // rows per item
-  static constexpr int ROWB = CS * 8 + 16;                    // padded pitch of a grid row in the ring
-  static constexpr int DATA_BYTES = RT * P * ROWB;
+  static constexpr int CS = HM_ROWS_CS;                       // mass columns per stage
+  static constexpr int BOXC = 16;                             // columns per grid box: 128 bytes, the swizzle span
+  static constexpr int NBOX = CS / BOXC;
+  static constexpr int RT = 64;                               // rows per item
+  static constexpr int BOX_BYTES = RT * BOXC * 8;
+  static constexpr int DATA_BYTES = P * NBOX * BOX_BYTES;
   static constexpr int W_BYTES = NV * CS * 8;
-  static constexpr int STAGE_BYTES = ((DATA_BYTES + W_BYTES + 127) / 128) * 128;
-  static constexpr int COMB_BYTES = RT * NV * 8;              // the item's sums, combined over the column groups
-  static constexpr int BUDGET = 226 * 1024 - 256 - COMB_BYTES;
-  static constexpr int NS = (BUDGET / STAGE_BYTES) > 6 ? 6 : (BUDGET / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = NS * STAGE_BYTES + COMB_BYTES + 256;
-  static_assert(RG == 1, "the in-kernel combine assumes that all consumer warps share the item's 64 rows");
-  static_assert(CW >= 2 && CW % 2 == 0, "a warp works on pairs of columns");
+  static constexpr int TX_BYTES = DATA_BYTES + W_BYTES;
+  static constexpr int STAGE_BYTES = ((TX_BYTES + 1023) / 1024) * 1024;
+  static constexpr int COMB_DOUBLES = RT * NV;                // one reader's buffer of the combine tree
+  static constexpr int COMB_BYTES = 4 * COMB_DOUBLES * 8;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int BUDGET = 227 * 1024 - BAR_BYTES - COMB_BYTES - 1024;   // 1024: alignment slack of the ring
+  static constexpr int NS = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = NS * STAGE_BYTES + COMB_BYTES + BAR_BYTES + 1024;
+  static_assert(CS == 4 * HM_CONSUMER_WARPS, "a consumer warp owns four columns of a stage");
   static_assert(NS >= 2, "the ring needs two stages");
 };
 
-template <int P, int FM, int RG, int CS>
-__global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const hm_quad_args a) {
-  using C = hm_rows_cfg<P, FM, RG, CS>;
-  constexpr int NW = C::NW, NV = C::NV, NS = C::NS, RT = C::RT, ROWB = C::ROWB;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* comb = reinterpret_cast<double*>(smem_raw + (size_t)NS * C::STAGE_BYTES);        // [NV][64 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * C::STAGE_BYTES + C::COMB_BYTES);   // full[NS], empty[NS]
+template <int P, int FM>
+__global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const hm_quad_args a,
+                                                                          const __grid_constant__ CUtensorMap tmG0,
+                                                                          const __grid_constant__ CUtensorMap tmG1,
+                                                                          const __grid_constant__ CUtensorMap tmW) {
+  using C = hm_rows_cfg<P, FM>;
+  constexpr int NW = C::NW, NV = C::NV, NS = C::NS, RT = C::RT, CS = C::CS;
+  extern __shared__ unsigned char smem_dyn[];
+  // SWIZZLE_128B boxes want 1024-byte aligned destinations
+  unsigned char* smem_raw = smem_dyn + ((1024u - (hm_smem_addr(smem_dyn) & 1023u)) & 1023u);
+  double* comb = reinterpret_cast<double*>(smem_raw + (size_t)NS * C::STAGE_BYTES);        // [4 readers][NV][64 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * C::STAGE_BYTES + C::COMB_BYTES);
   const uint32_t ring = hm_smem_addr(smem_raw);
   const uint32_t bar_full = hm_smem_addr(bars), bar_empty = hm_smem_addr(bars + NS);
+  const uint32_t bar_pfull = hm_smem_addr(bars + 2 * NS), bar_pempty = hm_smem_addr(bars + 2 * NS + 8);   // per writer warp
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
-      hm_mbar_init(bar_full + 8 * s, 32 * HM_ROWS_PW);    // every producer lane (cp.async arrive, .noinc)
+      hm_mbar_init(bar_full + 8 * s, 1);                  // the producer's arrive.expect_tx
       hm_mbar_init(bar_empty + 8 * s, HM_CONSUMER_WARPS);
+    }
+    for (int w = 0; w < 8; ++w) {
+      hm_mbar_init(bar_pfull + 8 * w, 1);
+      hm_mbar_init(bar_pempty + 8 * w, 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   // (sample, row tile) items dealt round-robin over the CTAs; every item walks the whole mass axis
-  const long long it0 = blockIdx.x, it1 = a.nitems;
+  const int it0 = blockIdx.x, it1 = (int)a.nitems;            // (host: nitems < 2^31)
   const int istep = gridDim.x, step_smp = istep / a.ntiles, step_tile = istep - step_smp * a.ntiles;
   const int nstages = (a.nM + CS - 1) / CS;
-  int smp = (int)(it0 / a.ntiles), tile = (int)(it0 - (long long)smp * a.ntiles);
+  int smp = it0 / a.ntiles, tile = it0 - smp * a.ntiles;
   int s = 0;
   uint32_t parity = 0;
 
-  if (warp >= HM_CONSUMER_WARPS) {
-    // ---- producer warps: one 16-byte cp.async per lane (LDGSTS: a warp instruction moves the 256-byte segments of
-    // two rows, landing at the padded pitch); the lanes' copies complete on the stage's mbarrier.  Producer warp pw
-    // moves row pairs pw, pw + PW, ... ; addresses are base + constant * stride so that the copies issue back to
-    // back.  (One TMA bulk copy per row segment -- 153 small copies per stage -- serialises on the SM's TMA unit:
-    // 654 us per launch against 240 us this way.) ----
-    constexpr int PW = HM_ROWS_PW;
-    constexpr int LPR = CS / 2;                 // lanes per row segment (16 bytes each)
-    constexpr int RPI = 32 / LPR;               // rows per warp instruction
-    static_assert(LPR == 32 || LPR == 16, "a warp instruction moves one or two whole row segments");
-    static_assert(RT % (PW * RPI) == 0, "rows split evenly over the producer warps");
-    const int pw = warp - HM_CONSUMER_WARPS;
-    const int lrow = lane / LPR, lcol = 2 * (lane % LPR);          // my row inside an instruction, my first column
-    const int nk = a.nk, nM = a.nM, ntiles = a.ntiles;
-    const uint32_t rowstep = (uint32_t)nM * 8u * (PW * RPI), wstep = (uint32_t)a.nMp * 8u * (PW * RPI);
-    const int r_first = pw * RPI + lrow;                           // my rows: r_first + PW*RPI*i
-    for (long long it = it0; it < it1; it += istep) {
-      const int row0 = tile * RT;
-      const bool full_tile = row0 + RT <= nk;
-      const char* gsrc[P];
+  if (warp == HM_CONSUMER_WARPS) {
+    // ---------------------------------- producer: one lane drives the TMA unit ----------------------------------
+    if (lane == 0) {
+      for (int it = it0; it < it1; it += istep) {
+        const int row = smp * a.nk + tile * RT;             // first row of the item in the [G*nk][nM] tensors
+        const int wrow = smp * NV;                          // first of its weight vectors in the [B*NW][nMp] tensor
+        for (int st = 0; st < nstages; ++st) {
+          const int m0 = st * CS;
+          hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);     // slot drained by all consumer warps
+          hm_mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)C::TX_BYTES);   // OOB parts of a box count as well
+          const uint32_t dst = ring + (uint32_t)s * C::STAGE_BYTES;
 #pragma unroll
-      for (int p = 0; p < P; ++p)
-        gsrc[p] = reinterpret_cast<const char*>(a.gridW[p] + ((size_t)smp * nk + row0 + (full_tile ? r_first : 0)) * (size_t)nM + lcol);
-      const char* wsrc = reinterpret_cast<const char*>(a.weights + ((size_t)smp * NV + (r_first < NV ? r_first : 0)) * (size_t)a.nMp + lcol);
-      for (int st = 0; st < nstages; ++st) {
-        const int m0 = st * CS;
-        const bool on = lcol < nM - m0;
-        if (lane == 0) hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);      // slot drained by all consumer warps
-        __syncwarp();
-        const uint32_t dst0 = ring + (uint32_t)s * C::STAGE_BYTES + 8u * lcol + (uint32_t)r_first * ROWB;
-        if (on) {
-          if (full_tile) {
+          for (int p = 0; p < P; ++p)
 #pragma unroll
-            for (int p = 0; p < P; ++p)
-#pragma unroll
-              for (int i = 0; i < RT / (PW * RPI); ++i)
-                hm_cp_async16(dst0 + (uint32_t)(p * RT + PW * RPI * i) * ROWB,
-                              gsrc[p] + (size_t)m0 * 8 + (size_t)((uint32_t)i * rowstep));
-          } else {                                            // last tile of a ragged k axis: clamp (never written)
-#pragma unroll
-            for (int p = 0; p < P; ++p)
-#pragma unroll 4
-              for (int i = 0; i < RT / (PW * RPI); ++i) {
-                const int r = (row0 + r_first + PW * RPI * i < nk) ? r_first + PW * RPI * i : nk - 1 - row0;
-                hm_cp_async16(dst0 + (uint32_t)(p * RT + PW * RPI * i) * ROWB, gsrc[p] + ((size_t)r * nM + m0) * 8);
-              }
-          }
-          const uint32_t wdst = ring + (uint32_t)s * C::STAGE_BYTES + C::DATA_BYTES + 8u * lcol + (uint32_t)r_first * (CS * 8);
-#pragma unroll
-          for (int i = 0; i < (NV + PW * RPI - 1) / (PW * RPI); ++i)
-            if (r_first + PW * RPI * i < NV)
-              hm_cp_async16(wdst + (uint32_t)(PW * RPI * i) * (CS * 8), wsrc + (size_t)m0 * 8 + (size_t)((uint32_t)i * wstep));
+            for (int cb = 0; cb < C::NBOX; ++cb)
+              hm_tma_2d(dst + (uint32_t)((p * C::NBOX + cb) * C::BOX_BYTES), p == 0 ? &tmG0 : &tmG1, m0 + cb * C::BOXC, row,
+                        bar_full + 8 * s);
+          hm_tma_2d(dst + (uint32_t)C::DATA_BYTES, &tmW, m0, wrow, bar_full + 8 * s);
+          if (++s == NS) { s = 0; parity ^= 1u; }
         }
-        hm_cp_async_mbar_arrive(bar_full + 8 * s);                        // fires when my copies have landed
-        if (++s == NS) { s = 0; parity ^= 1u; }
+        smp += step_smp; tile += step_tile;
+        if (tile >= a.ntiles) { tile -= a.ntiles; ++smp; }
       }
-      smp += step_smp; tile += step_tile;
-      if (tile >= ntiles) { tile -= ntiles; ++smp; }
     }
     return;
   }
 
   // ------------------------------------------- consumer warps --------------------------------------------------
-  const int rg = warp % RG, cg = warp / RG;
-  const int cbeg = cg * C::CW;
-  const uint32_t my_row = (uint32_t)(rg * 64 + lane) * ROWB;          // my first row inside a tracer's block of rows
-  for (long long it = it0; it < it1; it += istep) {
+  // my four columns of a stage: 4*warp .. 4*warp + 3 = 16-byte chunks q0, q0 + 1 of box warp / 4; inside a box the
+  // chunk index is XORed with (row & 7) (SWIZZLE_128B)
+  const uint32_t boxoff = (uint32_t)(warp >> 2) * C::BOX_BYTES + (uint32_t)lane * 128u;
+  const uint32_t q0 = 2u * (warp & 3), sw = lane & 7u;
+  const uint32_t xo0 = boxoff + (((q0) ^ sw) << 4), xo1 = boxoff + (((q0 + 1u) ^ sw) << 4);
+  const uint32_t wcol = 4u * warp * 8u;                            // byte offset of my columns in a weight row
+  uint32_t item_no = 0;
+  for (int it = it0; it < it1; it += istep, ++item_no) {
     double acc[2][NV];
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
       for (int j = 0; j < NV; ++j) acc[r][j] = 0.;
-    for (int st = 0; st < nstages; ++st) {
-      const int cols = (a.nM - st * CS < CS) ? a.nM - st * CS : CS;
-      const int cend = (cbeg + C::CW < cols) ? cbeg + C::CW : cols;
-      const unsigned char* stage = smem_raw + (size_t)s * C::STAGE_BYTES;
-      const unsigned char* wsm = stage + C::DATA_BYTES;
-      hm_mbar_wait(bar_full + 8 * s, parity);                 // every producer lane's copies have landed
 #pragma unroll 1
-      for (int c = cbeg; c < cend; c += 2) {
-        double2 x[2][P];
+    for (int st = 0; st < nstages; ++st) {
+      const unsigned char* stage = smem_raw + (size_t)s * C::STAGE_BYTES;
+      const unsigned char* wsm = stage + C::DATA_BYTES + wcol;
+      hm_mbar_wait(bar_full + 8 * s, parity);                 // the stage's boxes have landed
+#pragma unroll
+      for (int cp = 0; cp < 2; ++cp) {
+        double2 x[2][P];                                      // [row][tracer] of this column pair
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
           for (int p = 0; p < P; ++p)
-            x[r][p] = *reinterpret_cast<const double2*>(stage + my_row + (uint32_t)(p * RT + r * 32) * ROWB + c * 8);
+            x[r][p] = *reinterpret_cast<const double2*>(stage + (size_t)(p * C::NBOX) * C::BOX_BYTES + r * (32 * 128) +
+                                                        (cp == 0 ? xo0 : xo1));
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
           // basis value i of my two rows and two columns: G_p, G_p^2, G_u G_v in the order of the weight vectors
@@ -690,7 +764,7 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
           }
 #pragma unroll
           for (int f = 0; f < FM; ++f) {
-            const double2 w2 = *reinterpret_cast<const double2*>(wsm + ((f * NW + i) * CS + c) * 8);   // broadcast
+            const double2 w2 = *reinterpret_cast<const double2*>(wsm + ((f * NW + i) * CS + 2 * cp) * 8);   // broadcast
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
               acc[r][f * NW + i] = fma(w2.x, v[r].x, acc[r][f * NW + i]);
@@ -703,27 +777,51 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
       if (lane == 0) hm_mbar_arrive(bar_empty + 8 * s);       // my reads of the slot are done
       if (++s == NS) { s = 0; parity ^= 1u; }
     }
-    // combine the column groups in shared memory in warp order (a fixed summation order), then store the item's
-    // RT x NV sums once: partial[model][i][row], coalesced over rows
-#pragma unroll 1
-    for (int w = 0; w < HM_CONSUMER_WARPS; ++w) {
-      if (warp == w) {
+
+    // ---- combine the eight column groups: binary tree over the warps, pipelined with the next item.  Reader r owns
+    // buffer r; writer x signals pfull[x] once per item and reader drains it with pempty[x], so every pair barrier
+    // completes exactly one phase per item.  A writer waits until the previous occupant of its target buffer has been
+    // drained: the previous writer of this item, or the buffer's last writer of the previous item. ----
+    const uint32_t ph = item_no & 1u;
+#pragma unroll
+    for (int step = 4; step >= 1; step >>= 1) {
+      if (warp < step) {
+        const int xw = warp + step;
+        hm_mbar_wait(bar_pfull + 8 * xw, ph);
+        const double* src = comb + (size_t)warp * C::COMB_DOUBLES + lane;
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-          for (int j = 0; j < NV; ++j) {
-            double* c = comb + j * 64 + r * 32 + lane;
-            *c = (w == 0) ? acc[r][j] : *c + acc[r][j];
-          }
+          for (int j = 0; j < NV; ++j) acc[r][j] += src[j * 64 + r * 32];
+        __syncwarp();
+        if (lane == 0) hm_mbar_arrive(bar_pempty + 8 * xw);
+      } else if (warp < 2 * step) {
+        const int t = warp - step;
+        int pred;
+        uint32_t pph;
+        if (step == 4) { pred = (t == 0) ? 1 : (t == 1) ? 3 : warp; pph = ph ^ 1u; }
+        else if (step == 2) { pred = t + 4; pph = ph; }
+        else { pred = 2; pph = ph; }
+        hm_mbar_wait(bar_pempty + 8 * pred, pph);
+        double* dst = comb + (size_t)t * C::COMB_DOUBLES + lane;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int j = 0; j < NV; ++j) dst[j * 64 + r * 32] = acc[r][j];
+        __syncwarp();
+        if (lane == 0) hm_mbar_arrive(bar_pfull + 8 * warp);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    for (int idx = tid; idx < 64 * NV; idx += 32 * HM_CONSUMER_WARPS) {
-      const int j = idx >> 6, row = tile * RT + (idx & 63);
-      const int f = j / NW, i = j - f * NW;
-      if (row < a.nk) a.partial[(((size_t)smp * FM + f) * NW + i) * (size_t)a.nk + row] = comb[idx];
+    if (warp == 0) {      // the item's RT x NV sums: partial[model][i][row], coalesced over rows
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int row = tile * RT + r * 32 + lane;
+        if (row < a.nk) {
+#pragma unroll
+          for (int j = 0; j < NV; ++j) a.partial[((size_t)smp * NV + j) * (size_t)a.nk + row] = acc[r][j];
+        }
+      }
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");               // comb is free for the next item
     smp += step_smp; tile += step_tile;
     if (tile >= a.ntiles) { tile -= a.ntiles; ++smp; }
   }
@@ -880,6 +978,7 @@ static int hm_launch_beta(const hm_beta_args& a, int B, cudaStream_t st) {
 struct hm_epi_args {
   int nk, B, F, P, NW, S, nparts, nchunks;
   int simple_twohalo, subtract_shotnoise, correct_discrete, fence_out;
+  int use_cpart;             // the shot-noise / simple-two-halo integrals are needed (and were reduced by the weights kernel)
   int rows_layout;           // partial is [B][nparts][NW][nk] (row-per-lane kernel) instead of [B][nparts][nk][NW]
   double k_trunc;
   const double* k;
@@ -927,7 +1026,8 @@ __global__ void __launch_bounds__(256) hm_epilogue_kernel(const hm_epi_args a) {
   if (tid < 2 * HM_MAXP) {     // tid < 8: shot noise of tracer tid; tid >= 8: simple two-halo integral
     const double* cp = a.cpart + (size_t)b * a.nchunks * 2 * HM_MAXP + tid;
     double t = 0.;
-    for (int c = 0; c < a.nchunks; ++c) t += cp[(size_t)c * 2 * HM_MAXP];
+    if (a.use_cpart)
+      for (int c = 0; c < a.nchunks; ++c) t += cp[(size_t)c * 2 * HM_MAXP];
     scs[tid] = t * rhom;       // P_SN = rhom trapz((amplitude/norm^2) g/M) (:423-426); simple two-halo (:442-446)
   }
   __syncthreads();
@@ -1044,8 +1144,9 @@ extern "C" int hm_halo_weights(const hm_problem* pr, double* lowmass_dev, void* 
   a.scal = (double*)ws + L.scal_offset;
   a.cpart = (double*)ws + L.cpart_offset;
   a.lowmass = lowmass_dev;
-  dim3 grid(L.nchunks, (unsigned)L.B);
-  hm_weights_kernel<<<grid, HM_WCHUNK, 0, (cudaStream_t)stream>>>(a);
+  dim3 grid(L.nchunks + 1, (unsigned)pr->n_samples);
+  if (hm_needs_cpart(pr)) hm_weights_kernel<true><<<grid, HM_WCHUNK, 0, (cudaStream_t)stream>>>(a);
+  else hm_weights_kernel<false><<<grid, HM_WCHUNK, 0, (cudaStream_t)stream>>>(a);
   HM_LAUNCH_CHECK();
   return HM_OK;
 }
@@ -1088,29 +1189,83 @@ static int hm_launch_stream_h(hm_quad_args& a, cudaStream_t st) {
   return HM_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*hm_tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static hm_tmap_encode_fn hm_tmap_encoder() {
+  static hm_tmap_encode_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (hm_tmap_encode_fn)p;
+  }
+  return fn;
+}
+
+// Row-major [rows][cols] float64 tensor with `pitch` doubles between rows, boxes of box_rows x box_cols.
+static int hm_make_tmap_2d(CUtensorMap* tm, const double* base, uint64_t cols, uint64_t rows, uint64_t pitch,
+                           uint32_t box_cols, uint32_t box_rows, bool swizzle128) {
+  hm_tmap_encode_fn enc = hm_tmap_encoder();
+  if (!enc) {
+    hm_set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return HM_ERR_CUDA;
+  }
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {pitch * sizeof(double)};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    hm_set_error("cuTensorMapEncodeTiled failed with CUresult %d (%llu x %llu, pitch %llu)", (int)r,
+                 (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch);
+    return HM_ERR_CUDA;
+  }
+  return HM_OK;
+}
+
 template <int P, int FM>
 static int hm_launch_rows(hm_quad_args& a, cudaStream_t st) {
-  using C = hm_rows_cfg<P, FM, HM_ROWS_RG, HM_ROWS_CS>;
+  using C = hm_rows_cfg<P, FM>;
   static hm_once_per_device once;
   if (once.needed()) {
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_quad_rows_kernel<P, FM, HM_ROWS_RG, HM_ROWS_CS>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_quad_rows_kernel<P, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::SMEM_BYTES));
   }
   a.ntiles = (a.nk + C::RT - 1) / C::RT;
-  a.nitems = (long long)(a.B / FM) * a.ntiles;                 // items enumerate (sample, row tile)
+  const int G = a.B / FM;
+  a.nitems = (long long)G * a.ntiles;                          // items enumerate (sample, row tile)
+  CUtensorMap tmG[2], tmW;
+  int rc;
+  for (int p = 0; p < 2; ++p)
+    if ((rc = hm_make_tmap_2d(&tmG[p], a.gridW[p < P ? p : 0], (uint64_t)a.nM, (uint64_t)G * a.nk, (uint64_t)a.nM, C::BOXC,
+                              C::RT, true)))
+      return rc;
+  if ((rc = hm_make_tmap_2d(&tmW, a.weights, (uint64_t)a.nMp, (uint64_t)a.B * C::NW, (uint64_t)a.nMp, C::CS, C::NV, false)))
+    return rc;
   long long grid = hm_num_sms();
   if (grid > a.nitems) grid = a.nitems;
-  hm_quad_rows_kernel<P, FM, HM_ROWS_RG, HM_ROWS_CS><<<(int)grid, HM_ROWS_THREADS, C::SMEM_BYTES, st>>>(a);
+  hm_quad_rows_kernel<P, FM><<<(int)grid, HM_ROWS_THREADS, C::SMEM_BYTES, st>>>(a, tmG[0], tmG[1], tmW);
   HM_LAUNCH_CHECK();
   return HM_OK;
 }
 
 template <int P, int R>
 static int hm_launch_stream(hm_quad_args& a, cudaStream_t st) {
-  // five models per sample on one or two tracers (the five mass functions of BASELINE config 3) take the
+  // two to five models per sample on one or two tracers (the five mass functions of BASELINE config 3) take the
   // row-per-lane kernel, which reads the shared grids once; other combinations read them once per model
-  if constexpr (P <= 2) {
-    if (a.F == 5) return hm_launch_rows<P, 5>(a, st);         // must agree with hm_layout.rows
+  if constexpr (P <= 2) {                                      // must agree with hm_layout.rows
+    switch (a.F) {
+      case 2: return hm_launch_rows<P, 2>(a, st);
+      case 3: return hm_launch_rows<P, 3>(a, st);
+      case 4: return hm_launch_rows<P, 4>(a, st);
+      case 5: return hm_launch_rows<P, 5>(a, st);
+    }
   }
   if constexpr (P <= 3) {
     if (a.MC == 2 * HM_MC) return hm_launch_stream_h<P, R, 2>(a, st);
@@ -1155,7 +1310,7 @@ extern "C" int hm_mass_quadrature_stages(const hm_problem* pr, double* out_dev, 
   a.partial = (double*)ws + L.partial_offset;
   hm_epi_args e;
   e.nk = pr->nk; e.B = (int)L.B; e.F = pr->models_per_sample; e.P = L.P; e.NW = L.NW; e.S = L.S;
-  e.nparts = L.nparts; e.nchunks = L.nchunks; e.rows_layout = L.rows;
+  e.nparts = L.nparts; e.nchunks = L.nchunks + 1; e.rows_layout = L.rows; e.use_cpart = hm_needs_cpart(pr);
   e.simple_twohalo = pr->simple_twohalo; e.subtract_shotnoise = pr->subtract_shotnoise;
   e.correct_discrete = pr->correct_discrete; e.k_trunc = pr->k_trunc; e.k = pr->k_dev; e.Pk_lin = pr->Pk_lin_dev;
   e.fence_out = pr->output_is_peer;

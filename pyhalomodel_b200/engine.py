@@ -127,6 +127,49 @@ def average_batch(models_dev, M, sigma, funcs, models_per_sample=1):
     return out
 
 
+def multiplicity_function(desc: ModelDesc, M, sigma, want_n=False):
+    """M [nM], sigma [nM] -> F = M^2 n(M)/rhobar, or n(M) itself (pyhalomodel.py:286-315)."""
+    M, sigma = to_dev(M), to_dev(sigma)
+    out = torch.empty_like(M)
+    check(lib().hm_multiplicity_function(C.byref(desc), _ptr(M), _ptr(sigma), M.shape[0], None if want_n else _ptr(out),
+                                         _ptr(out) if want_n else None, _stream()))
+    return out
+
+
+def cross_halo_spectrum(desc: ModelDesc, k, Pk_lin, M, sigma, tracers, interp_weights, beta=None, simple_twohalo=False,
+                        k_trunc=None):
+    """tracers: engine.Tracer with [nk, nM] grids and scalar normalisations -> (out [P, 3, nk], [A, nu_h, b_h])."""
+    k, Pk_lin, M, sigma, L = to_dev(k), to_dev(Pk_lin), to_dev(M), to_dev(sigma), to_dev(interp_weights)
+    nk, nM, P = k.shape[0], M.shape[0], len(tracers)
+    ct = (_lib.Tracer*P)()
+    norms = (C.c_double*P)()
+    keep = []
+    for p, t in enumerate(tracers):
+        grid = to_dev(t.grid, (nk, nM))
+        keep.append(grid)
+        ct[p].grid_dev = grid.data_ptr()
+        if t.mode == _lib.GRID_SEPARATE:
+            wk = to_dev(t.wk, (nk, nM))
+            keep.append(wk)
+            ct[p].wk_dev = wk.data_ptr()
+        if t.amplitude is not None:
+            amp = to_dev(t.amplitude, (nM,))
+            keep.append(amp)
+            ct[p].amplitude_dev = amp.data_ptr()
+        ct[p].grid_mode, ct[p].mass_tracer, ct[p].discrete_tracer = int(t.mode), int(t.mass_tracer), int(t.discrete_tracer)
+        norms[p] = float(t.normalisation)
+    beta = to_dev(beta, (nk, nM)) if beta is not None else None
+    out = torch.empty((P, 3, nk), dtype=F64, device=k.device)
+    scal = torch.empty(3, dtype=F64, device=k.device)
+    nbytes = lib().hm_cross_halo_workspace(nM)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=k.device)
+    check(lib().hm_cross_halo_spectrum(C.byref(desc), _ptr(k), _ptr(Pk_lin), _ptr(M), _ptr(sigma), nk, nM, ct, norms, P,
+                                       _ptr(L), _ptr(beta), int(bool(simple_twohalo)),
+                                       float(k_trunc) if k_trunc is not None else 0., _ptr(out), _ptr(scal), _ptr(ws),
+                                       nbytes, _stream()))
+    return out, scal
+
+
 def weighted_rowsum(grid, w):
     """grid [nk, nM], w [nw, nM] -> [nw, nk] with out[j, k] = sum_m w[j, m] grid[k, m]."""
     grid, w = to_dev(grid), to_dev(w)

@@ -194,24 +194,12 @@ class model():
 
     def multiplicity_function(self, M, sigmaM):
         '''M^2 n(M)/rhobar (pyhalomodel.py:298-315): g(nu) dnu/dlnM with the reference's three-point Lagrange
-        derivative of ln sigma against ln R (utility.py:15-35), vectorised on the device.'''
-        on_dev = _wants_device(M, sigmaM)
-        Md, sd = engine.to_dev(M), engine.to_dev(sigmaM)
-        nu = self.dc/sd
-        x = torch.log(torch.as_tensor(self.Lagrangian_radius(engine.to_host(Md)), device=Md.device))
-        f = torch.log(sd)
-        n = x.shape[0]
-        i1 = torch.arange(n, device=Md.device).clamp(1, n-2)      # stencil centre: (0,1,2) and (n-3,n-2,n-1) at the ends
-        x0, x1, x2 = x[i1-1], x[i1], x[i1+1]
-        f0, f1, f2 = f[i1-1], f[i1], f[i1+1]
-        d = (f0*(2.*x-x1-x2)/((x0-x1)*(x0-x2))+f1*(2.*x-x0-x2)/((x1-x0)*(x1-x2))+f2*(2.*x-x0-x1)/((x2-x0)*(x2-x1)))
-        g, _ = engine.massfn_nu(self.descriptor(), nu, want_b=False)
-        return _give_back(g*(-(nu/6.)*(2.*d)), on_dev)
+        derivative of ln sigma against ln R (utility.py:15-35); one element-wise kernel (hm_multiplicity_function).'''
+        return _give_back(engine.multiplicity_function(self.descriptor(), M, sigmaM), _wants_device(M, sigmaM))
 
     def mass_function(self, M, sigmaM):
         '''n(M) = F rhom/M^2 (pyhalomodel.py:286-296)'''
-        F = self.multiplicity_function(M, sigmaM)
-        return F*self.rhom/M**2
+        return _give_back(engine.multiplicity_function(self.descriptor(), M, sigmaM, want_n=True), _wants_device(M, sigmaM))
 
     def Lagrangian_radius(self, M):
         '''Radius [Mpc/h] of a sphere containing mass M in a homogeneous universe (pyhalomodel.py:327-333)'''
@@ -360,51 +348,16 @@ def _cross_halo_spectrum(self, k, Pk_lin, M, sigmaM, profiles, M_halo, beta=None
         if np.shape(Mh) != np.shape(prof.M) or (Mh != prof.M).all():
             raise ValueError('Mass arrays must be identical to those in profiles')
     on_dev = _wants_device(k, Pk_lin, M, sigmaM)
-    Md, sig, Pk, kd = engine.to_dev(M), engine.to_dev(sigmaM), engine.to_dev(Pk_lin), engine.to_dev(k)
-    nu = self.dc/sig
-    g, b = engine.massfn_nu(self.descriptor(), nu)
-    tw = torch.empty_like(nu)                     # trapezoid rule in nu as weights (pyhalomodel.py:27)
-    tw[1:-1] = 0.5*(nu[2:]-nu[:-2])
-    tw[0], tw[-1] = 0.5*(nu[1]-nu[0]), 0.5*(nu[-1]-nu[-2])
-    A = 1.-float(torch.sum(tw*(g*b)).item())      # note: trapezoid here, not quad (pyhalomodel.py:624-625)
-    L = engine.to_dev(_cubic_interp_weights(np.log(Mh), np.log(M_halo)))     # cubic interpolation in ln M (:631-639)
-    nu_halo = torch.sum(L*nu).reshape(1)
-    _, b_halo = engine.massfn_nu(self.descriptor(), nu_halo, want_g=False)
-    b_halo = b_halo[0]
-    w2 = tw*(b*g)/Md
-    damp = (1.-torch.exp(-(kd/k_trunc)**2)) if k_trunc is not None else None
-    betad = engine.to_dev(beta) if beta is not None else None
+    L = _cubic_interp_weights(np.log(Mh), np.log(M_halo))              # cubic interpolation in ln M (:631-639)
+    names = list(profiles.keys())
     out2, out1, outh = {}, {}, {}
-    for name, prof in profiles.items():
-        amp = prof._amplitude
-        norm = float(prof.normalisation)
-        if prof._mode == _lib.GRID_UK:
-            cW, gridW = amp/norm, prof._grid
-        else:
-            cW, gridW = torch.ones_like(Md), (prof._grid if prof._mode == _lib.GRID_WK else prof._wk)
-        e = w2*cW
-        if prof.mass_tracer:
-            e = e.clone()
-            e[0] = e[0]+(A/Md[0])*cW[0]                                     # A W(k, M0)/M0 (:541-542)
-        sums = engine.weighted_rowsum(gridW, torch.stack([e, L*cW]))        # I_u(k)/rhom and W(k, M_halo)
-        if simple_twohalo:                                                 # (:648-650)
-            Iu = self.rhom*(torch.sum(w2*(amp/norm))+(A*(amp[0]/norm)/Md[0] if prof.mass_tracer else 0.))
-            Iu = Iu.expand(kd.shape[0])
-        else:
-            Iu = sums[0]*self.rhom
-        I_NL = 0.
-        if betad is not None:                                              # _I_beta_hu (:691-704)
-            wb = betad*(gridW*cW[None, :])*(w2[None, :])                    # beta W g b/M with trapezoid weights
-            integral = torch.sum(wb, dim=1)
-            if prof.mass_tracer:
-                integral = integral+A*betad[:, 0]*(gridW[:, 0]*cW[0])/Md[0]
-            I_NL = b_halo*integral*self.rhom
-        p2h = (b_halo*Iu+I_NL)*Pk                                           # (:689)
-        p1h = sums[1].clone()                                               # the profile at M = M_halo (:662)
-        if damp is not None:
-            p1h = p1h*damp
-        out2[name], out1[name] = _give_back(p2h, on_dev), _give_back(p1h, on_dev)
-        outh[name] = out2[name]+out1[name]
+    for i0 in range(0, len(names), _lib.HM_MAX_TRACERS):               # the kernel takes up to 8 tracers per launch
+        chunk = names[i0:i0+_lib.HM_MAX_TRACERS]
+        res, _ = engine.cross_halo_spectrum(self.descriptor(), k, Pk_lin, M, sigmaM, [profiles[n]._tracer() for n in chunk],
+                                            L, beta=beta, simple_twohalo=simple_twohalo, k_trunc=k_trunc)
+        res = res if on_dev else engine.to_host(res)
+        for p, name in enumerate(chunk):
+            out2[name], out1[name], outh[name] = _split3(res[p], on_dev)
     return out2, out1, outh
 
 

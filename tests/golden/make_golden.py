@@ -79,6 +79,28 @@ def golden_massfn():
     save('massfn.npz', **out)
 
 
+def golden_mass_function():
+    """multiplicity_function / mass_function (pyhalomodel.py:286-315, utility.py:15-35) for the five families at two
+    redshifts on 128 masses, with the sigma(M) they were evaluated on."""
+    nM = 128
+    M = syn.M_grid(nM)
+    Om_m = 0.3
+    Plin0 = syn.LinearSpectrum(Om_m, 0.7, 0.96, 0.8)
+    out = dict(M=M, Om_m=np.array(Om_m), zs=np.array([0., 1.]))
+    for z in out['zs']:
+        dc, Dv = dcDv(z, Om_m)
+        out['dcDv_z%g' % z] = np.array([dc, Dv])
+        sig = None
+        for short, name in SHORT.items():
+            hmod = ref.model(z, Om_m, name=name, Dv=Dv, dc=dc)
+            if sig is None:
+                sig, _ = sigma_of_M(hmod, M, Plin0, z)
+                out['sigmaM_z%g' % z] = sig
+            out['F_%s_z%g' % (short, z)] = hmod.multiplicity_function(M, sig)
+            out['n_%s_z%g' % (short, z)] = hmod.mass_function(M, sig)
+    save('mass_function.npz', **out)
+
+
 def golden_windows():
     """U_NFW, U_iso, concentration, radii, HOD on small grids, plus a wide-argument sici stress grid."""
     k = syn.k_grid(48, 1e-3, 1e2)
@@ -395,6 +417,7 @@ if __name__ == '__main__':
             globals()['golden_'+name]()
         sys.exit(0)
     golden_massfn()
+    golden_mass_function()
     golden_windows()
     golden_sigma()
     golden_power_c1()

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import assert_spectra_close
+from conftest import assert_spectra_close, load_golden
 from oracle import halo_oracle as orc
 from pyhalomodel_b200 import synthetic as syn
 from test_gpu_parity import _synthetic_case
@@ -90,20 +90,54 @@ def test_gram_64_tracers_vs_oracle_small_grid(halo):
             assert_spectra_close(got[t][key], want[t][key], rtol=RTOL, what='%s term %d' % (key, t))
 
 
-def test_gram_config4_size_vs_streaming_path(halo):
-    """Config 4 at full size (64 HOD tracers, NFW, 256 k x 2048 M): every pair among 8-tracer subsets must agree
-    with the <=8-tracer streaming-quadrature path (itself oracle-checked), and the run is bitwise reproducible."""
+def test_gram_replays_live_reference_golden_13_tracers(halo):
+    """tests/golden/power_many.npz -- matter + 12 HOD samples, 91 unique pairs, written by the LIVE reference's pair
+    loop (pyhalomodel.py:433-507) -- through the Gram path (13 tracers > 8)."""
+    g = load_golden('power_many.npz')
+    dc, Dv = g['dcDv']
+    hmod = halo.model(float(g['z']), float(g['Om_m']), name=orc.TINKER10, Dv=Dv, dc=dc)
+    hods = [dict(zip(('Mmin', 'sigma', 'M0', 'M1', 'alpha'), h)) for h in g['hods']]
+    profs = _tracers(halo, hmod, g, hods, True, False, nfw=True)
+    for i, rho in enumerate(g['rho_g']):
+        np.testing.assert_allclose(profs['g%d' % i].normalisation, rho, rtol=1e-13)
+    from pyhalomodel_b200 import _lib
+    assert len(profs) == 13 > _lib.HM_MAX_TRACERS
+    got = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs)
+    names = list(profs.keys())
+    assert list(got[0].keys()) == [u+'-'+v for u in names for v in names]
+    for iu, u in enumerate(names):
+        for v in names[iu:]:
+            want = g['P_%s-%s' % (u, v)]
+            for t in range(3):
+                assert_spectra_close(got[t][u+'-'+v], want[t], rtol=RTOL, what='golden many %s-%s term %d' % (u, v, t),
+                                     zero_scale=np.max(np.abs(want)))
+            assert got[2][v+'-'+u] is got[2][u+'-'+v]
+
+
+def test_gram_config4_size_vs_oracle_subsets_and_streaming_path(halo):
+    """Config 4 at full size (64 HOD tracers, NFW, 256 k x 2048 M): every pair among 8-tracer subsets against the
+    ORACLE on the same subset (rtol 1e-10) and against the <=8-tracer streaming-quadrature path (1e-12); the run is
+    bitwise reproducible."""
     g = _synthetic_case(256, 2048, z=0.)
     rng = np.random.default_rng(4)
     hods = [syn.draw_hod(rng) for _ in range(64)]
     hmod = halo.model(g['z'], g['Om_m'], Dv=g['Dv'], dc=g['dc'])
+    om = orc.make_model(g['z'], g['Om_m'], Dv=g['Dv'], dc=g['dc'])
     profs = _tracers(halo, hmod, g, hods, False, False, True)
     got = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs)
     again = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], profs)
     for key in ('g0-g0', 'g3-g60', 'g63-g63', 'g17-g18'):
         for t in range(3):
             assert np.array_equal(got[t][key], again[t][key])
-    for subset in ([0, 1, 2, 3, 4, 5, 6, 7], [0, 9, 18, 27, 36, 45, 54, 63], [56, 57, 58, 59, 60, 61, 62, 63]):
+    oprofs_all = _tracers(orc, om, g, hods, False, False, True)
+    for subset in ([0, 9, 18, 27, 36, 45, 54, 63], [56, 57, 58, 59, 60, 61, 62, 63]):
+        names = ['g%d' % i for i in subset]
+        want = orc.power_spectrum(om, g['k'], g['Pk_lin'], g['M'], g['sigmaM'], {n: oprofs_all[n] for n in names})
+        for t in range(3):
+            for u in names:
+                for v in names:
+                    assert_spectra_close(got[t][u+'-'+v], want[t][u+'-'+v], rtol=RTOL, what='C4 oracle %s-%s term %d' % (u, v, t))
+    for subset in ([0, 1, 2, 3, 4, 5, 6, 7], [0, 9, 18, 27, 36, 45, 54, 63]):
         names = ['g%d' % i for i in subset]
         ref = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], {n: profs[n] for n in names})
         for t in range(3):

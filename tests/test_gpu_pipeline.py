@@ -45,3 +45,21 @@ def test_end_to_end_pipeline_vs_oracle():
                 for t in range(3):
                     assert_spectra_close(out[i*len(fams)+f, sp, t], want[t][key], rtol=1e-10,
                                          what='sample %d %s %s term %d' % (i, fam, key, t))
+
+
+def test_end_to_end_pipeline_full_shape_vs_oracle():
+    """Config 5 at its full grid (256 k x 1024 M, Tinker10): two MCMC samples through the device chain against the
+    oracle chain (sigma(R) on 1024 radii x 1e5 wavenumbers, NFW Si/Ci profiles, spectra)."""
+    from pyhalomodel_b200 import pipeline
+    nk, nM = 256, 1024
+    k, M = syn.k_grid(nk), syn.M_grid(nM)
+    samples = pipeline.draw_samples(2, seed=4321)
+    out, extras = pipeline.EndToEnd(k, M, chunk=2).run(samples, return_inputs=True)
+    out = out.cpu().numpy()
+    sig_dev = extras[0]['sigma'].cpu().numpy()
+    for i, s in enumerate(samples):
+        want, sig = _oracle_chain(s, k, M, orc.TINKER10)
+        np.testing.assert_allclose(sig_dev[i], sig, rtol=1e-12)
+        for sp, key in enumerate(['m-m', 'm-g', 'g-g']):
+            for t in range(3):
+                assert_spectra_close(out[i, sp, t], want[t][key], rtol=1e-10, what='C5 full sample %d %s term %d' % (i, key, t))

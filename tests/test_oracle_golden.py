@@ -31,6 +31,20 @@ def test_massfn_bias_and_low_mass_correction():
     np.testing.assert_allclose(orc.linear_bias_nu(hm, nu), g['b_Tinker2010_pbs'], rtol=TIGHT)
 
 
+def test_mass_function_golden():
+    """multiplicity_function / mass_function (pyhalomodel.py:286-315 with utility.derivative_from_samples) for the
+    five families at two redshifts: the oracle repeats the reference's scipy `lagrange` arithmetic bit for bit."""
+    g = load_golden('mass_function.npz')
+    M, Om_m = g['M'], float(g['Om_m'])
+    for z in g['zs']:
+        dc, Dv = g['dcDv_z%g' % z]
+        sig = g['sigmaM_z%g' % z]
+        for short, name in SHORT.items():
+            hm = orc.make_model(z, Om_m, name=name, Dv=Dv, dc=dc)
+            np.testing.assert_allclose(orc.multiplicity_function(hm, M, sig), g['F_%s_z%g' % (short, z)], rtol=TIGHT)
+            np.testing.assert_allclose(orc.mass_function(hm, M, sig), g['n_%s_z%g' % (short, z)], rtol=TIGHT)
+
+
 def test_windows_concentration_hod():
     g = load_golden('windows.npz')
     k, M, z, Om_m, Dv = g['k'], g['M'], float(g['z']), float(g['Om_m']), float(g['Dv'])

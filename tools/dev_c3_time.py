@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from pyhalomodel_b200 import workloads, synthetic as syn
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-fams = syn.FAMILY_NAMES if (len(sys.argv) <= 2 or sys.argv[2] == '5') else syn.FAMILY_NAMES[3:4]
+nf = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+fams = syn.FAMILY_NAMES if nf == 5 else (syn.FAMILY_NAMES[3:4] if nf == 1 else syn.FAMILY_NAMES[5-nf:])
 batch = workloads.build(G, 256, 1024, ('m', 'g'), fams)
 plan = batch.plan()
 plan.run(); torch.cuda.synchronize()
