@@ -203,6 +203,10 @@ typedef struct hm_gram_problem {
 size_t hm_gram_workspace(const hm_gram_problem* prob);
 int hm_gram_power_spectrum(const hm_gram_problem* prob, double* out_dev, double* lowmass_dev,
                            void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Same, launching only part of the pipeline (for timing the contraction alone): bit 0 = the weight kernels,
+ * bit 1 = the Gram (FP64 DMMA) kernel, bit 2 = the epilogue. */
+int hm_gram_power_spectrum_stages(const hm_gram_problem* prob, double* out_dev, double* lowmass_dev,
+                                  void* workspace_dev, size_t workspace_bytes, void* stream, int stages);
 
 /* ---- Fourier profiles ------------------------------------------------------------------------------------
  * Si(x), Ci(x) element-wise (scipy.special.sici as used at pyhalomodel.py:1033-1035,1044-1049). */
@@ -227,6 +231,11 @@ int hm_window_configuration(const double* k_dev, const double* rv_dev, const dou
  * kgrid_dev: [nkg]; Pk_dev: [G][nkg]; R_dev: [G][nR]; out_dev: [G][nR]. */
 int hm_sigma_tophat(const double* kgrid_dev, const double* Pk_dev, double dlnk, int32_t nkg,
                     const double* R_dev, int32_t nR, int32_t G, double* out_dev, void* stream);
+
+/* ---- measurement ------------------------------------------------------------------------------------------
+ * FP64 roofline denominators of the current device, in TFLOP/s (2 flops per FMA): DFMA issue throughput and DMMA
+ * (mma.sync m8n8k4 f64) throughput.  Host pointers; synchronises `stream`; allocates and frees a scratch buffer. */
+int hm_measure_fp64_peaks(double* dfma_tflops_host, double* dmma_tflops_host, void* stream);
 
 #ifdef __cplusplus
 }

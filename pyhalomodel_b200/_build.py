@@ -33,18 +33,20 @@ def is_stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ into one shared library; returns its path."""
-    if not force and not is_stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile every .cu under csrc/ into one shared library; returns its path.  `defines` / `out` build an
+    experimental variant beside the product library (kernel A/B runs on the GPU box: HALOB200_LIB selects it)."""
+    lib = out or LIB
+    if out is None and not force and not is_stale():
         return LIB
     objs = []
     procs = []
-    builddir = os.path.join(HERE, 'build')
+    builddir = os.path.join(HERE, 'build', os.path.basename(lib)[:-3] if out else '')
     os.makedirs(builddir, exist_ok=True)
     for src in sources():
         obj = os.path.join(builddir, os.path.basename(src)[:-3]+'.o')
         objs.append(obj)
-        cmd = [_nvcc()]+NVCC_FLAGS+['-c', src, '-o', obj]
+        cmd = [_nvcc()]+NVCC_FLAGS+['-D'+d for d in defines]+['-c', src, '-o', obj]
         if verbose:
             cmd.insert(1, '-Xptxas=-v')
             print(' '.join(cmd))
@@ -55,13 +57,15 @@ def build(force=False, verbose=False):
             raise RuntimeError('nvcc failed on %s:\n%s' % (src, out))
         if verbose and out:
             print(out)
-    link = [_nvcc(), '-shared', '-o', LIB]+objs+['-lcudart']
+    link = [_nvcc(), '-shared', '-o', lib]+objs+['-lcudart']
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n'+r.stdout)
-    return LIB
+    return lib
 
 
 if __name__ == '__main__':
     import sys
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith('-D')]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith('--out=')]
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, defines=defs, out=outs[0] if outs else None))

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, 'libhalob200.so')
+LIBPATH = os.environ.get('HALOB200_LIB') or os.path.join(HERE, 'libhalob200.so')    # (override: kernel A/B runs)
 HM_MAX_TRACERS = 8
 
 PS74, ST99, SMT01, TINKER10, DESPALI16, TINKER10_PBS = range(6)
@@ -79,6 +79,8 @@ _SIGNATURES = {
     'hm_gram_workspace': (C.c_size_t, [C.POINTER(GramProblem)]),
     'hm_gram_power_spectrum': (C.c_int, [C.POINTER(GramProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
                                          C.c_void_p]),
+    'hm_gram_power_spectrum_stages': (C.c_int, [C.POINTER(GramProblem), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                                C.c_void_p, C.c_int]),
     'hm_sici': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     'hm_window_nfw': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                 C.c_void_p]),
@@ -86,6 +88,7 @@ _SIGNATURES = {
                                        C.c_void_p]),
     'hm_window_configuration': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_void_p]),
+    'hm_measure_fp64_peaks': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]),
     'hm_sigma_tophat': (C.c_int, [C.c_void_p, C.c_void_p, C.c_double, C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                   C.c_void_p, C.c_void_p]),
 }

@@ -586,6 +586,12 @@ extern "C" size_t hm_gram_workspace(const hm_gram_problem* pr) {
 
 extern "C" int hm_gram_power_spectrum(const hm_gram_problem* pr, double* out_dev, double* lowmass_dev, void* ws,
                                       size_t ws_bytes, void* stream) {
+  return hm_gram_power_spectrum_stages(pr, out_dev, lowmass_dev, ws, ws_bytes, stream, 7);
+}
+
+// stages: bit 0 = the three weight kernels, bit 1 = the Gram (DMMA) kernel, bit 2 = the epilogue
+extern "C" int hm_gram_power_spectrum_stages(const hm_gram_problem* pr, double* out_dev, double* lowmass_dev, void* ws,
+                                             size_t ws_bytes, void* stream, int stages) {
   int rc = hm_check_device();
   if (rc) return rc;
   if ((rc = hm_gram_validate(pr))) return rc;
@@ -614,12 +620,14 @@ extern "C" int hm_gram_power_spectrum(const hm_gram_problem* pr, double* out_dev
     w.discrete[p] = on ? (signed char)(t->discrete_tracer != 0) : 0;
   }
   w.gw = wsd; w.scal = wsd + L.scal_offset; w.tscal = wsd + L.tscal_offset; w.lowmass = lowmass_dev;
-  hm_gram_weights_kernel<<<dim3(L.nchunks, (unsigned)L.B), 256, 0, st>>>(w);
-  HM_LAUNCH_CHECK();
-  hm_gram_tracer_kernel<<<dim3(L.nchunks, L.P, (unsigned)L.B), 256, 0, st>>>(w);
-  HM_LAUNCH_CHECK();
-  hm_gram_scalars_kernel<<<dim3(L.P, (unsigned)L.B), 256, 0, st>>>(w);
-  HM_LAUNCH_CHECK();
+  if (stages & 1) {
+    hm_gram_weights_kernel<<<dim3(L.nchunks, (unsigned)L.B), 256, 0, st>>>(w);
+    HM_LAUNCH_CHECK();
+    hm_gram_tracer_kernel<<<dim3(L.nchunks, L.P, (unsigned)L.B), 256, 0, st>>>(w);
+    HM_LAUNCH_CHECK();
+    hm_gram_scalars_kernel<<<dim3(L.P, (unsigned)L.B), 256, 0, st>>>(w);
+    HM_LAUNCH_CHECK();
+  }
 
   hm_gram_args g;
   g.nk = pr->nk; g.nM = pr->nM; g.nMp = L.nMp; g.P = L.P; g.NB = L.NB; g.PT = L.PT; g.NW = L.NW;
@@ -638,10 +646,13 @@ extern "C" int hm_gram_power_spectrum(const hm_gram_problem* pr, double* out_dev
   g.nitems = (long long)L.B * L.ntiles * L.nparts;
   HM_REQUIRE(g.nitems < (1LL << 31), "too many work items for one launch");
   const long long grid = g.nitems < hm_num_sms() ? g.nitems : hm_num_sms();
-  if (NBT == 2) hm_gram_kernel<2, 2><<<(unsigned)grid, HM_GTHREADS, smem, st>>>(g);
-  else if (NBT == 4) hm_gram_kernel<2, 4><<<(unsigned)grid, HM_GTHREADS, smem, st>>>(g);
-  else hm_gram_kernel<2, 8><<<(unsigned)grid, HM_GTHREADS, smem, st>>>(g);
-  HM_LAUNCH_CHECK();
+  if (stages & 2) {
+    if (NBT == 2) hm_gram_kernel<2, 2><<<(unsigned)grid, HM_GTHREADS, smem, st>>>(g);
+    else if (NBT == 4) hm_gram_kernel<2, 4><<<(unsigned)grid, HM_GTHREADS, smem, st>>>(g);
+    else hm_gram_kernel<2, 8><<<(unsigned)grid, HM_GTHREADS, smem, st>>>(g);
+    HM_LAUNCH_CHECK();
+  }
+  if (!(stages & 4)) return HM_OK;
 
   hm_gram_eargs e;
   e.nk = pr->nk; e.nM = pr->nM; e.nMp = L.nMp; e.P = L.P; e.S = L.S; e.NW = L.NW; e.F = pr->models_per_sample;

@@ -128,47 +128,58 @@ struct hm_weights_args {
 };
 
 // grid (nchunks + 1, G): CTA (chunk, s) builds the weight vectors of 256 masses for ALL F models of sample s -- the
-// loads of sigma, M, amplitudes and variances and (when the models share delta_c) the three divisions behind nu are
-// shared by the F mass functions -- and CTA (nchunks, s) integrates the low-mass correction A of each model
+// loads of sigma, M, amplitudes and variances, the three divisions behind nu and ln(nu) are shared by the F mass
+// functions (hm_gb_nu_shared) -- and CTA (nchunks, s) integrates the low-mass correction A of each model
 // (pyhalomodel.py:413-414) and owns everything that needs it: e_p[0] with the A W(k,M0)/M0 term, the scalars, A.
 // RED: also reduce the shot-noise and simple-two-halo integrals (:423-426, :442-446); only non-default flags read
 // them (hm_epilogue_kernel), so the default path skips the 16 block reductions per model altogether.
-template <bool RED>
-__global__ void __launch_bounds__(HM_WCHUNK) hm_weights_kernel(const hm_weights_args a) {
-  constexpr int NRED = 2 * HM_MAXP;                     // shot noise [8], simple two-halo [8]
-  __shared__ double sred[HM_WCHUNK / 32][NRED];
-  __shared__ double sA[HM_WCHUNK / 32];
+// PT: compile-time bound on the number of tracers (2, 4 or 8).  The kernel is bound by the latency of its FP64
+// chains (exp, log, division), so what counts is resident warps: PT = 2 fits 64 registers, 32 warps per SM.
+template <int PT>
+struct hm_fam_consts { hm_model_desc d; hm_family_consts c; double rnorm[PT]; };
+
+template <bool RED, int PT>
+#ifndef HM_WMINB
+#define HM_WMINB 4
+#endif
+__global__ void __launch_bounds__(HM_WCHUNK, (PT <= 2) ? HM_WMINB : (PT <= 4 ? 3 : 2)) hm_weights_kernel(const hm_weights_args a) {
+  constexpr int NRED = 2 * PT;                          // shot noise [PT], simple two-halo [PT]
+  constexpr int FG = 8;                                 // models per group (shared constants, low-mass nodes)
+  __shared__ double sred[RED ? HM_WCHUNK / 32 : 1][RED ? NRED : 1];
+  __shared__ hm_fam_consts<PT> sfc[FG];
   const int s = blockIdx.y, chunk = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* sig = a.sigma + (size_t)s * a.nM;
   const double M0 = a.M[0];
 
   if (chunk == a.nchunks) {
-    // ---- low-mass CTA: A = 1 - int g b dnu from nu[0] by composite Gauss-Legendre, one node per thread, summed
-    // in a fixed order (warp butterflies, then the warps in order) ----
-    for (int f = 0; f < a.F; ++f) {
+    // ---- low-mass CTA: A = 1 - int g b dnu from nu[0] by composite Gauss-Legendre.  Warp w integrates model w, w + 8,
+    // ...: a lane evaluates five of the 160 nodes (independent chains), the warp adds them in a fixed order, and lane 0
+    // finishes the model's column m = 0. ----
+    const double sg0 = sig[0], sg1 = sig[1];
+    for (int f = warp; f < a.F; f += HM_WCHUNK / 32) {
       const int b = s * a.F + f;
       const hm_model_desc d = a.models ? a.models[b] : a.single;
-      const double part = hm_warp_sum(hm_lowmass_node(d, d.dc / sig[0], tid));
-      __syncthreads();                                  // sA is free again
-      if (lane == 0) sA[warp] = part;
-      __syncthreads();
-      if (tid == 0) {
-        double tot = 0.;
-#pragma unroll
-        for (int w = 0; w < HM_WCHUNK / 32; ++w) tot += sA[w];
-        const double A = 1. - tot;
+      const double nu = d.dc / sg0;
+      double part = 0.;
+#pragma unroll 1
+      for (int j = 0; j < HM_GL_NODES / 32; ++j) part += hm_lowmass_node(d, nu, lane + 32 * j);
+      const double A = 1. - hm_warp_sum(part);
+      if (lane == 0) {
         const double Aterm = A / M0;                    // multiplies W(k, M[0]) for mass tracers (:541-542)
-        const double nu = d.dc / sig[0], nu_hi = d.dc / sig[1];
+        const double nu_hi = d.dc / sg1;
         const double tw = 0.5 * (nu_hi - nu);
-        const double w2_plain = tw * (hm_b_nu(d, nu) * hm_g_nu(d, nu) / M0);
+        const hm_family_consts c = hm_make_family_consts(d);
+        double g, bg;
+        hm_gb_nu_shared(d, c, nu, log(nu), g, bg);      // the same arithmetic as the other masses' weights
+        const double w2_plain = tw * (bg * (1. / M0));
         double* wout = a.weights + (size_t)b * a.NW * a.nMp;
         double* sc = a.scal + (size_t)b * HM_NSCAL;
         double* cp = a.cpart + ((size_t)b * (a.nchunks + 1) + a.nchunks) * 2 * HM_MAXP;
         for (int p = 0; p < HM_MAXP; ++p) {
           double cW = 0., low = 0.;
           if (p < a.P) {
-            const double an = a.amplitude[p][(size_t)s * a.amp_stride[p]] / a.norm[p][b];
+            const double an = a.amplitude[p][(size_t)s * a.amp_stride[p]] * (1. / a.norm[p][b]);
             cW = (a.mode[p] == HM_GRID_UK) ? an : 1.;
             wout[(size_t)p * a.nMp] = a.mass[p] ? (w2_plain + Aterm) * cW : w2_plain * cW;   // e_p[0]
             if (a.mass[p]) low = Aterm * an;
@@ -185,25 +196,20 @@ __global__ void __launch_bounds__(HM_WCHUNK) hm_weights_kernel(const hm_weights_
     return;
   }
 
-  // per-model constants of a group of up to 8 models: parameter logarithms and reciprocal normalisations, computed
-  // once per CTA instead of once per thread
-  struct fam_consts { hm_family_consts c; double rnorm[HM_MAXP]; };
-  __shared__ fam_consts sfc[8];
-
   const int m = chunk * HM_WCHUNK + tid;
   const bool live = m < a.nM;
   const bool pad = !live && m < a.nMp;                  // padding column: zero weights
   double sg = 1., sg_hi = 1., sg_lo = 1., rM = 1.;
-  double amp[HM_MAXP], var[HM_MAXP];
+  double amp[PT], var[PT];
 #pragma unroll
-  for (int p = 0; p < HM_MAXP; ++p) amp[p] = var[p] = 0.;
+  for (int p = 0; p < PT; ++p) amp[p] = var[p] = 0.;
   if (live) {
     sg = sig[m];
     sg_hi = (m + 1 < a.nM) ? sig[m + 1] : sg;
     sg_lo = (m > 0) ? sig[m - 1] : sg;
     rM = 1. / a.M[m];
 #pragma unroll
-    for (int p = 0; p < HM_MAXP; ++p)
+    for (int p = 0; p < PT; ++p)
       if (p < a.P) {
         amp[p] = a.amplitude[p][(size_t)s * a.amp_stride[p] + m];
         if (a.variance[p]) var[p] = a.variance[p][(size_t)s * a.nM + m];
@@ -213,39 +219,44 @@ __global__ void __launch_bounds__(HM_WCHUNK) hm_weights_kernel(const hm_weights_
 #pragma unroll 1
   for (int f = 0; f < a.F; ++f) {
     const int b = s * a.F + f;
-    const hm_model_desc d = a.models ? a.models[b] : a.single;
-    if ((f & 7) == 0) {
+    if ((f & (FG - 1)) == 0) {
+      // per-model constants of the next group of models: parameter logarithms and reciprocal normalisations,
+      // computed once per CTA instead of once per thread
       __syncthreads();                                  // the previous group is done with sfc
-      if (tid < 8 && f + tid < a.F) {
+      if (tid < FG && f + tid < a.F) {
         const hm_model_desc dm = a.models ? a.models[b + tid] : a.single;
+        sfc[tid].d = dm;
         sfc[tid].c = hm_make_family_consts(dm);
-        for (int p = 0; p < HM_MAXP; ++p) sfc[tid].rnorm[p] = (p < a.P) ? 1. / a.norm[p][b + tid] : 0.;
+#pragma unroll
+        for (int p = 0; p < PT; ++p) sfc[tid].rnorm[p] = (p < a.P) ? 1. / a.norm[p][b + tid] : 0.;
       }
       __syncthreads();
     }
-    const fam_consts& fc = sfc[f & 7];
+    const hm_fam_consts<PT>& fc = sfc[f & (FG - 1)];
     double* wout = a.weights + (size_t)b * a.NW * a.nMp;
-    double red[NRED];
+    double red[RED ? NRED : 1];
 #pragma unroll
-    for (int i = 0; i < NRED; ++i) red[i] = 0.;
+    for (int i = 0; i < (RED ? NRED : 1); ++i) red[i] = 0.;
     if (pad) {
       for (int i = 0; i < a.NW; ++i) wout[(size_t)i * a.nMp + m] = 0.;
     } else if (live) {
-      if (f == 0 || d.dc != dc_prev) {                  // models of one sample usually share delta_c
-        nu = d.dc / sg;
-        const double nu_hi = (m + 1 < a.nM) ? d.dc / sg_hi : nu;
-        const double nu_lo = (m > 0) ? d.dc / sg_lo : nu;
+      const hm_model_desc& d = fc.d;
+      const double dc = d.dc;
+      if (f == 0 || dc != dc_prev) {                    // models of one sample usually share delta_c
+        nu = dc / sg;
+        const double nu_hi = (m + 1 < a.nM) ? dc / sg_hi : nu;
+        const double nu_lo = (m > 0) ? dc / sg_lo : nu;
         tw = 0.5 * (nu_hi - nu_lo);                     // trapezoid rule in nu as a weight (scipy trapezoid, :27)
         lnnu = log(nu);
-        dc_prev = d.dc;
+        dc_prev = dc;
       }
       double g, bg;
       hm_gb_nu_shared(d, fc.c, nu, lnnu, g, bg);
       const double w1 = tw * (g * rM);                  // one-halo weight  (:530)
       const double w2_plain = tw * (bg * rM);           // two-halo weight  (:539)
-      double cW[HM_MAXP];
+      double cW[PT];
 #pragma unroll
-      for (int p = 0; p < HM_MAXP; ++p) {
+      for (int p = 0; p < PT; ++p) {
         cW[p] = 0.;
         if (p < a.P) {
           const double rnorm = fc.rnorm[p];
@@ -262,22 +273,22 @@ __global__ void __launch_bounds__(HM_WCHUNK) hm_weights_kernel(const hm_weights_
           wout[(size_t)(a.P + p) * a.nMp + m] = __dmul_rn(__dmul_rn(w1, fac), uS * uS);     // d_p
           if (RED) {
             red[p] = w1 * (an * rnorm);                                                    // shot noise integrand (:425)
-            red[HM_MAXP + p] = w2_plain * an;                                              // simple two-halo (:442-446)
+            red[PT + p] = w2_plain * an;                                                   // simple two-halo (:442-446)
           }
         }
       }
       int idx = 2 * a.P;
 #pragma unroll
-      for (int u = 0; u < HM_MAXP; ++u)
+      for (int u = 0; u < PT; ++u)
 #pragma unroll
-        for (int v = u + 1; v < HM_MAXP; ++v)
+        for (int v = u + 1; v < PT; ++v)
           if (v < a.P) wout[(size_t)(idx++) * a.nMp + m] = w1 * cW[u] * cW[v];                     // q_uv
     }
     if (RED) {
-      // one reduction phase for the 16 sums: warp butterflies, then a fixed-order sum over the 8 warps
+      // one reduction phase for the 2 PT sums: warp butterflies, then a fixed-order sum over the 8 warps
 #pragma unroll
       for (int i = 0; i < NRED; ++i) {
-        const bool used = (i & (HM_MAXP - 1)) < a.P;    // the others are zero
+        const bool used = (i % PT) < a.P;               // the others are zero
         const double t = used ? hm_warp_sum(red[i]) : 0.;
         if (lane == 0) sred[warp][i] = t;
       }
@@ -286,9 +297,9 @@ __global__ void __launch_bounds__(HM_WCHUNK) hm_weights_kernel(const hm_weights_
         double t = 0.;
 #pragma unroll
         for (int w = 0; w < HM_WCHUNK / 32; ++w) t += sred[w][tid];
-        const int p = tid & (HM_MAXP - 1);
+        const int p = tid % PT, kind = tid / PT;        // kind 0: shot noise, 1: simple two-halo
         double* cp = a.cpart + ((size_t)b * (a.nchunks + 1) + chunk) * 2 * HM_MAXP;
-        cp[tid] = (tid >= HM_MAXP || (p < a.P && a.discrete[p])) ? t : 0.;
+        cp[kind * HM_MAXP + p] = (kind == 1 || (p < a.P && a.discrete[p])) ? t : 0.;
       }
       __syncthreads();
     }
@@ -1145,8 +1156,17 @@ extern "C" int hm_halo_weights(const hm_problem* pr, double* lowmass_dev, void* 
   a.cpart = (double*)ws + L.cpart_offset;
   a.lowmass = lowmass_dev;
   dim3 grid(L.nchunks + 1, (unsigned)pr->n_samples);
-  if (hm_needs_cpart(pr)) hm_weights_kernel<true><<<grid, HM_WCHUNK, 0, (cudaStream_t)stream>>>(a);
-  else hm_weights_kernel<false><<<grid, HM_WCHUNK, 0, (cudaStream_t)stream>>>(a);
+  const bool red = hm_needs_cpart(pr);
+  cudaStream_t st = (cudaStream_t)stream;
+#define HM_WLAUNCH(PT)                                                        \
+  do {                                                                        \
+    if (red) hm_weights_kernel<true, PT><<<grid, HM_WCHUNK, 0, st>>>(a);      \
+    else hm_weights_kernel<false, PT><<<grid, HM_WCHUNK, 0, st>>>(a);         \
+  } while (0)
+  if (L.P <= 2) HM_WLAUNCH(2);
+  else if (L.P <= 4) HM_WLAUNCH(4);
+  else HM_WLAUNCH(8);
+#undef HM_WLAUNCH
   HM_LAUNCH_CHECK();
   return HM_OK;
 }

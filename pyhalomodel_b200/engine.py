@@ -83,9 +83,15 @@ def _ptr(t):
 
 
 def pack_models(descs):
-    """list of ModelDesc -> uint8 CUDA tensor holding the packed hm_model_desc array."""
-    arr = (ModelDesc*len(descs))(*descs)
-    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    """list of ModelDesc, or numpy record array of hm_model_desc (halomodel.model_descriptors) -> uint8 CUDA tensor
+    holding the packed hm_model_desc array."""
+    if isinstance(descs, np.ndarray):
+        if descs.dtype.itemsize != C.sizeof(ModelDesc):
+            raise ValueError('record array does not have the layout of hm_model_desc')
+        host = torch.from_numpy(np.ascontiguousarray(descs).view(np.uint8).reshape(-1))
+    else:
+        arr = (ModelDesc*len(descs))(*descs)
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
     return host.to(device())
 
 
@@ -117,14 +123,23 @@ def average(desc: ModelDesc, M, sigma, funcs):
     return out
 
 
-def average_batch(models_dev, M, sigma, funcs, models_per_sample=1):
+def average_batch(models_dev, M, sigma, funcs, models_per_sample=1, out=None):
     """sigma, funcs: [G, nM]; models_dev: packed descriptors of the G*F models -> [G*F] halo averages."""
     M, sigma, funcs = to_dev(M), to_dev(sigma), to_dev(funcs)
     G, nM = sigma.shape
-    out = torch.empty(G*models_per_sample, dtype=F64, device=M.device)
+    if out is None:
+        out = torch.empty(G*models_per_sample, dtype=F64, device=M.device)
     check(lib().hm_average_batch(_ptr(models_dev), _ptr(M), _ptr(sigma), nM, G, models_per_sample, _ptr(funcs),
                                  _ptr(out), _stream()))
     return out
+
+
+def fp64_peaks():
+    """(DFMA, DMMA) TFLOP/s of the current device, measured now (roofline denominators of the FP64-bound kernels)."""
+    device()
+    f, m = C.c_double(0.), C.c_double(0.)
+    check(lib().hm_measure_fp64_peaks(C.byref(f), C.byref(m), _stream()))
+    return f.value, m.value
 
 
 def multiplicity_function(desc: ModelDesc, M, sigma, want_n=False):
@@ -188,21 +203,23 @@ def sici(x):
     return si, ci
 
 
-def window_nfw(k, rv, c):
+def window_nfw(k, rv, c, out=None):
     """k [nk]; rv, c [nM] or [G, nM]  ->  U [nk, nM] or [G, nk, nM] (pyhalomodel.py:1040-1055)."""
     k, rv, c = to_dev(k), to_dev(rv), to_dev(c)
     batched = rv.dim() == 2
     G, nM = (rv.shape if batched else (1, rv.shape[0]))
-    out = torch.empty((G, k.shape[0], nM), dtype=F64, device=k.device)
+    if out is None:
+        out = torch.empty((G, k.shape[0], nM), dtype=F64, device=k.device)
     check(lib().hm_window_nfw(_ptr(k), _ptr(rv), _ptr(c), k.shape[0], nM, G, _ptr(out), _stream()))
     return out if batched else out[0]
 
 
-def window_isothermal(k, rv):
+def window_isothermal(k, rv, out=None):
     k, rv = to_dev(k), to_dev(rv)
     batched = rv.dim() == 2
     G, nM = (rv.shape if batched else (1, rv.shape[0]))
-    out = torch.empty((G, k.shape[0], nM), dtype=F64, device=k.device)
+    if out is None:
+        out = torch.empty((G, k.shape[0], nM), dtype=F64, device=k.device)
     check(lib().hm_window_isothermal(_ptr(k), _ptr(rv), k.shape[0], nM, G, _ptr(out), _stream()))
     return out if batched else out[0]
 
@@ -381,8 +398,10 @@ class PowerSpectrumPlan:
 class PipelinedPlans:
     """Software pipelining of consecutive steps of a sweep: two plans (double-buffered workspaces and outputs)
     alternate between two CUDA streams, so the small weights and epilogue kernels of one step run beside the
-    persistent streaming kernel of the neighbouring step (their CTAs fit in the registers and the ~9 KB of shared
-    memory the streaming CTAs leave free on every SM).  submit() enqueues one step; drain() joins the streams."""
+    persistent streaming kernel of the neighbouring step (their CTAs fit in the registers and the shared memory the
+    streaming CTAs leave free on every SM).  submit() enqueues one step; drain() joins the streams.  Every submit
+    orders its step behind whatever the caller has enqueued on the current stream so far (refreshed inputs, a
+    consumer of the previous result); the object drains itself when it is dropped or leaves a `with` block."""
 
     def __init__(self, make_plan):
         self.plans = [make_plan(), make_plan()]
@@ -394,11 +413,9 @@ class PipelinedPlans:
         """Enqueue one step; `then(out, lowmass)`, if given, is called with the step's stream current (e.g. to
         enqueue a copy of the spectra behind the epilogue kernel)."""
         main = torch.cuda.current_stream()
-        if not self.forked:
-            for st in self.streams:
-                st.wait_stream(main)
-            self.forked = True
         i = self.n & 1
+        self.streams[i].wait_stream(main)
+        self.forked = True
         with torch.cuda.stream(self.streams[i]):
             res = self.plans[i].run(out=out, peer=peer)
             if then is not None:
@@ -407,10 +424,25 @@ class PipelinedPlans:
         return res
 
     def drain(self):
+        if not self.forked:
+            return
         main = torch.cuda.current_stream()
         for st in self.streams:
             main.wait_stream(st)
         self.forked = False
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.drain()
+        return False
+
+    def __del__(self):
+        try:        # the plans' buffers were allocated on the caller's stream: join before the allocator recycles them
+            self.drain()
+        except Exception:
+            pass
 
 
 class GramPlan:
@@ -486,6 +518,11 @@ class GramPlan:
         check(lib().hm_gram_power_spectrum(C.byref(self.problem), _ptr(self.out), _ptr(self.lowmass),
                                            _ptr(self.workspace), self.workspace_bytes, _stream()))
         return self.out, self.lowmass
+
+    def gram_only(self):
+        """The Gram (DMMA) kernel alone, on the weights of the last run() (for timing the contraction)."""
+        check(lib().hm_gram_power_spectrum_stages(C.byref(self.problem), _ptr(self.out), _ptr(self.lowmass),
+                                                  _ptr(self.workspace), self.workspace_bytes, _stream(), 2))
 
     def algorithmic_bytes(self):
         """Every grid once, four per-(tracer, mass) vectors once per model, three output vectors per pair."""

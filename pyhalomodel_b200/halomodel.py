@@ -29,7 +29,7 @@ dc_rel_tol = 1e-3
 Dv_rel_tol = 1e-3
 Tinker_z_dep = False    # redshift-dependent Tinker et al. (2010) parameters (pyhalomodel.py:20, :163-167)
 Tinker_PBS = False      # peak-background-split bias for Tinker et al. (2010) (pyhalomodel.py:22, :264-271)
-halo_integration = 'trapezoid'    # the only mass integrator with a parity oracle (pyhalomodel.py:27)
+halo_integration = 'trapezoid'    # mass integrator (pyhalomodel.py:27): the trapezoid rule is the one built on the device
 # W(k) integration scheme in r for configuration-space profiles (pyhalomodel.py:30-39).  The reference's default,
 # adaptive scipy quad with epsrel=1e-3, cannot be reproduced bit for bit (and its code path is broken under
 # scipy >= 1.14); the three sample-based schemes it offers are: 'trapezoid', 'simps', 'romb'.
@@ -63,8 +63,25 @@ def _lin_interp_extrap(x, xs, ys):
     return ((x-xs[lo])/(xs[hi]-xs[lo]))*ys[hi]+((xs[hi]-x)/(xs[hi]-xs[lo]))*ys[lo]
 
 
+def _check_halo_integration():
+    """The reference binds `halo_integration` to a scipy.integrate function and reads it at call time
+    (pyhalomodel.py:27, :359, :531, :540); only the trapezoid rule exists on the device, anything else is refused."""
+    hi = halo_integration
+    if hi == 'trapezoid' or getattr(hi, '__name__', None) in ('trapezoid', 'trapz'):
+        return
+    raise NotImplementedError("halo_integration: only the trapezoid rule is implemented on the B200 path")
+
+
 def _wants_device(*arrays):
     return any(isinstance(a, torch.Tensor) and a.is_cuda for a in arrays)
+
+
+def _own(x):
+    """Device copy of a profile input that the profile object owns (the reference copies every array it is given,
+    pyhalomodel.py:814-818).  Host arrays are uploaded -- the upload IS the copy; only a caller-owned CUDA tensor
+    needs a second buffer."""
+    t = engine.to_dev(x)
+    return t.clone() if (isinstance(x, torch.Tensor) and x.is_cuda and t.data_ptr() == x.data_ptr()) else t
 
 
 def _give_back(t, on_device):
@@ -215,7 +232,10 @@ class model():
         Mh = engine.to_host(M) if isinstance(M, torch.Tensor) else np.asarray(M)
         if not util.is_array_monotonic(Mh):
             raise ValueError('Halo mass array must be increasing monotonically')
+        _check_halo_integration()
         out = engine.average(self.descriptor(), M, sigmaM, func)
+        if np.ndim(func) > 1:       # func [nf, nM] broadcasts in the reference and gives one average per row
+            return out if _wants_device(M, sigmaM, func) else engine.to_host(out)
         return out[0] if _wants_device(M, sigmaM, func) else float(out[0].item())
 
     def cross_halo_spectrum(self, k, Pk_lin, M, sigmaM, profiles: dict, M_halo: float, beta=None, simple_twohalo=False,
@@ -227,6 +247,47 @@ class model():
         '''
         return _cross_halo_spectrum(self, k, Pk_lin, M, sigmaM, profiles, M_halo, beta=beta,
                                     simple_twohalo=simple_twohalo, k_trunc=k_trunc, verbose=verbose)
+
+    def _many_tracer_spectra(self, k, Pk_lin, M, sigmaM, tracers, beta, flags, on_dev):
+        """More than 8 profiles.  The Gram path (FP64 DMMA, up to 64 single-grid Fourier profiles, even nM, 16-byte
+        aligned grids, no beta) when its preconditions hold; otherwise -- profile(k, M, Uk, Wk) objects with separate
+        grids, odd nM, beta_NL, more than 64 profiles -- the quadrature path on unions of two blocks of tracers, so that
+        every pair the reference computes (pyhalomodel.py:433-507) is still produced.  Returns ([S, 3, nk], A)."""
+        P, nM = len(tracers), np.shape(M)[0]
+        gram_ok = (beta is None and P <= _lib.HM_GRAM_MAX_TRACERS and nM % 2 == 0
+                   and all(t.mode in (_lib.GRID_UK, _lib.GRID_WK) and t.grid.data_ptr() % 16 == 0 for t in tracers))
+        if gram_ok:
+            out, lowmass = engine.GramPlan(k, Pk_lin, M, sigmaM, tracers, [self.descriptor()], **flags).run()
+            if on_dev:
+                return out[0], float(lowmass[0].item())
+            packed = torch.cat([out.reshape(-1), lowmass]).cpu().numpy()
+            return packed[:-1].reshape(P*(P+1)//2, 3, -1), float(packed[-1])
+        blk = (6 if beta is not None else _lib.HM_MAX_TRACERS)//2
+        blocks = [list(range(i, min(i+blk, P))) for i in range(0, P, blk)]
+        pair_index = {}
+        s = 0
+        for u in range(P):
+            for v in range(u, P):
+                pair_index[(u, v)] = s
+                s += 1
+        res, A = None, 0.
+        for bi, rows in enumerate(blocks):
+            for cols in blocks[bi:]:
+                if rows is cols and len(blocks) > 1:
+                    continue            # the pairs inside a block come with its unions with the other blocks
+                ids = rows if rows is cols else rows+cols
+                plan = engine.PowerSpectrumPlan(k, Pk_lin, M, sigmaM, [tracers[i] for i in ids], [self.descriptor()],
+                                                beta=beta, do_I11=do_I11, do_I12_I21=do_I12_I21, **flags)
+                out, lowmass = plan.run()
+                if res is None:
+                    res = torch.empty((s, 3, plan.nk), dtype=torch.float64, device=out.device)
+                    A = float(lowmass[0].item())
+                t = 0
+                for a_ in range(len(ids)):
+                    for b_ in range(a_, len(ids)):
+                        res[pair_index[(ids[a_], ids[b_])]] = out[0, t]
+                        t += 1
+        return (res if on_dev else res.cpu().numpy()), A
 
     # -- the hot path ---------------------------------------------------------------------------------------
     def power_spectrum(self, k, Pk_lin, M, sigmaM, profiles: dict, beta=None, simple_twohalo=False,
@@ -256,21 +317,18 @@ class model():
         tracers = [prof._tracer() for prof in profiles.values()]
         flags = dict(simple_twohalo=simple_twohalo, subtract_shotnoise=subtract_shotnoise,
                      correct_discrete=correct_discrete, k_trunc=k_trunc)
+        _check_halo_integration()
         if len(names) > _lib.HM_MAX_TRACERS:    # many tracers: Gram contraction on the FP64 tensor cores
-            if len(names) > _lib.HM_GRAM_MAX_TRACERS:
-                raise NotImplementedError('more than %d tracers per call' % _lib.HM_GRAM_MAX_TRACERS)
-            if beta is not None:
-                raise NotImplementedError('beta_NL with more than %d tracers per call' % _lib.HM_MAX_TRACERS)
-            plan = engine.GramPlan(k, Pk_lin, M, sigmaM, tracers, [self.descriptor()], **flags)
+            res, A = self._many_tracer_spectra(k, Pk_lin, M, sigmaM, tracers, beta, flags, on_dev)
         else:
             plan = engine.PowerSpectrumPlan(k, Pk_lin, M, sigmaM, tracers, [self.descriptor()], beta=beta,
                                             do_I11=do_I11, do_I12_I21=do_I12_I21, **flags)
-        out, lowmass = plan.run()
-        if on_dev:
-            res, A = out[0], float(lowmass[0].item())
-        else:   # one device->host copy for everything the caller sees
-            packed = torch.cat([out.reshape(-1), lowmass]).cpu().numpy()
-            res, A = packed[:-1].reshape(plan.S, 3, plan.nk), float(packed[-1])
+            out, lowmass = plan.run()
+            if on_dev:
+                res, A = out[0], float(lowmass[0].item())
+            else:   # one device->host copy for everything the caller sees
+                packed = torch.cat([out.reshape(-1), lowmass]).cpu().numpy()
+                res, A = packed[:-1].reshape(plan.S, 3, plan.nk), float(packed[-1])
         if verbose:
             sig = engine.to_host(engine.to_dev(sigmaM))
             print('Redshift:', self.z)
@@ -299,6 +357,58 @@ class model():
         if verbose:
             print('Halomodel calculation time [s]:', time()-t_start, '\n')
         return ordered
+
+
+MODEL_DESC_DTYPE = np.dtype([('family', '<i4'), ('reserved', '<i4'), ('dc', '<f8'), ('rhom', '<f8'), ('par', '<f8', (12,))])
+
+
+def model_descriptors(z, Om_m, names, Dv, dc):
+    """The hm_model_desc records of len(z) x len(names) models, sample-major, built with array arithmetic: the same
+    expressions as model.__init__ / model.descriptor() element by element (pyhalomodel.py:73-184), so every record is
+    bit-identical to model(z[i], Om_m[i], name=names[f], Dv=Dv[i], dc=dc[i]).descriptor().  For sweeps, where building
+    the models one Python object at a time would cost more than the kernels.  Module switches (Tinker_z_dep,
+    Tinker_PBS) are read now, as the reference does."""
+    z, Om_m, Dv, dc = (np.atleast_1d(np.asarray(x, dtype=float)) for x in (z, Om_m, Dv, dc))
+    G, F = len(z), len(names)
+    out = np.zeros((G, F), dtype=MODEL_DESC_DTYPE)
+    rhom = cosmology.comoving_matter_density(Om_m)
+    for f, name in enumerate(names):
+        if name not in _FAMILY:
+            raise ValueError('Halo model not recognised')
+        rec = out[:, f]
+        rec['family'], rec['dc'], rec['rhom'] = _FAMILY[name], dc, rhom
+        par = np.zeros((G, 12))
+        if name in ('Sheth & Tormen (1999)', 'Sheth, Mo & Tormen (2001)'):
+            from scipy.special import gamma as Gamma
+            p_ST, q_ST = 0.3, 0.707
+            par[:, 0], par[:, 1], par[:, 2] = np.sqrt(2.*q_ST)/(np.sqrt(np.pi)+Gamma(0.5-p_ST)/2**p_ST), q_ST, p_ST
+            if name == 'Sheth, Mo & Tormen (2001)':
+                par[:, 3], par[:, 4], par[:, 5] = 0.707, 0.5, 0.6
+        elif name == 'Despali et al. (2016)':
+            p_ST, q_ST = 0.2536, 0.7689
+            par[:, 0], par[:, 1], par[:, 2] = 0.3295*np.sqrt(2.*q_ST/np.pi), q_ST, p_ST
+        elif name == 'Tinker et al. (2010)':
+            lnDv, lnDv_tab = np.log(Dv), np.log(_TINKER_DV)
+            hi = np.clip(np.searchsorted(lnDv_tab, lnDv), 1, len(lnDv_tab)-1)
+            lo = hi-1
+            tp = {}
+            for key, tab in _TINKER_TABLE4.items():
+                ys = np.asarray(tab, dtype=float)
+                tp[key] = ((lnDv-lnDv_tab[lo])/(lnDv_tab[hi]-lnDv_tab[lo]))*ys[hi] \
+                    + ((lnDv_tab[hi]-lnDv)/(lnDv_tab[hi]-lnDv_tab[lo]))*ys[lo]
+            if Tinker_z_dep:    # scalar pow per sample: numpy's array pow may differ from libm's in the last bit
+                for key, ex in (('beta', 0.20), ('gamma', -0.01), ('phi', -0.08), ('eta', 0.27)):
+                    tp[key] = tp[key]*np.array([(1.+zi)**ex for zi in z])
+            y = np.log10(Dv)
+            e = np.exp(-(4./y)**4)
+            cols = (tp['alpha'], tp['beta'], tp['gamma'], tp['phi'], tp['eta'], 1.+0.24*y*e, 0.44*y-0.88,
+                    np.full(G, 0.183), np.full(G, 1.5), 0.019+0.107*y+0.19*e, np.full(G, 2.4))
+            for i, col in enumerate(cols):
+                par[:, i] = col
+            if Tinker_PBS:
+                rec['family'] = _lib.TINKER10_PBS
+        rec['par'] = par
+    return out.reshape(G*F)
 
 
 def _cubic_interp_weights(x, x0):
@@ -378,16 +488,16 @@ class profile():
         self._init_common(k, M, amplitude, normalisation, variance, mass_tracer, discrete_tracer,
                           _wants_device(Uk, Wk))
         self._mode = _lib.GRID_SEPARATE
-        self._grid = engine.to_dev(Uk).clone()
-        self._wk = engine.to_dev(Wk).clone()
+        self._grid = _own(Uk)
+        self._wk = _own(Wk)
 
     def _init_common(self, k, M, amplitude, normalisation, variance, mass_tracer, discrete_tracer, on_dev):
         self.k = np.array(engine.to_host(k) if isinstance(k, torch.Tensor) else k, dtype=float)
         self.M = np.array(engine.to_host(M) if isinstance(M, torch.Tensor) else M, dtype=float)
         self._on_dev = on_dev
-        self._amplitude = engine.to_dev(amplitude).clone() if amplitude is not None else None
+        self._amplitude = _own(amplitude) if amplitude is not None else None
         self.normalisation = normalisation
-        self._variance = engine.to_dev(variance).clone() if variance is not None else None
+        self._variance = _own(variance) if variance is not None else None
         self.mass_tracer, self.discrete_tracer = mass_tracer, discrete_tracer
         self._wk = None
 
@@ -402,7 +512,7 @@ class profile():
         if tuple(Uk.shape) != (k.shape[0], M.shape[0]):
             raise ValueError('k, M, array shapes do not match')
         self = cls.__new__(cls)
-        grid = engine.to_dev(Uk).clone()
+        grid = _own(Uk)
         if amplitude is None:
             self._init_common(k, M, grid[0, :], normalisation, variance, mass_tracer, discrete_tracer,
                               _wants_device(Uk))
@@ -577,9 +687,20 @@ def _erf(x):
     return erf(x)
 
 
+_HOD_KEYS = {'simple': ('Mmin', 'Msat', 'alpha'), 'Zehavi et al. (2004)': ('Mmin', 'M1', 'alpha'),
+             'Zheng et al. (2005)': ('Mmin', 'sigma', 'M0', 'M1', 'alpha'),
+             'Zhai et al. (2017)': ('Mmin', 'sigma', 'Msat', 'alpha', 'Mcut')}
+
+
 def HOD_mean(M, method='Zheng et al. (2005)', **kwargs) -> tuple:
-    '''Mean numbers of central and satellite galaxies (pyhalomodel.py:1131-1201); same methods and keywords.'''
+    '''Mean numbers of central and satellite galaxies (pyhalomodel.py:1131-1201); same methods and keywords (an unknown
+    keyword is a TypeError, as it is for the reference's per-method functions).'''
     xp = _xp(M)
+    if method not in _HOD_KEYS:
+        raise ValueError('HOD method not recognised')
+    for key in kwargs:
+        if key not in _HOD_KEYS[method]:
+            raise TypeError("HOD_mean(method=%r) got an unexpected keyword argument %r" % (method, key))
     if method == 'simple':
         Mmin, Msat, alpha = kwargs.get('Mmin', 1e12), kwargs.get('Msat', 1e13), kwargs.get('alpha', 1.)
         Nc = _step(M-Mmin)
@@ -592,12 +713,10 @@ def HOD_mean(M, method='Zheng et al. (2005)', **kwargs) -> tuple:
         M1, alpha = kwargs.get('M1', 1e13), kwargs.get('alpha', 1.)
         Nc = _step(M-Mmin) if sigma == 0. else 0.5*(1.+_erf(xp.log10(M/Mmin)/sigma))
         return Nc, (_step(M-M0)*(M-M0)/M1)**alpha
-    if method == 'Zhai et al. (2017)':
-        Mmin, sigma = kwargs.get('Mmin', 10**13.68), kwargs.get('sigma', 0.82)
-        Msat, alpha, Mcut = kwargs.get('Msat', 10**14.87), kwargs.get('alpha', 0.41), kwargs.get('Mcut', 10**12.32)
-        Nc = _step(M-Mmin) if sigma == 0. else 0.5*(1.+_erf(xp.log10(M/Mmin)/sigma))
-        return Nc, ((M/Msat)**alpha)*xp.exp(-Mcut/M)
-    raise ValueError('HOD method not recognised')
+    Mmin, sigma = kwargs.get('Mmin', 10**13.68), kwargs.get('sigma', 0.82)
+    Msat, alpha, Mcut = kwargs.get('Msat', 10**14.87), kwargs.get('alpha', 0.41), kwargs.get('Mcut', 10**12.32)
+    Nc = _step(M-Mmin) if sigma == 0. else 0.5*(1.+_erf(xp.log10(M/Mmin)/sigma))
+    return Nc, ((M/Msat)**alpha)*xp.exp(-Mcut/M)
 
 
 def HOD_variance(p, lam, central_condition=False) -> tuple:

@@ -17,8 +17,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import _lib, constants, engine, synthetic as syn
-from .halomodel import model
+from . import _lib, constants, engine, halomodel, synthetic as syn
 
 F64 = torch.float64
 
@@ -78,13 +77,12 @@ class EndToEnd:
         Nc = 0.5*(1.+torch.erf(torch.log10(Mrow/Mmin)/sg))
         Ns = (((Mrow-M0) >= 0.).to(F64)*(Mrow-M0)/M1)**alpha
         N, V = (Nc+Ns).contiguous(), (Nc*(1.-Nc)+Ns).contiguous()
-        # 5. models (host scalars: Tinker table interpolation etc., pyhalomodel.py:56-192)
-        dch, Dvh = dc.cpu().numpy(), Dv.cpu().numpy()
-        models = [model(s['z'], s['Om_m'], name=fam, Dv=float(Dvh[i]), dc=float(dch[i]))
-                  for i, s in enumerate(samples) for fam in self.families]
-        mdev = engine.pack_models([m.descriptor() for m in models])
+        # 5. model descriptors (host, array arithmetic: Tinker table interpolation etc., pyhalomodel.py:56-192)
+        desc = halomodel.model_descriptors(z.cpu().numpy(), Om_m.cpu().numpy(), self.families, Dv.cpu().numpy(),
+                                           dc.cpu().numpy())
+        mdev = engine.pack_models(desc)
         rho_g = engine.average_batch(mdev, self.M, sigma, N, models_per_sample=F)
-        rho_m = torch.tensor([m.rhom for m in models], dtype=F64, device=dev)
+        rho_m = torch.as_tensor(np.ascontiguousarray(desc['rhom']), device=dev)
         # 6. Fourier profiles and spectra
         Mamp = self.M[None, :].expand(G, -1).contiguous()
         tracers = [engine.Tracer(engine.window_nfw(self.k, rv, conc), Mamp, rho_m, mode=_lib.GRID_UK, mass_tracer=True),
@@ -92,7 +90,7 @@ class EndToEnd:
                                  discrete_tracer=True)]
         plan = engine.PowerSpectrumPlan(self.k, Pk, self.M, sigma, tracers, mdev, models_per_sample=F)
         out, lowmass = plan.run()
-        return out, dict(sigma=sigma, Pk_lin=Pk, dc=dc, Dv=Dv, rv=rv, c=conc, N=N, V=V, rho_g=rho_g, models=models)
+        return out, dict(sigma=sigma, Pk_lin=Pk, dc=dc, Dv=Dv, rv=rv, c=conc, N=N, V=V, rho_g=rho_g, models=desc)
 
     def run(self, samples, keep_on_device=True, return_inputs=False):
         """Spectra [len(samples)*F, 3 pairs (m-m, m-g, g-g), 3 terms, nk] for all samples."""
@@ -115,3 +113,25 @@ def draw_samples(n, seed=4321):
         cs['hod'] = syn.draw_hod(rng)
         out.append(cs)
     return out
+
+
+
+class EndToEndShard:
+    """Adapter that lets sweep.ShardedSweep partition a chain over the ranks of one box: build(lo, hi) returns one
+    of these for samples[lo:hi]; .plan().run() evaluates the rank's samples and returns their spectra."""
+
+    def __init__(self, pipe: EndToEnd, samples):
+        self.pipe, self.samples = pipe, samples
+        F = len(pipe.families)
+        self.out = torch.empty((len(samples)*F, 3, 3, len(pipe.kh)), dtype=F64, device=pipe.k.device)
+
+    def plan(self):
+        return self
+
+    def run(self, out=None, peer=False):
+        dst = self.out if out is None else out
+        F = len(self.pipe.families)
+        for i in range(0, len(self.samples), self.pipe.chunk):
+            part, _ = self.pipe._chunk(self.samples[i:i+self.pipe.chunk])
+            dst[i*F:i*F+part.shape[0]].copy_(part)
+        return dst, None

@@ -75,6 +75,33 @@ def test_gram_path_vs_oracle(halo, ntr, nk, nM, name):
         assert got[1]['g0-m'] is got[1]['m-g0']
 
 
+def test_many_tracers_without_gram_preconditions_vs_oracle(halo):
+    """More than 8 profiles where the Gram path does not apply -- an odd number of masses, a profile(k, M, Uk, Wk)
+    object with separate grids, beta_NL -- fall back to the quadrature path on unions of tracer blocks and still
+    return every pair the reference computes (pyhalomodel.py:433-507)."""
+    g = _synthetic_case(9, 65, z=0.3)
+    rng = np.random.default_rng(5)
+    hods = [syn.draw_hod(rng) for _ in range(8)]
+    om = orc.make_model(g['z'], g['Om_m'], Dv=g['Dv'], dc=g['dc'])
+    hmod = halo.model(g['z'], g['Om_m'], Dv=g['Dv'], dc=g['dc'])
+    op = _tracers(orc, om, g, hods, True, True, nfw=False)          # 10 tracers, odd nM
+    gp = _tracers(halo, hmod, g, hods, True, True, nfw=False)
+    Uk = 1./(1.+np.outer(g['k'], np.linspace(0.1, 2., 65)))
+    Wk = Uk*rng.uniform(0.5, 1.5, size=Uk.shape)
+    amp = rng.uniform(0.5, 2., 65)
+    op['x'] = orc.Profile(g['k'], g['M'], Uk, Wk, amplitude=amp, normalisation=2.2)
+    gp['x'] = halo.profile(g['k'], g['M'], Uk, Wk, amplitude=amp, normalisation=2.2)
+    beta = rng.normal(0., 0.3, size=(9, 65, 65))
+    for kw in ({}, dict(beta=beta), dict(subtract_shotnoise=False, k_trunc=0.4)):
+        want = orc.power_spectrum(om, g['k'], g['Pk_lin'], g['M'], g['sigmaM'], op, **kw)
+        got = hmod.power_spectrum(g['k'], g['Pk_lin'], g['M'], g['sigmaM'], gp, **kw)
+        assert list(got[0].keys()) == list(want[0].keys()) and len(got[0]) == 121
+        for t in range(3):
+            for key in want[t]:
+                assert_spectra_close(got[t][key], want[t][key], rtol=RTOL, what='blocked %s term %d' % (key, t),
+                                     zero_scale=np.max(np.abs(want[2][key])))
+
+
 def test_gram_64_tracers_vs_oracle_small_grid(halo):
     """All 2080 unique pairs of 64 HOD tracers (config 4's tracer count) on a grid the oracle finishes in seconds."""
     g = _synthetic_case(6, 128, z=0.2)

@@ -77,3 +77,43 @@ def test_utility_and_model_validation():
                  'Tinker et al. (2010)', 'Despali et al. (2016)'):
         d = halo.model(0.3, 0.3, name=name, Dv=330., dc=1.68).descriptor()
         assert d.dc == 1.68 and d.rhom > 0. and 0 <= d.family <= 5
+
+
+def test_vectorised_model_descriptors_are_bit_identical_to_model_objects():
+    """halomodel.model_descriptors (array arithmetic, for sweeps) against model(...).descriptor() per model, including
+    the Tinker table extrapolation and both module switches (pyhalomodel.py:73-184, :20-22)."""
+    from pyhalomodel_b200 import synthetic as syn
+    rng = np.random.default_rng(0)
+    G = 40
+    z, Om = rng.uniform(0, 2, G), rng.uniform(.25, .35, G)
+    Omz = syn.Om_m_of_z(z, Om)
+    dc, Dv = cosmology.dc_NakamuraSuto(Omz), cosmology.Dv_BryanNorman(Omz)
+    Dv[:5] = [150., 200., 3200., 5000., 800.]
+    try:
+        for zdep, pbs in [(False, False), (True, True)]:
+            halo.Tinker_z_dep, halo.Tinker_PBS = zdep, pbs
+            rec = halo.model_descriptors(z, Om, syn.FAMILY_NAMES, Dv, dc)
+            assert rec.shape == (G*5,) and rec.dtype.itemsize == 120
+            for i in range(G):
+                for f, name in enumerate(syn.FAMILY_NAMES):
+                    d = halo.model(z[i], Om[i], name=name, Dv=Dv[i], dc=dc[i]).descriptor()
+                    assert bytes(d) == rec[i*5+f].tobytes(), (zdep, i, name)
+    finally:
+        halo.Tinker_z_dep, halo.Tinker_PBS = False, False
+    with pytest.raises(ValueError):
+        halo.model_descriptors(z, Om, ['nope'], Dv, dc)
+
+
+def test_hod_keywords_and_halo_integration_switch():
+    M = np.logspace(10, 15, 8)
+    with pytest.raises(TypeError):
+        halo.HOD_mean(M, Mmim=1e12)                       # the reference's per-method functions reject unknown keywords
+    with pytest.raises(TypeError):
+        halo.HOD_mean(M, method='simple', sigma=0.2)
+    halo.halo_integration = 'simps'
+    try:
+        with pytest.raises(NotImplementedError):
+            halomodel._check_halo_integration()
+    finally:
+        halo.halo_integration = 'trapezoid'
+    halomodel._check_halo_integration()

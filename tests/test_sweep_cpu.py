@@ -57,7 +57,7 @@ def _worker(rank, world, port, n_items, result_dir):
             def plan(self):
                 return FakePlan(self.lo, self.hi, 5)
 
-        sw = sweep.ShardedSweep(n_items, FakeBatch, models_per_sample=5)
+        sw = sweep.ShardedSweep(n_items, FakeBatch, models_per_sample=5, tail_shape=(S, 3, nk))
         out = sw.run()
         assert out.shape == (n_items*5, S, 3, nk)
         assert torch.equal(out[:, 0, 0, 0], torch.arange(n_items*5, dtype=torch.float64))
@@ -66,7 +66,7 @@ def _worker(rank, world, port, n_items, result_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('world,n_items', [(2, 8), (2, 7), (3, 10)])
+@pytest.mark.parametrize('world,n_items', [(2, 8), (2, 7), (3, 10), (3, 2)])     # (3, 2): one rank owns no sample
 def test_gather_over_gloo(tmp_path, world, n_items):
     port = _free_port()
     mp.spawn(_worker, args=(world, port, n_items, str(tmp_path)), nprocs=world, join=True)
