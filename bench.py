@@ -647,12 +647,15 @@ def measure_e2e(args, rank, world, sweep, syn, halo, engine, barrier, max_over_r
                     'windows, <N> normalisations, 5 mass functions, spectra on the device -> D2H numpy; wall clock around %d runs' % steps)
     legs = {}
     if rank == 0:
-        # reference-shaped per-model API, host vectors in, numpy out (what a user of the reference types)
+        # reference-shaped per-model API (what a user of the reference types), numpy spectra out.  "from vectors": the
+        # per-sample vectors r_v, c are uploaded as CUDA tensors, so the windows never leave the device; "from host
+        # grids": the two (k, M) grids come from numpy and cross PCIe for every model.
         def api_model(cs, name, grids=None):
             hmod = halo.model(cs['z'], cs['Om_m'], name=name, Dv=cs['Dv'], dc=cs['dc'])
             if grids is None:
-                Um = halo.window_function(k, cs['rv'], cs['c'], profile='NFW')
-                Ug = halo.window_function(k, cs['rv'], profile='isothermal')
+                rv_d, c_d = torch.as_tensor(cs['rv']).cuda(), torch.as_tensor(cs['c']).cuda()
+                Um = halo.window_function(k, rv_d, c_d, profile='NFW')
+                Ug = halo.window_function(k, rv_d, profile='isothermal')
             else:
                 Um, Ug = grids
             profs = {'m': halo.profile.Fourier(k, M, Um, amplitude=M, normalisation=hmod.rhom, mass_tracer=True),
@@ -665,11 +668,14 @@ def measure_e2e(args, rank, world, sweep, syn, halo, engine, barrier, max_over_r
         t0 = time.perf_counter()
         for cs in cases:
             for name in FAMILIES:
-                api_model(cs, name)
+                res1 = api_model(cs, name)
         torch.cuda.synchronize()
         dt = time.perf_counter()-t0
+        assert isinstance(res1[0]['m-m'], np.ndarray)
         legs['per_model_api_from_vectors'] = dict(value=len(cases)*len(FAMILIES)*S/dt, unit=UNIT, models=len(cases)*len(FAMILIES),
-                                                  path='model() + window_function x2 + profile.Fourier x2 + average + power_spectrum per model, numpy in/out')
+                                                  ms_per_model=1e3*dt/(len(cases)*len(FAMILIES)),
+                                                  path='model() + window_function x2 (r_v, c as CUDA tensors) + profile.Fourier x2 + average + '
+                                                       'power_spectrum per model, numpy spectra out')
         grids = [(halo.window_function(k, cs['rv'], cs['c'], profile='NFW'), halo.window_function(k, cs['rv'], profile='isothermal'))
                  for cs in cases]
         t0 = time.perf_counter()
@@ -679,7 +685,7 @@ def measure_e2e(args, rank, world, sweep, syn, halo, engine, barrier, max_over_r
         torch.cuda.synchronize()
         dt = time.perf_counter()-t0
         legs['per_model_api_from_host_grids'] = dict(value=len(cases)*len(FAMILIES)*S/dt, unit=UNIT,
-                                                     h2d_bytes_per_model=2*NK*NM*8,
+                                                     ms_per_model=1e3*dt/(len(cases)*len(FAMILIES)), h2d_bytes_per_model=2*NK*NM*8,
                                                      path='as above with the two (k, M) grids uploaded from numpy per model')
     e2e['legs'] = legs
     return e2e

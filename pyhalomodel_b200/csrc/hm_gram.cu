@@ -7,9 +7,10 @@
 // intensity (~6 flop/B at P=64) is beyond what the streaming-quadrature kernel's per-pair register accumulators
 // can hold, so this path tiles it for mma.sync.m8n8k4.f64 (SASS DMMA; there is no tcgen05 FP64 MMA):
 //
-//   hm_gram_weights_kernel  w1, w2, per-tracer c_p (W = c_p*grid) and d_p (auto one-halo weight) per mass; A
+//   hm_gram_weights_kernel  w1, w2 and r2 = w2/sqrt(w1) per mass; A
+//   hm_gram_tracer_kernel   s_p = sqrt(w1) c_p (the staged tile is Y = s_p*grid, so that the contraction needs no weight:
+//                           sum_m w1 W_u W_v = sum_m Y_u Y_v with W = c_p*grid) and d_p (auto one-halo weight)
 //   hm_gram_scalars_kernel  shot noise and simple-two-halo integrals per (tracer, model)
-//   hm_gram_tracer_kernel   c_p and d_p per (tracer, mass)
 //   hm_gram_kernel<RK,NBT>  persistent warp-specialised CTA per SM over (model, RK wavenumbers, mass part) items:
 //                           prep warps stream the tracer rows of the next 64-mass chunk with cp.async into one of
 //                           three W-tile buffers, scale them in place to W and keep the diagonal work (two-halo
@@ -25,6 +26,7 @@
 #define HM_GLD (HM_GMCH + 8)       // padded row stride of the W tile: 576 B = 64 mod 128, so the 16-byte DMMA
                                    // fragment loads of a quarter warp (2 rows x 4 lanes) hit all 32 banks once
 #define HM_GNSCAL 4
+#define HM_GNTS 3                  // per (model, tracer) scalars: shot noise, simple two-halo integral, c_p[M0]
 #define HM_GWARPS 8
 
 struct hm_gram_layout {
@@ -53,10 +55,10 @@ static hm_gram_layout hm_gram_make_layout(const hm_gram_problem* pr) {
   L.MP = (((pr->nM + nparts - 1) / nparts) + HM_GMCH - 1) / HM_GMCH * HM_GMCH;
   L.nparts = (pr->nM + L.MP - 1) / L.MP;
   auto align = [](size_t x) { return (x + 31) & ~(size_t)31; };
-  L.gw_stride = (size_t)(2 + 2 * L.P) * L.nMp;
+  L.gw_stride = (size_t)(3 + 2 * L.P) * L.nMp;          // w1, w2, s_p [P], d_p [P], r2
   L.scal_offset = align(L.B * L.gw_stride);
   L.tscal_offset = align(L.scal_offset + L.B * HM_GNSCAL);
-  L.partial_offset = align(L.tscal_offset + L.B * (size_t)L.P * 2);
+  L.partial_offset = align(L.tscal_offset + L.B * (size_t)L.P * HM_GNTS);
   L.total_bytes = (L.partial_offset + L.B * (size_t)L.nparts * L.NW * (size_t)pr->nk) * sizeof(double);
   return L;
 }
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(256) hm_gram_weights_kernel(const hm_gram_warg
   if (m >= a.nM) {
     gw[m] = 0.;
     gw[(size_t)a.nMp + m] = 0.;
+    gw[(size_t)(2 + 2 * a.P) * a.nMp + m] = 0.;
     return;
   }
   const double nu = d.dc / sig[m];
@@ -115,9 +118,11 @@ __global__ void __launch_bounds__(256) hm_gram_weights_kernel(const hm_gram_warg
   const double w2 = tw * ((bias * g) / Mm);    // two-halo weight (:539)
   gw[m] = w1;
   gw[(size_t)a.nMp + m] = w2;
+  gw[(size_t)(2 + 2 * a.P) * a.nMp + m] = (w1 > 0.) ? w2 / sqrt(w1) : 0.;   // sum_m w2 W_p = sum_m r2 Y_p  (:539)
 }
 
-// per-(tracer, mass) factors: c_p (W = c_p * grid) and d_p (auto one-halo weight); grid = (mass chunk, tracer, model)
+// per-(tracer, mass) factors: s_p = sqrt(w1) c_p (W = c_p * grid, Y = s_p * grid) and d_p (auto one-halo weight);
+// grid = (mass chunk, tracer, model)
 __global__ void __launch_bounds__(256) hm_gram_tracer_kernel(const hm_gram_wargs a) {
   const int p = blockIdx.y, b = blockIdx.z, s = b / a.F;
   const int m = blockIdx.x * 256 + threadIdx.x;
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(256) hm_gram_tracer_kernel(const hm_gram_wargs
     else { c = 1.; uS = 1. / (amp * norm); }                                        // HM_GRID_WK
     dw = __dmul_rn(__dmul_rn(gw[m], fac), uS * uS);                                 // d_p = w1 fac uS^2 (:475-477)
   }
-  gw[(size_t)(2 + p) * a.nMp + m] = c;
+  gw[(size_t)(2 + p) * a.nMp + m] = (m < a.nM) ? sqrt(gw[m]) * c : 0.;
   gw[(size_t)(2 + a.P + p) * a.nMp + m] = dw;
 }
 
@@ -157,9 +162,10 @@ __global__ void __launch_bounds__(256) hm_gram_scalars_kernel(const hm_gram_warg
   if (threadIdx.x == 0) {
     const double A = a.scal[(size_t)b * HM_GNSCAL], rhom = a.scal[(size_t)b * HM_GNSCAL + 1];
     if (a.mass[p]) si += (A / a.M[0]) * (a.amplitude[p][aoff] / norm);
-    double* t = a.tscal + ((size_t)b * a.P + p) * 2;
+    double* t = a.tscal + ((size_t)b * a.P + p) * HM_GNTS;
     t[0] = a.discrete[p] ? sn * rhom : 0.;
     t[1] = si * rhom;
+    t[2] = (a.mode[p] == HM_GRID_UK) ? a.amplitude[p][aoff] / norm : 1.;      // c_p[M0]: low-mass term of the epilogue
   }
 }
 
@@ -218,30 +224,23 @@ __device__ __forceinline__ void hm_gram_mma_jj(double (&acc)[RK][2][4][2], int r
   if constexpr (F::v2(JJ)) hm_dmma884(acc[r][1][JJ][0], acc[r][1][JJ][1], HALF ? a2.y : a2.x, HALF ? bb.y : bb.x);
 }
 
-// C[u,v] += sum_m (w1 W_u) W_v over one staged 64-mass tile.  Two k4-steps per 16-byte fragment load: within an
+// C[u,v] += sum_m Y_u Y_v over one staged 64-mass tile (Y = sqrt(w1) W: the weight is folded into both operands).  Two k4-steps per 16-byte fragment load: within an
 // 8-mass block step 0 takes masses {0,2,4,6} and step 1 {1,3,5,7} (any assignment works as long as A, B and w1
 // agree: the sum over masses is order-free).
 template <int RK, int NBT, int WQ, int E>
-__device__ __forceinline__ void hm_gram_mma(double (&acc)[RK][2][4][2], const double* __restrict__ Yt,
-                                            const double* __restrict__ w1t, int fr, int fk) {
+__device__ __forceinline__ void hm_gram_mma(double (&acc)[RK][2][4][2], const double* __restrict__ Yt, int fr, int fk) {
   using F = hm_gram_frag<NBT, WQ, E>;
   constexpr int PT = 8 * NBT;
   if constexpr (!F::ROW1) return;
   const double* Yb = Yt + 2 * fk + (size_t)fr * HM_GLD;
-  const double* w1b = w1t + 2 * fk;
 #pragma unroll 2
   for (int blk = 0; blk < HM_GMCH / 8; ++blk) {
-    const double2 w1p = *reinterpret_cast<const double2*>(w1b + 8 * blk);
 #pragma unroll
     for (int r = 0; r < RK; ++r) {
       const double* Yr = Yb + (size_t)r * PT * HM_GLD + 8 * blk;
-      double2 a1 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * F::I1) * HM_GLD);
+      const double2 a1 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * F::I1) * HM_GLD);
       double2 a2 = make_double2(0., 0.);
-      a1.x *= w1p.x; a1.y *= w1p.y;
-      if constexpr (F::ROW2) {
-        a2 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * F::I2) * HM_GLD);
-        a2.x *= w1p.x; a2.y *= w1p.y;
-      }
+      if constexpr (F::ROW2) a2 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * F::I2) * HM_GLD);
       double2 b0 = make_double2(0., 0.), b1 = b0, b2 = b0, b3 = b0;
       if constexpr (F::v1(0) || F::v2(0)) b0 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * (0 + E)) * HM_GLD);
       if constexpr (F::v1(1) || F::v2(1)) b1 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * (2 + E)) * HM_GLD);
@@ -332,7 +331,6 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
   constexpr size_t tile_doubles = (size_t)RK * PT * HM_GLD;
   constexpr int NDV = NBT * RK * 2;                     // diagonal sums per prep warp (<= 32)
   double* Ys = gsm;                                     // [3][RK][PT][HM_GLD]  W tiles (raw grid rows until scaled)
-  double* w1s = Ys + 3 * tile_doubles;                  // [3][HM_GMCH]
   const int P = a.P;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform: role dispatch does not diverge
@@ -384,27 +382,36 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
     int n = 0;
     while (true) {
       const int buf = n % 3;
+      const int m = cur.mbeg + cur.ch * HM_GMCH + 2 * lane;
+      const bool in = m < cur.mend;                     // nM and MP are even: a lane's two masses are in or out together
+      const double* __restrict__ gw = a.gw + (size_t)cur.b * a.gw_stride;
+      constexpr int TH = (NBT + 1) / 2;                 // tracers per half: bounds the registers held by s_p, d_p
+      // the per-(tracer, mass) factors of the first half come from L2: issue their loads before anything that may wait
+      double2 cc[TH], dd[TH];
+#pragma unroll
+      for (int tt = 0; tt < TH; ++tt) {
+        const int p = pw + 8 * tt;
+        const bool on = in && p < P;
+        cc[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + p) * a.nMp + m) : zero;
+        dd[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + P + p) * a.nMp + m) : zero;
+      }
+      const double2 w2v = in ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + 2 * P) * a.nMp + m) : zero;   // r2
       if (more) {                                       // prefetch chunk n+1 into its buffer once the MMA warps are
         const int nb = (n + 1) % 3;                     // done with chunk n-2, which used it
         if (n + 1 >= 3) hm_bar_sync(HM_GBAR_EMPTY + nb);
         issue(fill, nb);
       }
-      const int m = cur.mbeg + cur.ch * HM_GMCH + 2 * lane;
-      const bool in = m < cur.mend;                     // nM and MP are even: a lane's two masses are in or out together
-      const double* __restrict__ gw = a.gw + (size_t)cur.b * a.gw_stride;
-      const double2 w2v = in ? *reinterpret_cast<const double2*>(gw + (size_t)a.nMp + m) : zero;
-      const double2 w1v = (pw == 0 && in) ? *reinterpret_cast<const double2*>(gw + m) : zero;
       double* Y = Ys + (size_t)buf * tile_doubles + 2 * lane;
-      constexpr int TH = (NBT + 1) / 2;                 // tracers per half: bounds the registers held by c_p, d_p
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        double2 cc[TH], dd[TH];
+        if (half == 1) {
 #pragma unroll
-        for (int tt = 0; tt < TH; ++tt) {
-          const int t = half * TH + tt, p = pw + 8 * t;
-          const bool on = in && t < NBT && p < P;
-          cc[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + p) * a.nMp + m) : zero;
-          dd[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + P + p) * a.nMp + m) : zero;
+          for (int tt = 0; tt < TH; ++tt) {
+            const int t = TH + tt, p = pw + 8 * t;
+            const bool on = in && t < NBT && p < P;
+            cc[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + p) * a.nMp + m) : zero;
+            dd[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + P + p) * a.nMp + m) : zero;
+          }
         }
         if (half == 0) {                                // my copies of chunk n have landed (n+1 may still fly)
           if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -419,16 +426,17 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
               double2* cell = reinterpret_cast<double2*>(Y + ((size_t)r * PT + p) * HM_GLD);
               const double2 xv = *cell;                 // raw grid values (zero-filled where off)
               const double2 y = make_double2(cc[tt].x * xv.x, cc[tt].y * xv.y);
-              *cell = y;                                // W = c_p * grid, in place
+              *cell = y;                                // Y = s_p * grid, in place
               if ((t * RK + r) * 2 + 1 < 32) {
-                vals[(t * RK + r) * 2] += fma(w2v.x, y.x, w2v.y * y.y);                          // sum_m w2 W_p   (:539)
-                vals[(t * RK + r) * 2 + 1] += fma(dd[tt].x * xv.x, xv.x, (dd[tt].y * xv.y) * xv.y);   // sum_m d_p U^2  (:475-477)
+                double& v2h = vals[(t * RK + r) * 2];
+                double& v1h = vals[(t * RK + r) * 2 + 1];
+                v2h = fma(w2v.x, y.x, fma(w2v.y, y.y, v2h));                                      // sum_m r2 Y_p = sum_m w2 W_p  (:539)
+                v1h = fma(dd[tt].x * xv.x, xv.x, fma(dd[tt].y * xv.y, xv.y, v1h));                // sum_m d_p U^2  (:475-477)
               }
             }
           }
         }
       }
-      if (pw == 0) *reinterpret_cast<double2*>(w1s + buf * HM_GMCH + 2 * lane) = w1v;
       __threadfence_block();
       hm_bar_arrive(HM_GBAR_FULL + buf);
 
@@ -469,8 +477,7 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
     hm_bar_sync(HM_GBAR_FULL + buf);                    // the W tile of this chunk is staged
     {
       const double* Yt = Ys + (size_t)buf * tile_doubles;
-      const double* w1t = w1s + buf * HM_GMCH;
-      HM_GRAM_WARP_SWITCH(hm_gram_mma, acc, Yt, w1t, fr, fk)
+      HM_GRAM_WARP_SWITCH(hm_gram_mma, acc, Yt, fr, fk)
     }
     hm_bar_arrive(HM_GBAR_EMPTY + buf);                 // all my reads of the tile have been consumed by DMMAs
     if (cur.ch + 1 == cur.nch_item) {                   // item finished: write and reset my fragments
@@ -531,14 +538,14 @@ __global__ void __launch_bounds__(256) hm_gram_epilogue_kernel(const hm_gram_ear
   const double* gw = a.gw + (size_t)b * a.gw_stride;
   const double Aterm = A / a.M[0];
   const size_t goff = ((size_t)smp * a.nk + row) * (size_t)a.nM;     // W_p(k, M[0]) = c_p[0] * grid_p[k, 0]  (:541-542)
-  if (a.mass[u]) fu += Aterm * (gw[(size_t)(2 + u) * a.nMp] * a.grid[u][goff]);
-  if (a.mass[v]) fv += Aterm * (gw[(size_t)(2 + v) * a.nMp] * a.grid[v][goff]);
-  const double Iu = a.simple_twohalo ? a.tscal[((size_t)b * P + u) * 2 + 1] : fu * rhom;
-  const double Iv = a.simple_twohalo ? a.tscal[((size_t)b * P + v) * 2 + 1] : fv * rhom;
+  if (a.mass[u]) fu += Aterm * (a.tscal[((size_t)b * P + u) * HM_GNTS + 2] * a.grid[u][goff]);
+  if (a.mass[v]) fv += Aterm * (a.tscal[((size_t)b * P + v) * HM_GNTS + 2] * a.grid[v][goff]);
+  const double Iu = a.simple_twohalo ? a.tscal[((size_t)b * P + u) * HM_GNTS + 1] : fu * rhom;
+  const double Iv = a.simple_twohalo ? a.tscal[((size_t)b * P + v) * HM_GNTS + 1] : fv * rhom;
   const double p2h = __dmul_rn(__dadd_rn(__dmul_rn(Iu, Iv), 0.), a.Pk_lin[(size_t)smp * a.nk + row]);   // :524
   double p1h = f1 * rhom;                                                                              // :532
   if (u == v && a.discrete[u]) {                                                                       // :484-491
-    const double sn = a.tscal[((size_t)b * P + u) * 2];
+    const double sn = a.tscal[((size_t)b * P + u) * HM_GNTS];
     if (a.correct_discrete && !a.subtract_shotnoise) p1h += sn;
     else if (!a.correct_discrete && a.subtract_shotnoise) p1h -= sn;
   }
@@ -636,7 +643,7 @@ extern "C" int hm_gram_power_spectrum_stages(const hm_gram_problem* pr, double* 
   g.gw = wsd; g.partial = wsd + L.partial_offset;
   // the kernel is instantiated for block grids of 2, 4 and 8 (16, 32, 64 tracer rows); pad up to the next one
   const int NBT = (L.NB <= 2) ? 2 : (L.NB <= 4) ? 4 : 8;
-  const size_t smem = (3 * (size_t)L.RK * (8 * NBT) * HM_GLD + 3 * HM_GMCH) * sizeof(double);
+  const size_t smem = 3 * (size_t)L.RK * (8 * NBT) * HM_GLD * sizeof(double);
   static hm_once_per_device once;
   if (once.needed()) {
     HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
