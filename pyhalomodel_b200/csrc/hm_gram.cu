@@ -22,9 +22,11 @@
 #include "hm_common.cuh"
 
 #define HM_GMAXP HM_GRAM_MAX_TRACERS
-#define HM_GMCH 64                 // masses per chunk
-#define HM_GLD (HM_GMCH + 8)       // padded row stride of the W tile: 576 B = 64 mod 128, so the 16-byte DMMA
+#define HM_GMCH 32                 // masses per chunk
+#define HM_GLD (HM_GMCH + 8)       // padded row stride of the tile: 320 B = 64 mod 128, so the 16-byte DMMA
                                    // fragment loads of a quarter warp (2 rows x 4 lanes) hit all 32 banks once
+#define HM_GNBUF 5                 // tile buffers (40 KB each at 64 tracer rows x 2 wavenumbers) ...
+#define HM_GDEPTH 3                // ... of which this many are in flight from HBM ahead of the one being scaled
 #define HM_GNSCAL 4
 #define HM_GNTS 3                  // per (model, tracer) scalars: shot noise, simple two-halo integral, c_p[M0]
 #define HM_GWARPS 8
@@ -49,7 +51,7 @@ static hm_gram_layout hm_gram_make_layout(const hm_gram_problem* pr) {
   // split the mass axis so that there are a few waves of CTAs (2 resident per SM); parts are multiples of 64 masses
   const long long rows = (long long)L.B * L.ntiles;
   int nparts = 1;
-  const int maxparts = (pr->nM + 4 * HM_GMCH - 1) / (4 * HM_GMCH);       // at least 256 masses per part
+  const int maxparts = (pr->nM + 255) / 256;                             // at least 256 masses per part
   while (nparts < maxparts && rows * nparts < 6LL * 148) nparts *= 2;
   if (nparts > maxparts) nparts = maxparts;
   L.MP = (((pr->nM + nparts - 1) / nparts) + HM_GMCH - 1) / HM_GMCH * HM_GMCH;
@@ -299,9 +301,24 @@ __device__ __forceinline__ void hm_gram_flush(double (&acc)[RK][2][4][2], double
     default: FN<RK, NBT, 3, 1>(__VA_ARGS__); break;            \
   }
 
-// ---- named barriers between the two warp roles (ids 1..4; 0 is __syncthreads) ---------------------------------
-#define HM_GBAR_FULL 1      // + buf (0..2): prep warps arrive, MMA warps wait
-#define HM_GBAR_EMPTY 4     // + buf (0..2): MMA warps arrive, prep warps wait
+// ---- named barriers between the two warp roles (ids 1..10; 0 is __syncthreads) --------------------------------
+#define HM_GBAR_FULL 1                   // + buf: prep warps arrive, MMA warps wait
+#define HM_GBAR_EMPTY (1 + HM_GNBUF)     // + buf: MMA warps arrive, prep warps wait
+
+// v[0..16) per lane -> the lane whose low four bits are j holds the sum of v[j] over the 16 lanes of its half warp
+__device__ __forceinline__ double hm_half_transpose_sum16(double (&v)[16], int lane) {
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const double send = upper ? v[i] : v[i + off];
+      const double keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
 #define HM_GTHREADS (64 * HM_GWARPS)
 __device__ __forceinline__ void hm_bar_sync(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(HM_GTHREADS) : "memory");
@@ -317,20 +334,24 @@ __device__ __forceinline__ bool hm_gram_advance(hm_gram_cursor& c, long long it1
 }
 
 // Persistent, warp-specialised CTA (one per SM, 16 warps):
-//   prep warps 8..15  stream the tracer rows of the next 64-mass chunk from HBM (16-byte loads), scale them to
-//                     W = c_p * grid, stage the W tile in shared memory (double buffered) and accumulate the
-//                     diagonal work -- two-halo sums sum_m w2 W_p and auto one-halo sums sum_m d_p grid_p^2 --
-//                     in per-lane shared-memory accumulators that are reduced once per item;
+//   prep warps 8..15  stream the tracer rows of 32-mass chunks from HBM with cp.async (LDGSTS, no registers held by
+//                     loads in flight) into a ring of HM_GNBUF tile buffers, HM_GDEPTH chunks (120 KB per SM) ahead of
+//                     the chunk being worked on -- with a single chunk in flight the role ran at 2.8 TB/s and bounded
+//                     the kernel (measured with the DMMAs compiled out: 102 of 147 us); scale the landed tile in place
+//                     to Y = s_p * grid (s_p = sqrt(w1) c_p, so the contraction needs no weight) and accumulate the
+//                     diagonal work -- two-halo sums sum_m w2 W_p and auto one-halo sums sum_m d_p grid_p^2 -- in
+//                     registers, reduced once per item;
 //   MMA warps 0..7    run DMMA over their fragments of the staged tile.
 // The roles hand tiles over with named barriers (bar.arrive / bar.sync), so loads, staging and tensor work of
 // different chunks overlap and there is no CTA-wide synchronisation.
 template <int RK, int NBT>
 __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_args a) {
+  static_assert(RK == 2 && HM_GMCH == 32, "a prep lane owns one mass pair of the chunk for both wavenumber rows");
+  static_assert(2 * NBT <= 16, "the diagonal sums of a prep lane fit one 16-value reduction");
   extern __shared__ __align__(16) double gsm[];
   constexpr int PT = 8 * NBT;
   constexpr size_t tile_doubles = (size_t)RK * PT * HM_GLD;
-  constexpr int NDV = NBT * RK * 2;                     // diagonal sums per prep warp (<= 32)
-  double* Ys = gsm;                                     // [3][RK][PT][HM_GLD]  W tiles (raw grid rows until scaled)
+  double* Ys = gsm;                                     // [HM_GNBUF][RK][PT][HM_GLD]  tiles (raw grid rows until scaled)
   const int P = a.P;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform: role dispatch does not diverge
@@ -346,118 +367,131 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
 
   if (warp >= HM_GWARPS) {
     // =============================== prep warps ===============================
-    // cp.async (LDGSTS) streams the raw tracer rows of chunk n+1 into its W-tile buffer while chunk n is scaled in
-    // place: no registers are held by loads in flight, so a whole 64 KB chunk per SM is always on its way.
-    const int pw = warp - HM_GWARPS;                    // owns tracers pw, pw+8, ...
+    // Warp pw owns tracers pw, pw + 8, ...; inside it a lane owns one mass pair of the 32-mass chunk (mp) for BOTH
+    // wavenumber rows and every second one of the warp's tracers (th), so the per-(tracer, mass) factors s_p, d_p are
+    // loaded once for the two rows.  They come from L2 (~1000 cycles under load): the factors of chunk n + 1 are
+    // loaded while chunk n is scaled, a full iteration before they are used.
+    static_assert(NBT % 2 == 0, "the two lane halves split the warp's tracers");
+    constexpr int TL = NBT / 2;                         // tracers per lane
+    const int pw = warp - HM_GWARPS;
+    const int mp = lane & 15, th = lane >> 4;
     const double2 zero = make_double2(0., 0.);
-    double vals[32];                                    // diagonal sums of the current item (per lane)
+    double vals[16];                                    // diagonal sums of the current item: [tt][row][2h, auto 1h]
 #pragma unroll
-    for (int i = 0; i < 32; ++i) vals[i] = 0.;
+    for (int i = 0; i < 16; ++i) vals[i] = 0.;
 
     auto issue = [&](const hm_gram_cursor& c, int buf) {
-      const int m = c.mbeg + c.ch * HM_GMCH + 2 * lane;
+      const int m = c.mbeg + c.ch * HM_GMCH + 2 * mp;
       const bool in = m < c.mend;
       const int mc = in ? m : 0;                        // keep the (unread) source address inside the row
-      const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(Ys + (size_t)buf * tile_doubles + 2 * lane);
+      const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(Ys + (size_t)buf * tile_doubles + 2 * mp);
 #pragma unroll
       for (int r = 0; r < RK; ++r) {
         const int row = (c.row0 + r < a.nk) ? c.row0 + r : a.nk - 1;         // clamp: duplicates are never written
         const size_t off = ((size_t)c.smp * a.nk + row) * (size_t)a.nM + mc;
 #pragma unroll
-        for (int t = 0; t < NBT; ++t) {
-          const int p = pw + 8 * t;
+        for (int tt = 0; tt < TL; ++tt) {
+          const int p = pw + 8 * (2 * tt + th);
           const bool on = in && p < P;
           const double* src = a.grid[on ? p : 0] + off;
           const uint32_t dst = dst0 + (uint32_t)(((size_t)r * PT + p) * HM_GLD * sizeof(double));
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(on ? 16 : 0) : "memory");
         }
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-
-    hm_gram_cursor fill = cur;                          // `fill` runs one chunk ahead of `cur`
-    issue(fill, 0);
-    bool more = hm_gram_advance(fill, it1);
-    if (more && fill.ch == 0) hm_gram_decode<RK>(fill, a);
-    int n = 0;
-    while (true) {
-      const int buf = n % 3;
-      const int m = cur.mbeg + cur.ch * HM_GMCH + 2 * lane;
-      const bool in = m < cur.mend;                     // nM and MP are even: a lane's two masses are in or out together
-      const double* __restrict__ gw = a.gw + (size_t)cur.b * a.gw_stride;
-      constexpr int TH = (NBT + 1) / 2;                 // tracers per half: bounds the registers held by s_p, d_p
-      // the per-(tracer, mass) factors of the first half come from L2: issue their loads before anything that may wait
-      double2 cc[TH], dd[TH];
+    double2 cc[TL], dd[TL], w2v;                        // s_p, d_p of my tracers and r2 at my mass pair, for chunk `cur`
+    auto load_factors = [&](const hm_gram_cursor& c) {
+      const int m = c.mbeg + c.ch * HM_GMCH + 2 * mp;
+      const bool in = m < c.mend;                       // nM and MP are even: a lane's two masses are in or out together
+      const double* __restrict__ gw = a.gw + (size_t)c.b * a.gw_stride;
 #pragma unroll
-      for (int tt = 0; tt < TH; ++tt) {
-        const int p = pw + 8 * tt;
+      for (int tt = 0; tt < TL; ++tt) {
+        const int p = pw + 8 * (2 * tt + th);
         const bool on = in && p < P;
         cc[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + p) * a.nMp + m) : zero;
         dd[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + P + p) * a.nMp + m) : zero;
       }
-      const double2 w2v = in ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + 2 * P) * a.nMp + m) : zero;   // r2
-      if (more) {                                       // prefetch chunk n+1 into its buffer once the MMA warps are
-        const int nb = (n + 1) % 3;                     // done with chunk n-2, which used it
-        if (n + 1 >= 3) hm_bar_sync(HM_GBAR_EMPTY + nb);
-        issue(fill, nb);
-      }
-      double* Y = Ys + (size_t)buf * tile_doubles + 2 * lane;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (half == 1) {
-#pragma unroll
-          for (int tt = 0; tt < TH; ++tt) {
-            const int t = TH + tt, p = pw + 8 * t;
-            const bool on = in && t < NBT && p < P;
-            cc[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + p) * a.nMp + m) : zero;
-            dd[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + P + p) * a.nMp + m) : zero;
-          }
-        }
-        if (half == 0) {                                // my copies of chunk n have landed (n+1 may still fly)
-          if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
-          else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-#pragma unroll
-        for (int tt = 0; tt < TH; ++tt) {
-          const int t = half * TH + tt, p = pw + 8 * t;
-          if (t < NBT) {
-#pragma unroll
-            for (int r = 0; r < RK; ++r) {
-              double2* cell = reinterpret_cast<double2*>(Y + ((size_t)r * PT + p) * HM_GLD);
-              const double2 xv = *cell;                 // raw grid values (zero-filled where off)
-              const double2 y = make_double2(cc[tt].x * xv.x, cc[tt].y * xv.y);
-              *cell = y;                                // Y = s_p * grid, in place
-              if ((t * RK + r) * 2 + 1 < 32) {
-                double& v2h = vals[(t * RK + r) * 2];
-                double& v1h = vals[(t * RK + r) * 2 + 1];
-                v2h = fma(w2v.x, y.x, fma(w2v.y, y.y, v2h));                                      // sum_m r2 Y_p = sum_m w2 W_p  (:539)
-                v1h = fma(dd[tt].x * xv.x, xv.x, fma(dd[tt].y * xv.y, xv.y, v1h));                // sum_m d_p U^2  (:475-477)
-              }
-            }
-          }
-        }
-      }
-      __threadfence_block();
-      hm_bar_arrive(HM_GBAR_FULL + buf);
+      w2v = in ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + 2 * P) * a.nMp + m) : zero;    // r2
+    };
 
-      if (cur.ch + 1 == cur.nch_item) {                 // item finished: reduce and write my tracers' diagonal sums
-        const int part = cur.item % a.nparts;
-        double* dst = a.partial + ((size_t)cur.b * a.nparts + part) * (size_t)a.NW * a.nk;
-        const double tot = hm_warp_transpose_sum32(vals, lane);          // lane j now holds value j of this warp
-        const int t = lane / (2 * RK), r = (lane >> 1) % RK, kind = lane & 1, p = pw + 8 * t;
-        if (lane < NDV && p < P && cur.row0 + r < a.nk) dst[(size_t)(kind * P + p) * a.nk + cur.row0 + r] = tot;
+    hm_gram_cursor fill = cur;                          // `fill` runs HM_GDEPTH chunks ahead of `cur`
+    bool more = true;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) vals[i] = 0.;
-      }
-      ++n;
-      const int prev_item = cur.item;
-      if (!hm_gram_advance(cur, it1)) break;
-      if (cur.item != prev_item) hm_gram_decode<RK>(cur, a);
+    for (int d = 0; d < HM_GDEPTH; ++d) {               // one cp.async group per chunk, empty when there is none
       if (more) {
-        const int pf = fill.item;
+        issue(fill, d);
         more = hm_gram_advance(fill, it1);
-        if (more && fill.item != pf) hm_gram_decode<RK>(fill, a);
+        if (more && fill.ch == 0) hm_gram_decode<RK>(fill, a);
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    load_factors(cur);
+    int n = 0;
+    while (true) {
+      const int buf = n % HM_GNBUF;
+      if (more) {                                       // chunk n + DEPTH goes into the buffer chunk n + DEPTH - NBUF used,
+        const int nb = (n + HM_GDEPTH) % HM_GNBUF;      // once the MMA warps are done with that one
+        if (n + HM_GDEPTH >= HM_GNBUF) hm_bar_sync(HM_GBAR_EMPTY + nb);
+        issue(fill, nb);
+        more = hm_gram_advance(fill, it1);
+        if (more && fill.ch == 0) hm_gram_decode<RK>(fill, a);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group %0;" ::"n"(HM_GDEPTH) : "memory");      // my copies of chunk n have landed
+      double* Y = Ys + (size_t)buf * tile_doubles + 2 * mp;
+      double2 xv[TL][RK];
+#ifdef HM_GRAM_DEBUG_NO_SCALE
+#pragma unroll
+      for (int tt = 0; tt < TL; ++tt)
+#pragma unroll
+        for (int r = 0; r < RK; ++r) xv[tt][r] = zero;
+      if (false)
+#endif
+#pragma unroll
+      for (int tt = 0; tt < TL; ++tt)
+#pragma unroll
+        for (int r = 0; r < RK; ++r) {
+          const int p = pw + 8 * (2 * tt + th);
+          double2* cell = reinterpret_cast<double2*>(Y + ((size_t)r * PT + p) * HM_GLD);
+          xv[tt][r] = *cell;                            // raw grid values (zero-filled where off)
+          const double2 y = make_double2(cc[tt].x * xv[tt][r].x, cc[tt].y * xv[tt][r].y);
+          *cell = y;                                    // Y = s_p * grid, in place
+#ifndef HM_GRAM_DEBUG_NO_DIAG
+          double& v2h = vals[(tt * RK + r) * 2];
+          v2h = fma(w2v.x, y.x, fma(w2v.y, y.y, v2h));                                             // sum_m r2 Y_p = sum_m w2 W_p  (:539)
+#endif
+        }
+      // No __threadfence_block() here: bar.arrive orders this thread's shared-memory stores before the barrier completes
+      // for the threads that bar.sync on it, and a CTA-scope fence would also wait for the cp.async copies of the NEXT
+      // chunks still in flight -- it turned the ring into one DRAM round trip per chunk (prep role alone: 100 us).
+      hm_bar_arrive(HM_GBAR_FULL + buf);                // the tile is staged: the rest of the iteration is off the MMA warps' path
+#ifndef HM_GRAM_DEBUG_NO_DIAG
+#pragma unroll
+      for (int tt = 0; tt < TL; ++tt)
+#pragma unroll
+        for (int r = 0; r < RK; ++r) {
+          double& v1h = vals[(tt * RK + r) * 2 + 1];
+          v1h = fma(dd[tt].x * xv[tt][r].x, xv[tt][r].x, fma(dd[tt].y * xv[tt][r].y, xv[tt][r].y, v1h));   // sum_m d_p U^2  (:475-477)
+        }
+#endif
+      const bool item_done = cur.ch + 1 == cur.nch_item;
+      const hm_gram_cursor done = cur;
+      ++n;
+      const bool go_on = hm_gram_advance(cur, it1);
+      if (go_on) {
+        if (cur.item != done.item) hm_gram_decode<RK>(cur, a);
+        load_factors(cur);                              // for the next iteration: a whole iteration of latency hiding
+      }
+      if (item_done) {                                  // item finished: reduce and write my tracers' diagonal sums
+        const int part = done.item % a.nparts;
+        double* dst = a.partial + ((size_t)done.b * a.nparts + part) * (size_t)a.NW * a.nk;
+        const double tot = hm_half_transpose_sum16(vals, lane);          // lane (th, j) now holds value j of its half
+        const int tt = mp >> 2, r = (mp >> 1) & 1, kind = mp & 1, p = pw + 8 * (2 * tt + th);
+        if (tt < TL && p < P && done.row0 + r < a.nk) dst[(size_t)(kind * P + p) * a.nk + done.row0 + r] = tot;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) vals[i] = 0.;
+      }
+      if (!go_on) break;
     }
     return;
   }
@@ -473,11 +507,13 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
   const int fr = lane >> 2, fk = lane & 3;
   int n = 0;
   while (true) {
-    const int buf = n % 3;
+    const int buf = n % HM_GNBUF;
     hm_bar_sync(HM_GBAR_FULL + buf);                    // the W tile of this chunk is staged
     {
+#ifndef HM_GRAM_DEBUG_NO_MMA
       const double* Yt = Ys + (size_t)buf * tile_doubles;
       HM_GRAM_WARP_SWITCH(hm_gram_mma, acc, Yt, fr, fk)
+#endif
     }
     hm_bar_arrive(HM_GBAR_EMPTY + buf);                 // all my reads of the tile have been consumed by DMMAs
     if (cur.ch + 1 == cur.nch_item) {                   // item finished: write and reset my fragments
@@ -643,7 +679,7 @@ extern "C" int hm_gram_power_spectrum_stages(const hm_gram_problem* pr, double* 
   g.gw = wsd; g.partial = wsd + L.partial_offset;
   // the kernel is instantiated for block grids of 2, 4 and 8 (16, 32, 64 tracer rows); pad up to the next one
   const int NBT = (L.NB <= 2) ? 2 : (L.NB <= 4) ? 4 : 8;
-  const size_t smem = 3 * (size_t)L.RK * (8 * NBT) * HM_GLD * sizeof(double);
+  const size_t smem = (size_t)HM_GNBUF * L.RK * (8 * NBT) * HM_GLD * sizeof(double);
   static hm_once_per_device once;
   if (once.needed()) {
     HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));

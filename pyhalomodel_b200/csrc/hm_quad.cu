@@ -24,6 +24,8 @@
 //                          discrete/shot-noise/k_trunc fix-ups and P_hm (:456-501).
 //
 // Algorithmic bytes per launch of the streaming kernel: 8*(G*P*nk*nM + B*(P+S)*nM).
+#include <stdlib.h>
+
 #include <cuda.h>      // CUtensorMap: types only, the encoder is fetched through cudaGetDriverEntryPoint
 
 #include "hm_common.cuh"
@@ -316,6 +318,10 @@ struct hm_quad_args {
   const double* gridU[HM_MAXP];      // auto one-halo source (== gridW unless HM_GRID_SEPARATE)
   const double* weights;
   double* partial;                   // [B][nparts][nk][NW]
+  // fused epilogue of the row-per-lane kernel (default flags only): spectra straight from the item's sums
+  const double* scal;                // [B][HM_NSCAL]
+  const double* Pk_lin;              // [G][nk]
+  double* out;                       // [B][S][3][nk]
 };
 
 // acc[r*NW + i] += w_i * (grid values the weight vector i multiplies), for one mass column.
@@ -658,7 +664,7 @@ struct hm_rows_cfg {
   static_assert(NS >= 2, "the ring needs two stages");
 };
 
-template <int P, int FM>
+template <int P, int FM, bool FUSED>
 __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const hm_quad_args a,
                                                                           const __grid_constant__ CUtensorMap tmG0,
                                                                           const __grid_constant__ CUtensorMap tmG1,
@@ -794,6 +800,20 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
     // completes exactly one phase per item.  A writer waits until the previous occupant of its target buffer has been
     // drained: the previous writer of this item, or the buffer's last writer of the previous item. ----
     const uint32_t ph = item_no & 1u;
+    // (fused epilogue) the root warp fetches the per-model scalars and P_lin of its rows now, so that the loads fly
+    // while it waits for the other warps' sums instead of serialising behind the last hand-over
+    double rh[FUSED ? FM : 1], pl[2] = {0., 0.};
+    if constexpr (FUSED) {
+      if (warp == 0) {
+#pragma unroll
+        for (int f = 0; f < FM; ++f) rh[f] = a.scal[((size_t)smp * FM + f) * HM_NSCAL + 1];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int row = tile * RT + r * 32 + lane;
+          pl[r] = a.Pk_lin[(size_t)smp * a.nk + (row < a.nk ? row : a.nk - 1)];
+        }
+      }
+    }
 #pragma unroll
     for (int step = 4; step >= 1; step >>= 1) {
       if (warp < step) {
@@ -823,13 +843,40 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
         if (lane == 0) hm_mbar_arrive(bar_pfull + 8 * warp);
       }
     }
-    if (warp == 0) {      // the item's RT x NV sums: partial[model][i][row], coalesced over rows
+    if (warp == 0) {      // the item's RT x NV sums, coalesced over rows
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int row = tile * RT + r * 32 + lane;
         if (row < a.nk) {
+          if constexpr (FUSED) {
+            // default flags (no beta_NL, simple two-halo, k_trunc or shot-noise fix-up): the spectra follow from the
+            // sums directly, with the arithmetic of hm_epilogue_kernel (pyhalomodel.py:456-501)
+            constexpr int S = C::S;
+            const double plin = pl[r];
 #pragma unroll
-          for (int j = 0; j < NV; ++j) a.partial[((size_t)smp * NV + j) * (size_t)a.nk + row] = acc[r][j];
+            for (int f = 0; f < FM; ++f) {
+              const size_t b = (size_t)smp * FM + f;
+              const double rhom = rh[f];
+              double* o = a.out + b * S * 3 * (size_t)a.nk + row;
+              int sidx = 0, icross = 2 * P;
+#pragma unroll
+              for (int u = 0; u < P; ++u)
+#pragma unroll
+                for (int v = u; v < P; ++v) {
+                  const double Iu = acc[r][f * NW + u] * rhom, Iv = acc[r][f * NW + v] * rhom;            // :540-543
+                  const double p2h = __dmul_rn(__dmul_rn(Iu, Iv), plin);                                  // :524
+                  const double p1h = acc[r][f * NW + (u == v ? P + u : icross)] * rhom;                   // :532
+                  if (u != v) ++icross;
+                  o[(size_t)(sidx * 3 + 0) * a.nk] = p2h;
+                  o[(size_t)(sidx * 3 + 1) * a.nk] = p1h;
+                  o[(size_t)(sidx * 3 + 2) * a.nk] = __dadd_rn(p2h, p1h);                                 // :500-501
+                  ++sidx;
+                }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) a.partial[((size_t)smp * NV + j) * (size_t)a.nk + row] = acc[r][j];   // [model][i][row]
+          }
         }
       }
     }
@@ -1250,11 +1297,13 @@ static int hm_make_tmap_2d(CUtensorMap* tm, const double* base, uint64_t cols, u
 }
 
 template <int P, int FM>
-static int hm_launch_rows(hm_quad_args& a, cudaStream_t st) {
+static int hm_launch_rows(hm_quad_args& a, bool fused, cudaStream_t st) {
   using C = hm_rows_cfg<P, FM>;
   static hm_once_per_device once;
   if (once.needed()) {
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_quad_rows_kernel<P, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_quad_rows_kernel<P, FM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::SMEM_BYTES));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_quad_rows_kernel<P, FM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      C::SMEM_BYTES));
   }
   a.ntiles = (a.nk + C::RT - 1) / C::RT;
@@ -1270,21 +1319,22 @@ static int hm_launch_rows(hm_quad_args& a, cudaStream_t st) {
     return rc;
   long long grid = hm_num_sms();
   if (grid > a.nitems) grid = a.nitems;
-  hm_quad_rows_kernel<P, FM><<<(int)grid, HM_ROWS_THREADS, C::SMEM_BYTES, st>>>(a, tmG[0], tmG[1], tmW);
+  if (fused) hm_quad_rows_kernel<P, FM, true><<<(int)grid, HM_ROWS_THREADS, C::SMEM_BYTES, st>>>(a, tmG[0], tmG[1], tmW);
+  else hm_quad_rows_kernel<P, FM, false><<<(int)grid, HM_ROWS_THREADS, C::SMEM_BYTES, st>>>(a, tmG[0], tmG[1], tmW);
   HM_LAUNCH_CHECK();
   return HM_OK;
 }
 
 template <int P, int R>
-static int hm_launch_stream(hm_quad_args& a, cudaStream_t st) {
+static int hm_launch_stream(hm_quad_args& a, bool fused, cudaStream_t st) {
   // two to five models per sample on one or two tracers (the five mass functions of BASELINE config 3) take the
   // row-per-lane kernel, which reads the shared grids once; other combinations read them once per model
   if constexpr (P <= 2) {                                      // must agree with hm_layout.rows
     switch (a.F) {
-      case 2: return hm_launch_rows<P, 2>(a, st);
-      case 3: return hm_launch_rows<P, 3>(a, st);
-      case 4: return hm_launch_rows<P, 4>(a, st);
-      case 5: return hm_launch_rows<P, 5>(a, st);
+      case 2: return hm_launch_rows<P, 2>(a, fused, st);
+      case 3: return hm_launch_rows<P, 3>(a, fused, st);
+      case 4: return hm_launch_rows<P, 4>(a, fused, st);
+      case 5: return hm_launch_rows<P, 5>(a, fused, st);
     }
   }
   if constexpr (P <= 3) {
@@ -1328,6 +1378,11 @@ extern "C" int hm_mass_quadrature_stages(const hm_problem* pr, double* out_dev, 
   }
   a.weights = (const double*)ws;
   a.partial = (double*)ws + L.partial_offset;
+  // sweeps under default flags: the row-per-lane kernel finishes the spectra itself (no partial sums, no epilogue launch)
+  static const bool allow_fused = getenv("HALOB200_NO_FUSED_EPILOGUE") == nullptr;      // (A/B switch for timing runs)
+  const bool fused = allow_fused && L.rows && !pr->simple_twohalo && !(pr->k_trunc > 0.) && !pr->beta_dev &&
+                     !hm_needs_cpart(pr) && !pr->output_is_peer;
+  a.scal = (const double*)ws + L.scal_offset; a.Pk_lin = pr->Pk_lin_dev; a.out = out_dev;
   hm_epi_args e;
   e.nk = pr->nk; e.B = (int)L.B; e.F = pr->models_per_sample; e.P = L.P; e.NW = L.NW; e.S = L.S;
   e.nparts = L.nparts; e.nchunks = L.nchunks + 1; e.rows_layout = L.rows; e.use_cpart = hm_needs_cpart(pr);
@@ -1348,11 +1403,11 @@ extern "C" int hm_mass_quadrature_stages(const hm_problem* pr, double* out_dev, 
 #define HM_CASE(PP, RR)                                                            \
   case PP:                                                                         \
     if (stages & 1) {                                                              \
-      rc = L.stream ? hm_launch_stream<PP, RR>(a, st) : hm_launch_fallback<PP, RR>(a, aligned, sep, st); \
+      rc = L.stream ? hm_launch_stream<PP, RR>(a, fused, st) : hm_launch_fallback<PP, RR>(a, aligned, sep, st); \
       if (rc) return rc;                                                           \
       if (pr->beta_dev && (rc = hm_launch_beta<PP>(bt, (int)L.B, st))) return rc;  \
     }                                                                              \
-    return (stages & 2) ? hm_launch_epilogue<PP>(e, st) : HM_OK;
+    return ((stages & 2) && !fused) ? hm_launch_epilogue<PP>(e, st) : HM_OK;
   switch (L.P) {
     HM_CASE(1, 8)
     HM_CASE(2, 4)

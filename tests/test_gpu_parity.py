@@ -320,13 +320,15 @@ def test_batched_plan_equals_single_models(halo, names, with_gal, shape):
     rng = np.random.default_rng(3)
     cases = [_synthetic_case(nk, nM, z=z, Om_m=Om) for z, Om in [(0., 0.3), (0.7, 0.27), (1.5, 0.33)]]
     k, M = cases[0]['k'], cases[0]['M']
-    models, grids_m, grids_g, amp_g, var_g, norm_g, norm_m, singles = [], [], [], [], [], [], [], []
+    FLAGSETS = ({}, dict(k_trunc=0.2, subtract_shotnoise=False))     # default flags take the fused epilogue of the sweep kernel
+    models, grids_m, grids_g, amp_g, var_g, norm_g, norm_m, singles = [], [], [], [], [], [], [], [[] for _ in FLAGSETS]
     for cs in cases:
         hod = syn.draw_hod(rng)
         for name in names:
             hmod = halo.model(cs['z'], cs['Om_m'], name=name, Dv=cs['Dv'], dc=cs['dc'])
             profs = _gpu_profiles(halo, hmod, cs, [hod] if with_gal else [], False)
-            singles.append(hmod.power_spectrum(k, cs['Pk_lin'], M, cs['sigmaM'], profs))
+            for i, kw in enumerate(FLAGSETS):
+                singles[i].append(hmod.power_spectrum(k, cs['Pk_lin'], M, cs['sigmaM'], profs, **kw))
             models.append(hmod.descriptor())
             norm_m.append(profs['m'].normalisation)
             if with_gal:
@@ -344,17 +346,18 @@ def test_batched_plan_equals_single_models(halo, names, with_gal, shape):
         tr.append(engine.Tracer(torch.stack(grids_g), torch.stack(amp_g), np.array(norm_g), variance=torch.stack(var_g),
                                 mode=_lib.GRID_UK, discrete_tracer=True))
         keys = ['m-m', 'm-g0', 'g0-g0']
-    plan = engine.PowerSpectrumPlan(k, np.stack([c['Pk_lin'] for c in cases]), M, np.stack([c['sigmaM'] for c in cases]),
-                                    tr, models, models_per_sample=len(names))
-    out, A = plan.run()
-    out = out.cpu().numpy()
-    for b, single in enumerate(singles):
-        for s, key in enumerate(keys):
-            for t in range(3):
-                if 2 <= len(names) <= 5:   # fused row-per-lane kernel: same integrals, different summation order
-                    np.testing.assert_allclose(out[b, s, t], single[t][key], rtol=1e-13, atol=0., err_msg=str((b, key, t)))
-                else:
-                    assert np.array_equal(out[b, s, t], single[t][key]), (b, key, t)
+    for i, kw in enumerate(FLAGSETS):
+        plan = engine.PowerSpectrumPlan(k, np.stack([c['Pk_lin'] for c in cases]), M, np.stack([c['sigmaM'] for c in cases]),
+                                        tr, models, models_per_sample=len(names), **kw)
+        out, A = plan.run()
+        out = out.cpu().numpy()
+        for b, single in enumerate(singles[i]):
+            for s, key in enumerate(keys):
+                for t in range(3):
+                    if 2 <= len(names) <= 5:   # fused row-per-lane kernel: same integrals, different summation order
+                        np.testing.assert_allclose(out[b, s, t], single[t][key], rtol=1e-13, atol=0., err_msg=str((b, key, t, kw)))
+                    else:
+                        assert np.array_equal(out[b, s, t], single[t][key]), (b, key, t, kw)
 
 
 def test_fused_sweep_many_items_vs_per_family_plans(halo):
