@@ -46,14 +46,16 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
 // ---------------------------------------------------------------------------------------------------------------
 // Workspace layout (doubles):
 //   weights [B][NW][nMp]            per-mass weight vectors
-//   scal    [B][HM_NSCAL]           A, rhom, w2[0], -, c_p[0] (8): the last two feed the beta_NL edge terms
+//   scal    [B][HM_NSCAL]           A, rhom, w2[0], -, c_p[0] (8): the last two feed the beta_NL edge terms; then the
+//                                   per-(model, tracer) factors of the row-per-lane kernel (see hm_weights_kernel)
 //   inl     [B][S][nk]              non-linear-bias two-halo term I_NL (only when beta is given)
 //   cpart   [B][nchunks+1][2*HM_MAXP] per-mass-chunk partial sums of the shot-noise and simple-two-halo integrals
 //                                   (last slot: the low-mass term of the latter); only written when flags need them
 //   partial [B][nparts][nk][NW]     partial row sums over mass sub-ranges written by the quadrature kernel
 //                                   (streaming kernel: one part per consumer warp per 512-mass slice)
 // ---------------------------------------------------------------------------------------------------------------
-#define HM_NSCAL 12
+#define HM_NSCAL 20          // per model: A, rhom, w2[0], -, c_p[0] (8); row-per-lane sweeps: s_p (2), rn_p^2 (2), low-mass term (2), - (2)
+#define HM_RSCAL 12          // first of the row-per-lane kernel's per-(model, tracer) scalars
 #define HM_WCHUNK 256        // masses per CTA of the weights kernel
 #define HM_MC 512            // masses per slice of the streaming kernel per pair of columns a consumer thread owns
                              // (256 consumer threads x double2); slices are HM_MC or 2*HM_MC wide
@@ -65,6 +67,7 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
 
 struct hm_layout {
   int P, S, NW, nMp, nchunks, nslices, nparts, MC;
+  int NVEC;                  // row-per-lane sweeps: factored weight vectors per SAMPLE (2 F + 2 P)
   bool stream, rows;
   size_t B, scal_offset, cpart_offset, partial_offset, inl_offset, total_bytes;
 };
@@ -96,14 +99,16 @@ static hm_layout hm_make_layout(const hm_problem* pr) {
   // the register budget up to 3 tracers and are used when the mass axis is long enough to fill them
   // two to five mass functions per sample on one or two tracers (BASELINE config 3 has five): the row-per-lane
   // kernel reads the shared grids once for all of them and combines its column groups itself (one part)
-  L.rows = L.stream && pr->models_per_sample >= 2 && pr->models_per_sample <= HM_ROWS_MAXF && L.P <= 2;
+  L.rows = L.stream && pr->models_per_sample >= 2 && pr->models_per_sample <= HM_ROWS_MAXF && L.P <= 2 && !pr->beta_dev;
+  L.NVEC = 2 * pr->models_per_sample + 2 * L.P;
   L.MC = (pr->nM >= 2 * HM_MC && L.P <= 3 && !L.rows) ? 2 * HM_MC : HM_MC;
   L.nslices = L.stream ? (pr->nM + L.MC - 1) / L.MC : 1;
   L.nparts = L.stream ? L.nslices * HM_CONSUMER_WARPS : 1;
   if (L.rows) { L.nslices = 1; L.nparts = 1; }
   L.B = (size_t)pr->n_samples * (size_t)pr->models_per_sample;
   auto align = [](size_t x) { return (x + 31) & ~(size_t)31; };
-  L.scal_offset = align(L.B * (size_t)L.NW * (size_t)L.nMp);
+  const size_t wvecs = L.rows ? (size_t)pr->n_samples * L.NVEC : L.B * (size_t)L.NW;
+  L.scal_offset = align(wvecs * (size_t)L.nMp);
   L.cpart_offset = align(L.scal_offset + L.B * HM_NSCAL);
   L.partial_offset = align(L.cpart_offset + L.B * (size_t)(L.nchunks + 1) * 2 * HM_MAXP);
   L.inl_offset = align(L.partial_offset + L.B * (size_t)L.nparts * L.NW * (size_t)pr->nk);
@@ -113,6 +118,7 @@ static hm_layout hm_make_layout(const hm_problem* pr) {
 
 struct hm_weights_args {
   int nM, nMp, P, NW, F, nchunks;
+  int rows, NVEC;                    // factored layout of the row-per-lane sweep kernel: NVEC vectors per sample
   int correct_discrete;
   const double* M;
   const double* sigma;             // [G][nM]
@@ -133,6 +139,13 @@ struct hm_weights_args {
 // loads of sigma, M, amplitudes and variances, the three divisions behind nu and ln(nu) are shared by the F mass
 // functions (hm_gb_nu_shared) -- and CTA (nchunks, s) integrates the low-mass correction A of each model
 // (pyhalomodel.py:413-414) and owns everything that needs it: e_p[0] with the A W(k,M0)/M0 term, the scalars, A.
+// Factored layout (a.rows; the row-per-lane sweep kernel): every weight vector of the reference is a product of a
+// mass-function part, a tracer part and a per-(model, tracer) scalar,
+//   e_p^f = w2^f * A_p * s_p^f,   d_p^f = w1^f * T_p * (rn_p^f)^2,   q_uv^f = w1^f * A_u A_v * s_u^f s_v^f,
+// with A_p = amplitude (1 for HM_GRID_WK), T_p = <N(N-1)> etc. (divided by amplitude^2 for HM_GRID_WK), rn = 1 /
+// normalisation and s_p = rn (1 for HM_GRID_WK).  The kernel then writes 2 F + 2 P vectors per SAMPLE -- w2^f, w1^f,
+// A_p, T_p -- instead of F (P + S) per sample, and the scalars and the low-mass term A W(k, M0) / M0 (:541-542) go to
+// scal[HM_RSCAL ...]: the sweep kernel applies them once per row at the end of the mass axis.
 // RED: also reduce the shot-noise and simple-two-halo integrals (:423-426, :442-446); only non-default flags read
 // them (hm_epilogue_kernel), so the default path skips the 16 block reductions per model altogether.
 // PT: compile-time bound on the number of tracers (2, 4 or 8).  The kernel is bound by the latency of its FP64
@@ -140,7 +153,7 @@ struct hm_weights_args {
 template <int PT>
 struct hm_fam_consts { hm_model_desc d; hm_family_consts c; double rnorm[PT]; };
 
-template <bool RED, int PT>
+template <bool RED, int PT, bool ROWS>
 #ifndef HM_WMINB
 #define HM_WMINB 4
 #endif
@@ -183,8 +196,14 @@ __global__ void __launch_bounds__(HM_WCHUNK, (PT <= 2) ? HM_WMINB : (PT <= 4 ? 3
           if (p < a.P) {
             const double an = a.amplitude[p][(size_t)s * a.amp_stride[p]] * (1. / a.norm[p][b]);
             cW = (a.mode[p] == HM_GRID_UK) ? an : 1.;
-            wout[(size_t)p * a.nMp] = a.mass[p] ? (w2_plain + Aterm) * cW : w2_plain * cW;   // e_p[0]
+            if (!ROWS) wout[(size_t)p * a.nMp] = a.mass[p] ? (w2_plain + Aterm) * cW : w2_plain * cW;   // e_p[0]
             if (a.mass[p]) low = Aterm * an;
+            if (ROWS && p < 2) {
+              const double rn = 1. / a.norm[p][b];
+              sc[HM_RSCAL + p] = (a.mode[p] == HM_GRID_UK) ? rn : 1.;       // s_p
+              sc[HM_RSCAL + 2 + p] = rn * rn;                               // rn_p^2
+              sc[HM_RSCAL + 4 + p] = a.mass[p] ? Aterm * cW : 0.;           // multiplies G_p(k, M0) in I_p
+            }
           }
           sc[4 + p] = cW;                               // w2[0] and c_p[0]: edge terms of the beta_NL integral
           if (RED) { cp[p] = 0.; cp[HM_MAXP + p] = low; }
@@ -217,6 +236,24 @@ __global__ void __launch_bounds__(HM_WCHUNK, (PT <= 2) ? HM_WMINB : (PT <= 4 ? 3
         if (a.variance[p]) var[p] = a.variance[p][(size_t)s * a.nM + m];
       }
   }
+  if (ROWS && (live || pad)) {
+    // family-independent tracer vectors A_p, T_p of this sample
+    double* wv = a.weights + ((size_t)s * a.NVEC + 2 * a.F) * a.nMp + m;
+#pragma unroll
+    for (int p = 0; p < PT; ++p)
+      if (p < a.P) {
+        double fac = (a.correct_discrete && a.discrete[p]) ? __dmul_rn(amp[p], __dadd_rn(amp[p], -1.))
+                                                           : __dmul_rn(amp[p], amp[p]);
+        if (a.variance[p]) fac = __dadd_rn(fac, var[p]);
+        double A = amp[p], T = fac;
+        if (a.mode[p] != HM_GRID_UK) {
+          const double ra = 1. / amp[p];
+          A = 1.; T = __dmul_rn(fac, ra * ra);
+        }
+        wv[(size_t)p * a.nMp] = live ? A : 0.;
+        wv[(size_t)(a.P + p) * a.nMp] = live ? T : 0.;
+      }
+  }
   double dc_prev = 0., nu = 0., lnnu = 0., tw = 0.;
 #pragma unroll 1
   for (int f = 0; f < a.F; ++f) {
@@ -239,8 +276,11 @@ __global__ void __launch_bounds__(HM_WCHUNK, (PT <= 2) ? HM_WMINB : (PT <= 4 ? 3
     double red[RED ? NRED : 1];
 #pragma unroll
     for (int i = 0; i < (RED ? NRED : 1); ++i) red[i] = 0.;
+    double* wrow = a.weights + ((size_t)s * a.NVEC + f) * a.nMp + m;     // factored layout: w2^f, and w1^f F vectors on
     if (pad) {
-      for (int i = 0; i < a.NW; ++i) wout[(size_t)i * a.nMp + m] = 0.;
+      if (ROWS) { wrow[0] = 0.; wrow[(size_t)a.F * a.nMp] = 0.; }
+      else
+        for (int i = 0; i < a.NW; ++i) wout[(size_t)i * a.nMp + m] = 0.;
     } else if (live) {
       const hm_model_desc& d = fc.d;
       const double dc = d.dc;
@@ -256,11 +296,12 @@ __global__ void __launch_bounds__(HM_WCHUNK, (PT <= 2) ? HM_WMINB : (PT <= 4 ? 3
       hm_gb_nu_shared(d, fc.c, nu, lnnu, g, bg);
       const double w1 = tw * (g * rM);                  // one-halo weight  (:530)
       const double w2_plain = tw * (bg * rM);           // two-halo weight  (:539)
+      if (ROWS) { wrow[0] = w2_plain; wrow[(size_t)a.F * a.nMp] = w1; }
       double cW[PT];
 #pragma unroll
       for (int p = 0; p < PT; ++p) {
         cW[p] = 0.;
-        if (p < a.P) {
+        if (p < a.P && (RED || !ROWS)) {
           const double rnorm = fc.rnorm[p];
           // <N(N-1)> or <N^2> plus variance (:466-473); no FMA contraction so exact zeros stay exact
           double fac = (a.correct_discrete && a.discrete[p]) ? __dmul_rn(amp[p], __dadd_rn(amp[p], -1.))
@@ -271,8 +312,10 @@ __global__ void __launch_bounds__(HM_WCHUNK, (PT <= 2) ? HM_WMINB : (PT <= 4 ? 3
           if (a.mode[p] == HM_GRID_UK) { cW[p] = an; uS = rnorm; }
           else if (a.mode[p] == HM_GRID_WK) { cW[p] = 1.; uS = rnorm / amp[p]; }
           else { cW[p] = 1.; uS = rnorm; }
-          if (m != 0) wout[(size_t)p * a.nMp + m] = w2_plain * cW[p];                      // e_p (e_p[0]: low-mass CTA)
-          wout[(size_t)(a.P + p) * a.nMp + m] = __dmul_rn(__dmul_rn(w1, fac), uS * uS);     // d_p
+          if (!ROWS) {
+            if (m != 0) wout[(size_t)p * a.nMp + m] = w2_plain * cW[p];                    // e_p (e_p[0]: low-mass CTA)
+            wout[(size_t)(a.P + p) * a.nMp + m] = __dmul_rn(__dmul_rn(w1, fac), uS * uS);   // d_p
+          }
           if (RED) {
             red[p] = w1 * (an * rnorm);                                                    // shot noise integrand (:425)
             red[PT + p] = w2_plain * an;                                                   // simple two-halo (:442-446)
@@ -284,7 +327,7 @@ __global__ void __launch_bounds__(HM_WCHUNK, (PT <= 2) ? HM_WMINB : (PT <= 4 ? 3
       for (int u = 0; u < PT; ++u)
 #pragma unroll
         for (int v = u + 1; v < PT; ++v)
-          if (v < a.P) wout[(size_t)(idx++) * a.nMp + m] = w1 * cW[u] * cW[v];                     // q_uv
+          if (v < a.P && !ROWS) wout[(size_t)(idx++) * a.nMp + m] = w1 * cW[u] * cW[v];         // q_uv
     }
     if (RED) {
       // one reduction phase for the 2 PT sums: warp butterflies, then a fixed-order sum over the 8 warps
@@ -645,13 +688,14 @@ struct hm_rows_cfg {
   static constexpr int S = P * (P + 1) / 2;
   static constexpr int NW = P + S;
   static constexpr int NV = FM * NW;                          // sums per grid row
+  static constexpr int NVEC = 2 * FM + 2 * P;                 // factored weight vectors per sample: w2^f, w1^f, A_p, T_p
   static constexpr int CS = HM_ROWS_CS;                       // mass columns per stage
   static constexpr int BOXC = 16;                             // columns per grid box: 128 bytes, the swizzle span
   static constexpr int NBOX = CS / BOXC;
   static constexpr int RT = 64;                               // rows per item
   static constexpr int BOX_BYTES = RT * BOXC * 8;
   static constexpr int DATA_BYTES = P * NBOX * BOX_BYTES;
-  static constexpr int W_BYTES = NV * CS * 8;
+  static constexpr int W_BYTES = NVEC * CS * 8;
   static constexpr int TX_BYTES = DATA_BYTES + W_BYTES;
   static constexpr int STAGE_BYTES = ((TX_BYTES + 1023) / 1024) * 1024;
   static constexpr int COMB_DOUBLES = RT * NV;                // one reader's buffer of the combine tree
@@ -707,7 +751,7 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
     if (lane == 0) {
       for (int it = it0; it < it1; it += istep) {
         const int row = smp * a.nk + tile * RT;             // first row of the item in the [G*nk][nM] tensors
-        const int wrow = smp * NV;                          // first of its weight vectors in the [B*NW][nMp] tensor
+        const int wrow = smp * C::NVEC;                     // first of its weight vectors in the [G*NVEC][nMp] tensor
         for (int st = 0; st < nstages; ++st) {
           const int m0 = st * CS;
           hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);     // slot drained by all consumer warps
@@ -757,35 +801,43 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
           for (int p = 0; p < P; ++p)
             x[r][p] = *reinterpret_cast<const double2*>(stage + (size_t)(p * C::NBOX) * C::BOX_BYTES + r * (32 * 128) +
                                                         (cp == 0 ? xo0 : xo1));
+        // basis values of my two rows and two columns, in the order of the sums: A_p G_p, T_p G_p^2, (A_u G_u)(A_v G_v).
+        // The tracer factors are lane-uniform: broadcast 16-byte loads, like the mass-function weights below.
+        double2 v[2][NW];
 #pragma unroll
-        for (int i = 0; i < NW; ++i) {
-          // basis value i of my two rows and two columns: G_p, G_p^2, G_u G_v in the order of the weight vectors
-          double2 v[2];
+        for (int p = 0; p < P; ++p) {
+          const double2 Av = *reinterpret_cast<const double2*>(wsm + ((2 * FM + p) * CS + 2 * cp) * 8);
+          const double2 Tv = *reinterpret_cast<const double2*>(wsm + ((2 * FM + P + p) * CS + 2 * cp) * 8);
 #pragma unroll
           for (int r = 0; r < 2; ++r) {
-            if (i < P) {
-              v[r] = x[r][i];
-            } else if (i < 2 * P) {
-              v[r] = make_double2(x[r][i - P].x * x[r][i - P].x, x[r][i - P].y * x[r][i - P].y);
-            } else {
-              int idx = 2 * P, uu = 0, vv = 1;
-#pragma unroll
-              for (int u = 0; u < P; ++u)
-#pragma unroll
-                for (int w = u + 1; w < P; ++w) {
-                  if (idx == i) { uu = u; vv = w; }
-                  ++idx;
-                }
-              v[r] = make_double2(x[r][uu].x * x[r][vv].x, x[r][uu].y * x[r][vv].y);
-            }
+            v[r][p] = make_double2(Av.x * x[r][p].x, Av.y * x[r][p].y);
+            // no FMA contraction and T first: T = 0 (e.g. central galaxies) keeps the sum an exact zero
+            v[r][P + p] = make_double2(__dmul_rn(__dmul_rn(Tv.x, x[r][p].x), x[r][p].x),
+                                       __dmul_rn(__dmul_rn(Tv.y, x[r][p].y), x[r][p].y));
           }
+        }
+        {
+          int idx = 2 * P;
 #pragma unroll
-          for (int f = 0; f < FM; ++f) {
-            const double2 w2 = *reinterpret_cast<const double2*>(wsm + ((f * NW + i) * CS + 2 * cp) * 8);   // broadcast
+          for (int u = 0; u < P; ++u)
+#pragma unroll
+            for (int w = u + 1; w < P; ++w) {
+#pragma unroll
+              for (int r = 0; r < 2; ++r) v[r][idx] = make_double2(v[r][u].x * v[r][w].x, v[r][u].y * v[r][w].y);
+              ++idx;
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < FM; ++f) {
+          const double2 w2 = *reinterpret_cast<const double2*>(wsm + (f * CS + 2 * cp) * 8);            // two-halo weight
+          const double2 w1 = *reinterpret_cast<const double2*>(wsm + ((FM + f) * CS + 2 * cp) * 8);     // one-halo weight
+#pragma unroll
+          for (int i = 0; i < NW; ++i) {
+            const double2 w = (i < P) ? w2 : w1;
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
-              acc[r][f * NW + i] = fma(w2.x, v[r].x, acc[r][f * NW + i]);
-              acc[r][f * NW + i] = fma(w2.y, v[r].y, acc[r][f * NW + i]);
+              acc[r][f * NW + i] = fma(w.x, v[r][i].x, acc[r][f * NW + i]);
+              acc[r][f * NW + i] = fma(w.y, v[r][i].y, acc[r][f * NW + i]);
             }
           }
         }
@@ -795,18 +847,20 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
       if (++s == NS) { s = 0; parity ^= 1u; }
     }
 
-    // ---- combine the eight column groups: binary tree over the warps, pipelined with the next item.  Reader r owns
-    // buffer r; writer x signals pfull[x] once per item and reader drains it with pempty[x], so every pair barrier
-    // completes exactly one phase per item.  A writer waits until the previous occupant of its target buffer has been
-    // drained: the previous writer of this item, or the buffer's last writer of the previous item. ----
+    // ---- combine the eight column groups: binary tree over the warps, pipelined with the next item.  The tree runs on
+    // VIRTUAL warp numbers vw = (warp - item) mod 8, so the root -- which reads three buffers, applies the per-model
+    // factors and stores the item -- is a different warp every item and no warp is the slowest on average.  Reader r
+    // owns buffer r; writer x signals pfull[x] once per item and its reader drains it with pempty[x], so every pair
+    // barrier completes exactly one phase per item whoever plays the role.  A writer waits until the previous occupant
+    // of its target buffer has been drained: the previous writer of this item, or the buffer's last writer of the
+    // previous item. ----
     const uint32_t ph = item_no & 1u;
-    // (fused epilogue) the root warp fetches the per-model scalars and P_lin of its rows now, so that the loads fly
-    // while it waits for the other warps' sums instead of serialising behind the last hand-over
-    double rh[FUSED ? FM : 1], pl[2] = {0., 0.};
+    const int vw = (int)((warp - item_no) & 7u);
+    // (fused epilogue) the root warp fetches P_lin of its rows now, so that the loads fly while it waits for the other
+    // warps' sums instead of serialising behind the last hand-over
+    double pl[2] = {0., 0.};
     if constexpr (FUSED) {
-      if (warp == 0) {
-#pragma unroll
-        for (int f = 0; f < FM; ++f) rh[f] = a.scal[((size_t)smp * FM + f) * HM_NSCAL + 1];
+      if (vw == 0) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           const int row = tile * RT + r * 32 + lane;
@@ -816,21 +870,21 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
     }
 #pragma unroll
     for (int step = 4; step >= 1; step >>= 1) {
-      if (warp < step) {
-        const int xw = warp + step;
+      if (vw < step) {
+        const int xw = vw + step;
         hm_mbar_wait(bar_pfull + 8 * xw, ph);
-        const double* src = comb + (size_t)warp * C::COMB_DOUBLES + lane;
+        const double* src = comb + (size_t)vw * C::COMB_DOUBLES + lane;
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
           for (int j = 0; j < NV; ++j) acc[r][j] += src[j * 64 + r * 32];
         __syncwarp();
         if (lane == 0) hm_mbar_arrive(bar_pempty + 8 * xw);
-      } else if (warp < 2 * step) {
-        const int t = warp - step;
+      } else if (vw < 2 * step) {
+        const int t = vw - step;
         int pred;
         uint32_t pph;
-        if (step == 4) { pred = (t == 0) ? 1 : (t == 1) ? 3 : warp; pph = ph ^ 1u; }
+        if (step == 4) { pred = (t == 0) ? 1 : (t == 1) ? 3 : vw; pph = ph ^ 1u; }
         else if (step == 2) { pred = t + 4; pph = ph; }
         else { pred = 2; pph = ph; }
         hm_mbar_wait(bar_pempty + 8 * pred, pph);
@@ -840,42 +894,69 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
 #pragma unroll
           for (int j = 0; j < NV; ++j) dst[j * 64 + r * 32] = acc[r][j];
         __syncwarp();
-        if (lane == 0) hm_mbar_arrive(bar_pfull + 8 * warp);
+        if (lane == 0) hm_mbar_arrive(bar_pfull + 8 * vw);
       }
     }
-    if (warp == 0) {      // the item's RT x NV sums, coalesced over rows
+    if (vw == 0) {      // the item's RT x NV sums, coalesced over rows
+      constexpr int S = C::S;
+      // first mass column of my rows: the low-mass term A W(k, M0) / M0 of mass tracers (:541-542)
+      double g0[2][P];
 #pragma unroll
       for (int r = 0; r < 2; ++r) {
         const int row = tile * RT + r * 32 + lane;
-        if (row < a.nk) {
-          if constexpr (FUSED) {
-            // default flags (no beta_NL, simple two-halo, k_trunc or shot-noise fix-up): the spectra follow from the
-            // sums directly, with the arithmetic of hm_epilogue_kernel (pyhalomodel.py:456-501)
-            constexpr int S = C::S;
-            const double plin = pl[r];
 #pragma unroll
-            for (int f = 0; f < FM; ++f) {
-              const size_t b = (size_t)smp * FM + f;
-              const double rhom = rh[f];
+        for (int p = 0; p < P; ++p)
+          g0[r][p] = a.gridW[p][((size_t)smp * a.nk + (row < a.nk ? row : a.nk - 1)) * (size_t)a.nM];
+      }
+#pragma unroll
+      for (int f = 0; f < FM; ++f) {
+        const size_t b = (size_t)smp * FM + f;
+        const double* sc = a.scal + b * HM_NSCAL;
+        const double rhom = sc[1];
+        double sp[P], rn2[P], low[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) { sp[p] = sc[HM_RSCAL + p]; rn2[p] = sc[HM_RSCAL + 2 + p]; low[p] = sc[HM_RSCAL + 4 + p]; }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int row = tile * RT + r * 32 + lane;
+          // the per-(model, tracer) factors the factored weights left out (hm_weights_kernel)
+          double* t = &acc[r][f * NW];
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            t[p] = fma(low[p], g0[r][p], t[p] * sp[p]);
+            t[P + p] = __dmul_rn(t[P + p], rn2[p]);
+          }
+          {
+            int idx = 2 * P;
+#pragma unroll
+            for (int u = 0; u < P; ++u)
+#pragma unroll
+              for (int w = u + 1; w < P; ++w) t[idx++] *= sp[u] * sp[w];
+          }
+          if (row < a.nk) {
+            if constexpr (FUSED) {
+              // default flags (no beta_NL, simple two-halo, k_trunc or shot-noise fix-up): the spectra follow from the
+              // sums directly, with the arithmetic of hm_epilogue_kernel (pyhalomodel.py:456-501)
+              const double plin = pl[r];
               double* o = a.out + b * S * 3 * (size_t)a.nk + row;
               int sidx = 0, icross = 2 * P;
 #pragma unroll
               for (int u = 0; u < P; ++u)
 #pragma unroll
                 for (int v = u; v < P; ++v) {
-                  const double Iu = acc[r][f * NW + u] * rhom, Iv = acc[r][f * NW + v] * rhom;            // :540-543
+                  const double Iu = t[u] * rhom, Iv = t[v] * rhom;                                        // :540-543
                   const double p2h = __dmul_rn(__dmul_rn(Iu, Iv), plin);                                  // :524
-                  const double p1h = acc[r][f * NW + (u == v ? P + u : icross)] * rhom;                   // :532
+                  const double p1h = t[u == v ? P + u : icross] * rhom;                                   // :532
                   if (u != v) ++icross;
                   o[(size_t)(sidx * 3 + 0) * a.nk] = p2h;
                   o[(size_t)(sidx * 3 + 1) * a.nk] = p1h;
                   o[(size_t)(sidx * 3 + 2) * a.nk] = __dadd_rn(p2h, p1h);                                 // :500-501
                   ++sidx;
                 }
-            }
-          } else {
+            } else {
 #pragma unroll
-            for (int j = 0; j < NV; ++j) a.partial[((size_t)smp * NV + j) * (size_t)a.nk + row] = acc[r][j];   // [model][i][row]
+              for (int i = 0; i < NW; ++i) a.partial[(b * NW + i) * (size_t)a.nk + row] = t[i];           // [model][i][row]
+            }
           }
         }
       }
@@ -1187,6 +1268,7 @@ extern "C" int hm_halo_weights(const hm_problem* pr, double* lowmass_dev, void* 
   if ((rc = hm_check_workspace("hm_halo_weights", L, ws, ws_bytes))) return rc;
   hm_weights_args a;
   a.nM = pr->nM; a.nMp = L.nMp; a.P = L.P; a.NW = L.NW; a.F = pr->models_per_sample; a.nchunks = L.nchunks;
+  a.rows = L.rows; a.NVEC = L.NVEC;
   a.correct_discrete = pr->correct_discrete;
   a.M = pr->M_dev; a.sigma = pr->sigma_dev; a.models = pr->models_dev; a.single = pr->model_host;
   for (int p = 0; p < HM_MAXP; ++p) {
@@ -1205,14 +1287,15 @@ extern "C" int hm_halo_weights(const hm_problem* pr, double* lowmass_dev, void* 
   dim3 grid(L.nchunks + 1, (unsigned)pr->n_samples);
   const bool red = hm_needs_cpart(pr);
   cudaStream_t st = (cudaStream_t)stream;
-#define HM_WLAUNCH(PT)                                                        \
-  do {                                                                        \
-    if (red) hm_weights_kernel<true, PT><<<grid, HM_WCHUNK, 0, st>>>(a);      \
-    else hm_weights_kernel<false, PT><<<grid, HM_WCHUNK, 0, st>>>(a);         \
+#define HM_WLAUNCH(PT, ROWS)                                                    \
+  do {                                                                          \
+    if (red) hm_weights_kernel<true, PT, ROWS><<<grid, HM_WCHUNK, 0, st>>>(a);  \
+    else hm_weights_kernel<false, PT, ROWS><<<grid, HM_WCHUNK, 0, st>>>(a);     \
   } while (0)
-  if (L.P <= 2) HM_WLAUNCH(2);
-  else if (L.P <= 4) HM_WLAUNCH(4);
-  else HM_WLAUNCH(8);
+  if (L.rows) HM_WLAUNCH(2, true);
+  else if (L.P <= 2) HM_WLAUNCH(2, false);
+  else if (L.P <= 4) HM_WLAUNCH(4, false);
+  else HM_WLAUNCH(8, false);
 #undef HM_WLAUNCH
   HM_LAUNCH_CHECK();
   return HM_OK;
@@ -1315,7 +1398,7 @@ static int hm_launch_rows(hm_quad_args& a, bool fused, cudaStream_t st) {
     if ((rc = hm_make_tmap_2d(&tmG[p], a.gridW[p < P ? p : 0], (uint64_t)a.nM, (uint64_t)G * a.nk, (uint64_t)a.nM, C::BOXC,
                               C::RT, true)))
       return rc;
-  if ((rc = hm_make_tmap_2d(&tmW, a.weights, (uint64_t)a.nMp, (uint64_t)a.B * C::NW, (uint64_t)a.nMp, C::CS, C::NV, false)))
+  if ((rc = hm_make_tmap_2d(&tmW, a.weights, (uint64_t)a.nMp, (uint64_t)G * C::NVEC, (uint64_t)a.nMp, C::CS, C::NVEC, false)))
     return rc;
   long long grid = hm_num_sms();
   if (grid > a.nitems) grid = a.nitems;
@@ -1326,11 +1409,11 @@ static int hm_launch_rows(hm_quad_args& a, bool fused, cudaStream_t st) {
 }
 
 template <int P, int R>
-static int hm_launch_stream(hm_quad_args& a, bool fused, cudaStream_t st) {
+static int hm_launch_stream(hm_quad_args& a, bool rows, bool fused, cudaStream_t st) {
   // two to five models per sample on one or two tracers (the five mass functions of BASELINE config 3) take the
   // row-per-lane kernel, which reads the shared grids once; other combinations read them once per model
-  if constexpr (P <= 2) {                                      // must agree with hm_layout.rows
-    switch (a.F) {
+  if constexpr (P <= 2) {
+    if (rows) switch (a.F) {
       case 2: return hm_launch_rows<P, 2>(a, fused, st);
       case 3: return hm_launch_rows<P, 3>(a, fused, st);
       case 4: return hm_launch_rows<P, 4>(a, fused, st);
@@ -1403,7 +1486,7 @@ extern "C" int hm_mass_quadrature_stages(const hm_problem* pr, double* out_dev, 
 #define HM_CASE(PP, RR)                                                            \
   case PP:                                                                         \
     if (stages & 1) {                                                              \
-      rc = L.stream ? hm_launch_stream<PP, RR>(a, fused, st) : hm_launch_fallback<PP, RR>(a, aligned, sep, st); \
+      rc = L.stream ? hm_launch_stream<PP, RR>(a, L.rows, fused, st) : hm_launch_fallback<PP, RR>(a, aligned, sep, st); \
       if (rc) return rc;                                                           \
       if (pr->beta_dev && (rc = hm_launch_beta<PP>(bt, (int)L.B, st))) return rc;  \
     }                                                                              \
