@@ -62,7 +62,9 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
 #define HM_CONSUMER_WARPS 8
 #define HM_STREAM_THREADS (32 * (HM_CONSUMER_WARPS + 1))
 #define HM_ROWS_CS 32        // row-per-lane kernel: mass columns per stage (four per consumer warp)
-#define HM_ROWS_THREADS (32 * (HM_CONSUMER_WARPS + 1))
+#define HM_ROWS_THREADS (32 * (HM_CONSUMER_WARPS + 4))   // two consumer warpgroups + the producer's warpgroup (setmaxnreg)
+#define HM_ROWS_PRODUCER_REGS 24
+#define HM_ROWS_CONSUMER_REGS 232
 #define HM_ROWS_MAXF 5       // ... for 2..5 models per sample on one or two tracers
 
 struct hm_layout {
@@ -746,9 +748,13 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
   int s = 0;
   uint32_t parity = 0;
 
-  if (warp == HM_CONSUMER_WARPS) {
+  if (warp >= HM_CONSUMER_WARPS) {
     // ---------------------------------- producer: one lane drives the TMA unit ----------------------------------
-    if (lane == 0) {
+    // Its warpgroup hands its registers back first: twelve warps at the launch bound of 168 registers fill the SM's
+    // register file, and what the producer's four warps release lets the consumers grow to 232 (setmaxnreg below),
+    // room for the 100 accumulators plus the operands of the next column pair in flight.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HM_ROWS_PRODUCER_REGS));
+    if (warp == HM_CONSUMER_WARPS && lane == 0) {
       for (int it = it0; it < it1; it += istep) {
         const int row = smp * a.nk + tile * RT;             // first row of the item in the [G*nk][nM] tensors
         const int wrow = smp * C::NVEC;                     // first of its weight vectors in the [G*NVEC][nMp] tensor
@@ -774,6 +780,7 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
   }
 
   // ------------------------------------------- consumer warps --------------------------------------------------
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(HM_ROWS_CONSUMER_REGS));
   // my four columns of a stage: 4*warp .. 4*warp + 3 = 16-byte chunks q0, q0 + 1 of box warp / 4; inside a box the
   // chunk index is XORed with (row & 7) (SWIZZLE_128B)
   const uint32_t boxoff = (uint32_t)(warp >> 2) * C::BOX_BYTES + (uint32_t)lane * 128u;

@@ -381,17 +381,25 @@ class PowerSpectrumPlan:
                                       self.workspace_bytes, _stream()))
         return dst, self.lowmass
 
+    def weight_vectors(self):
+        """Per-mass weight vectors the quadrature kernel reads: P + S per model, or -- sweeps of 2..5 mass functions on
+        one or two tracers, where the weights are kept factored (hm_quad.cu) -- 2 F + 2 P per sample."""
+        F = self.B//self.G
+        rows = (2 <= F <= 5 and self.P <= 2 and self.nM % 2 == 0 and self.beta is None
+                and all(t.mode != _lib.GRID_SEPARATE for t in self.tracers))
+        return self.G*(2*F+2*self.P) if rows else self.B*(self.P+self.S)
+
     def stream_kernel_bytes(self):
-        """Algorithmic bytes of the streaming quadrature kernel alone: every distinct grid once plus the weight
-        vectors of every model once (its partial-sum writes are an implementation artefact and not counted)."""
+        """Algorithmic bytes of the streaming quadrature kernel alone: every distinct grid once plus its weight
+        vectors once (its partial-sum writes are an implementation artefact and not counted)."""
         ngrids = sum(2 if t.mode == _lib.GRID_SEPARATE else 1 for t in self.tracers)
-        return 8*(self.G*ngrids*self.nk*self.nM + self.B*(self.P+self.S)*self.nM)
+        return 8*(self.G*ngrids*self.nk*self.nM + self.weight_vectors()*self.nM)
 
     def algorithmic_bytes(self):
         """Bytes the quadrature kernel must move per launch: every distinct grid once, the weight vectors once
         per model, P_lin once per sample, three output vectors per unique pair."""
         ngrids = sum(2 if t.mode == _lib.GRID_SEPARATE else 1 for t in self.tracers)
-        return 8*(self.G*ngrids*self.nk*self.nM + self.B*(self.P+self.S)*self.nM + self.G*self.nk
+        return 8*(self.G*ngrids*self.nk*self.nM + self.weight_vectors()*self.nM + self.G*self.nk
                   + self.B*3*self.S*self.nk)
 
 
