@@ -509,7 +509,10 @@ struct hm_stream_cfg {
   static constexpr int STAGE_DOUBLES = R * P * MC;
   static constexpr int STAGE_BYTES = STAGE_DOUBLES * 8;
   static constexpr int BUDGET = 226 * 1024 - 256;
-  static constexpr int NS = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
+#ifndef HM_ROWS_NS_MAX
+#define HM_ROWS_NS_MAX 8
+#endif
+  static constexpr int NS = (BUDGET / STAGE_BYTES) > HM_ROWS_NS_MAX ? HM_ROWS_NS_MAX : (BUDGET / STAGE_BYTES);
   static constexpr int SMEM_BYTES = NS * STAGE_BYTES + 256;
 };
 
@@ -701,10 +704,17 @@ struct hm_rows_cfg {
   static constexpr int TX_BYTES = DATA_BYTES + W_BYTES;
   static constexpr int STAGE_BYTES = ((TX_BYTES + 1023) / 1024) * 1024;
   static constexpr int COMB_DOUBLES = RT * NV;                // one reader's buffer of the combine tree
+#ifdef HM_ROWS_DEBUG_NO_COMBINE
+  static constexpr int COMB_BYTES = 0;
+#else
   static constexpr int COMB_BYTES = 4 * COMB_DOUBLES * 8;
+#endif
   static constexpr int BAR_BYTES = 256;
   static constexpr int BUDGET = 227 * 1024 - BAR_BYTES - COMB_BYTES - 1024;   // 1024: alignment slack of the ring
-  static constexpr int NS = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
+#ifndef HM_ROWS_NS_MAX
+#define HM_ROWS_NS_MAX 8
+#endif
+  static constexpr int NS = (BUDGET / STAGE_BYTES) > HM_ROWS_NS_MAX ? HM_ROWS_NS_MAX : (BUDGET / STAGE_BYTES);
   static constexpr int SMEM_BYTES = NS * STAGE_BYTES + COMB_BYTES + BAR_BYTES + 1024;
   static_assert(CS == 4 * HM_CONSUMER_WARPS, "a consumer warp owns four columns of a stage");
   static_assert(NS >= 2, "the ring needs two stages");
@@ -788,6 +798,7 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
   const uint32_t xo0 = boxoff + (((q0) ^ sw) << 4), xo1 = boxoff + (((q0 + 1u) ^ sw) << 4);
   const uint32_t wcol = 4u * warp * 8u;                            // byte offset of my columns in a weight row
   uint32_t item_no = 0;
+  uint32_t landed = 0;                                        // the early probe of the current stage's barrier succeeded
   for (int it = it0; it < it1; it += istep, ++item_no) {
     double acc[2][NV];
 #pragma unroll
@@ -798,9 +809,14 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
     for (int st = 0; st < nstages; ++st) {
       const unsigned char* stage = smem_raw + (size_t)s * C::STAGE_BYTES;
       const unsigned char* wsm = stage + C::DATA_BYTES + wcol;
-      hm_mbar_wait(bar_full + 8 * s, parity);                 // the stage's boxes have landed
+      if (!landed) hm_mbar_wait(bar_full + 8 * s, parity);    // the stage's boxes have landed
+      const int sn = (s + 1 == NS) ? 0 : s + 1;
+      const uint32_t pn = (s + 1 == NS) ? parity ^ 1u : parity;
 #pragma unroll
       for (int cp = 0; cp < 2; ++cp) {
+        // The barrier probe takes a few hundred cycles to answer even when the data is there: ask about the NEXT stage
+        // in the middle of this one (the ring runs on across items; past the last stage the answer is never used)
+        if (cp == 1) landed = hm_mbar_test(bar_full + 8 * sn, pn);
         double2 x[2][P];                                      // [row][tracer] of this column pair
 #pragma unroll
         for (int r = 0; r < 2; ++r)
@@ -851,7 +867,7 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
       }
       __syncwarp();
       if (lane == 0) hm_mbar_arrive(bar_empty + 8 * s);       // my reads of the slot are done
-      if (++s == NS) { s = 0; parity ^= 1u; }
+      s = sn; parity = pn;
     }
 
     // ---- combine the eight column groups: binary tree over the warps, pipelined with the next item.  The tree runs on
@@ -875,6 +891,9 @@ __global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const 
         }
       }
     }
+#ifdef HM_ROWS_DEBUG_NO_COMBINE
+    if (false)
+#endif
 #pragma unroll
     for (int step = 4; step >= 1; step >>= 1) {
       if (vw < step) {
