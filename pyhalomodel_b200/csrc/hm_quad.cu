@@ -354,6 +354,150 @@ __global__ void __launch_bounds__(HM_WCHUNK, (PT <= 2) ? HM_WMINB : (PT <= 4 ? 3
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Weights of a sweep in the factored layout under default flags (no shot-noise / simple two-halo reductions): the
+// sweep's own kernel.  hm_weights_kernel is straight-line code -- one pass over ~2300 instructions per warp, five
+// inlined family bodies -- and ncu shows it waiting for instructions (27 % of its stall samples) and for the eight
+// threads that prepare the per-model constants behind a CTA barrier (13 %).  Here a thread owns FOUR masses, so that
+// each family body runs as a loop (fetched once, executed four times), the constants are prepared by the first F
+// threads WHILE the others do the family-independent part (nu, ln nu, the trapezoid weight, the tracer vectors), and
+// CTAs are small (128 threads, 512 masses): 1024 of them for 512 samples spread evenly over the SMs in one wave.
+// grid (ceil(nMp / 512) + 1, G); the last CTA of a sample integrates the low-mass corrections (as in hm_weights_kernel).
+// ---------------------------------------------------------------------------------------------------------------
+#define HM_WS_THREADS 128
+#define HM_WS_PER 4
+__global__ void __launch_bounds__(HM_WS_THREADS, 7) hm_weights_sweep_kernel(const hm_weights_args a) {
+  constexpr int PT = 2;
+  __shared__ hm_fam_consts<PT> sfc[HM_ROWS_MAXF];
+  const int s = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double* sig = a.sigma + (size_t)s * a.nM;
+  const double M0 = a.M[0];
+
+  if (chunk == (int)gridDim.x - 1) {
+    // ---- low-mass CTA: warp w integrates model w, w + 4, ... (pyhalomodel.py:413-414) and writes the model's scalars
+    const double sg0 = sig[0], sg1 = sig[1];
+    for (int f = warp; f < a.F; f += HM_WS_THREADS / 32) {
+      const int b = s * a.F + f;
+      const hm_model_desc d = a.models ? a.models[b] : a.single;
+      const double nu = d.dc / sg0;
+      double part = 0.;
+#pragma unroll 1
+      for (int j = 0; j < HM_GL_NODES / 32; ++j) part += hm_lowmass_node(d, nu, lane + 32 * j);
+      const double A = 1. - hm_warp_sum(part);
+      if (lane == 0) {
+        const double Aterm = A / M0;                    // multiplies W(k, M[0]) for mass tracers (:541-542)
+        const double nu_hi = d.dc / sg1;
+        const double tw = 0.5 * (nu_hi - nu);
+        const hm_family_consts c = hm_make_family_consts(d);
+        double g, bg;
+        hm_gb_nu_shared(d, c, nu, log(nu), g, bg);
+        double* sc = a.scal + (size_t)b * HM_NSCAL;
+        for (int p = 0; p < HM_MAXP; ++p) {
+          double cW = 0.;
+          if (p < a.P) {
+            const double rn = 1. / a.norm[p][b];
+            const double an = a.amplitude[p][(size_t)s * a.amp_stride[p]] * rn;
+            cW = (a.mode[p] == HM_GRID_UK) ? an : 1.;
+            if (p < 2) {
+              sc[HM_RSCAL + p] = (a.mode[p] == HM_GRID_UK) ? rn : 1.;       // s_p
+              sc[HM_RSCAL + 2 + p] = rn * rn;                               // rn_p^2
+              sc[HM_RSCAL + 4 + p] = a.mass[p] ? Aterm * cW : 0.;           // multiplies G_p(k, M0) in I_p
+            }
+          }
+          sc[4 + p] = cW;
+        }
+        sc[0] = A;
+        sc[1] = d.rhom;
+        sc[2] = tw * (bg * (1. / M0));
+        if (a.lowmass) a.lowmass[b] = A;
+      }
+    }
+    return;
+  }
+
+  if (tid < a.F) {                                      // per-model constants: ready when the others reach the barrier
+    const hm_model_desc dm = a.models ? a.models[s * a.F + tid] : a.single;
+    sfc[tid].d = dm;
+    sfc[tid].c = hm_make_family_consts(dm);
+  }
+  // ---- family-independent part of my four masses: nu, ln nu and tw / M wait in shared memory (column tid: no bank
+  // conflicts), so that the family loop below can run over them with a rolled loop and few registers ----
+  __shared__ double s_nu[HM_WS_PER][HM_WS_THREADS], s_ln[HM_WS_PER][HM_WS_THREADS], s_tw[HM_WS_PER][HM_WS_THREADS];
+  const double dc0 = a.models ? a.models[(size_t)s * a.F].dc : a.single.dc;
+  const int m0 = chunk * (HM_WS_THREADS * HM_WS_PER) + tid;
+  auto shared_part = [&](double dc) {                  // (rolled loops: this kernel waits for instructions, not for results)
+#pragma unroll 1
+    for (int j = 0; j < HM_WS_PER; ++j) {
+      const int m = m0 + j * HM_WS_THREADS;
+      const bool live = m < a.nM;
+      const double sg = live ? sig[m] : 1.;
+      const double sg_hi = (live && m + 1 < a.nM) ? sig[m + 1] : sg;
+      const double sg_lo = (live && m > 0) ? sig[m - 1] : sg;
+      const double rM = live ? 1. / a.M[m] : 0.;
+      const double nu = dc / sg;
+      // trapezoid rule in nu as a weight (scipy trapezoid, :27); one-sided at the ends, where the missing neighbour is
+      // the mass itself (dc / sg is nu bit for bit)
+      const double tw = 0.5 * (dc / sg_hi - dc / sg_lo);
+      s_nu[j][tid] = nu;
+      s_ln[j][tid] = log(nu);
+      s_tw[j][tid] = tw * rM;
+    }
+  };
+  shared_part(dc0);
+  // tracer vectors A_p, T_p of this sample (see hm_weights_kernel)
+#pragma unroll 1
+  for (int j = 0; j < HM_WS_PER; ++j) {
+    const int m = m0 + j * HM_WS_THREADS;
+    if (m < a.nMp) {
+      const bool live = m < a.nM;
+      double* wv = a.weights + ((size_t)s * a.NVEC + 2 * a.F) * a.nMp + m;
+#pragma unroll
+      for (int p = 0; p < PT; ++p)
+        if (p < a.P) {
+          double A = 0., T = 0.;
+          if (live) {
+            const double amp = a.amplitude[p][(size_t)s * a.amp_stride[p] + m];
+            double fac = (a.correct_discrete && a.discrete[p]) ? __dmul_rn(amp, __dadd_rn(amp, -1.)) : __dmul_rn(amp, amp);
+            if (a.variance[p]) fac = __dadd_rn(fac, a.variance[p][(size_t)s * a.nM + m]);
+            A = amp; T = fac;
+            if (a.mode[p] != HM_GRID_UK) {
+              const double ra = 1. / amp;
+              A = 1.; T = __dmul_rn(fac, ra * ra);
+            }
+          }
+          wv[(size_t)p * a.nMp] = A;
+          wv[(size_t)(a.P + p) * a.nMp] = T;
+        }
+    }
+  }
+  __syncthreads();
+  double dc_cur = dc0;
+#pragma unroll 1
+  for (int f = 0; f < a.F; ++f) {
+    const hm_fam_consts<PT>& fc = sfc[f];
+    const double dc = fc.d.dc;
+    if (dc != dc_cur) {                                 // models of one sample usually share delta_c
+      shared_part(dc);
+      dc_cur = dc;
+    }
+    double* wrow = a.weights + ((size_t)s * a.NVEC + f) * a.nMp;
+#pragma unroll 1
+    for (int j = 0; j < HM_WS_PER; ++j) {
+      const int m = m0 + j * HM_WS_THREADS;
+      if (m < a.nM) {
+        double g, bg;
+        hm_gb_nu_shared(fc.d, fc.c, s_nu[j][tid], s_ln[j][tid], g, bg);
+        const double twM = s_tw[j][tid];
+        wrow[m] = twM * bg;                                              // w2: two-halo weight  (:539)
+        wrow[(size_t)a.F * a.nMp + m] = twM * g;                         // w1: one-halo weight  (:530)
+      } else if (m < a.nMp) {
+        wrow[m] = 0.; wrow[(size_t)a.F * a.nMp + m] = 0.;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Shared pieces of the two quadrature kernels
 // ---------------------------------------------------------------------------------------------------------------
 struct hm_quad_args {
@@ -1318,7 +1462,11 @@ extern "C" int hm_halo_weights(const hm_problem* pr, double* lowmass_dev, void* 
     if (red) hm_weights_kernel<true, PT, ROWS><<<grid, HM_WCHUNK, 0, st>>>(a);  \
     else hm_weights_kernel<false, PT, ROWS><<<grid, HM_WCHUNK, 0, st>>>(a);     \
   } while (0)
-  if (L.rows) HM_WLAUNCH(2, true);
+  static const bool no_sweep_kernel = getenv("HALOB200_NO_SWEEP_WEIGHTS") != nullptr;      // (A/B switch for timing runs)
+  if (L.rows && !red && !no_sweep_kernel) {
+    dim3 gs((L.nMp + HM_WS_THREADS * HM_WS_PER - 1) / (HM_WS_THREADS * HM_WS_PER) + 1, (unsigned)pr->n_samples);
+    hm_weights_sweep_kernel<<<gs, HM_WS_THREADS, 0, st>>>(a);
+  } else if (L.rows) HM_WLAUNCH(2, true);
   else if (L.P <= 2) HM_WLAUNCH(2, false);
   else if (L.P <= 4) HM_WLAUNCH(4, false);
   else HM_WLAUNCH(8, false);
