@@ -22,17 +22,20 @@
 #include "hm_common.cuh"
 
 #define HM_GMAXP HM_GRAM_MAX_TRACERS
-#define HM_GMCH 32                 // masses per chunk
-#define HM_GLD (HM_GMCH + 8)       // padded row stride of the tile: 320 B = 64 mod 128, so the 16-byte DMMA
-                                   // fragment loads of a quarter warp (2 rows x 4 lanes) hit all 32 banks once
-#define HM_GNBUF 5                 // tile buffers (40 KB each at 64 tracer rows x 2 wavenumbers) ...
-#define HM_GDEPTH 3                // ... of which this many are in flight from HBM ahead of the one being scaled
+#define HM_GMCH 32                 // masses per chunk = one stage of the ring (256-byte row segments)
+#define HM_GRK 4                   // wavenumbers per group; two MMA warps share a wavenumber
+#define HM_GMMA_WARPS (2 * HM_GRK)
+#define HM_GNS 3                   // stages (64 KB each at 64 tracers)
+#define HM_GPROD_WARPS 4
+#define HM_GTHREADS (32 * (HM_GMMA_WARPS + HM_GPROD_WARPS))
+#define HM_GPROD_REGS 40
+#define HM_GMMA_REGS 232
 #define HM_GNSCAL 4
 #define HM_GNTS 3                  // per (model, tracer) scalars: shot noise, simple two-halo integral, c_p[M0]
-#define HM_GWARPS 8
 
 struct hm_gram_layout {
-  int P, NB, PT, S, NW, nMp, nchunks, nparts, MP, RK, ntiles;
+  int P, NB, PT, S, NW, nMp, nchunks, ngroups, CH, ncta, J;
+  long long total;
   size_t B, gw_stride, scal_offset, tscal_offset, partial_offset, total_bytes;
 };
 
@@ -45,23 +48,21 @@ static hm_gram_layout hm_gram_make_layout(const hm_gram_problem* pr) {
   L.NW = L.P + L.S;                       // [2h sums P][auto 1h P][cross 1h P(P-1)/2]
   L.nMp = (pr->nM + 1) & ~1;
   L.nchunks = (L.nMp + 255) / 256;
-  L.RK = 2;
-  L.ntiles = (pr->nk + L.RK - 1) / L.RK;
   L.B = (size_t)pr->n_samples * (size_t)pr->models_per_sample;
-  // split the mass axis so that there are a few waves of CTAs (2 resident per SM); parts are multiples of 64 masses
-  const long long rows = (long long)L.B * L.ntiles;
-  int nparts = 1;
-  const int maxparts = (pr->nM + 255) / 256;                             // at least 256 masses per part
-  while (nparts < maxparts && rows * nparts < 6LL * 148) nparts *= 2;
-  if (nparts > maxparts) nparts = maxparts;
-  L.MP = (((pr->nM + nparts - 1) / nparts) + HM_GMCH - 1) / HM_GMCH * HM_GMCH;
-  L.nparts = (pr->nM + L.MP - 1) / L.MP;
+  // units of the Gram kernel (see hm_gram_args): equal contiguous ranges per persistent CTA; a group of HM_GRK
+  // wavenumbers is then shared by at most J CTAs, each with its own partial-result slot
+  L.ngroups = (pr->nk + HM_GRK - 1) / HM_GRK;
+  L.CH = (pr->nM + HM_GMCH - 1) / HM_GMCH;
+  L.total = (long long)L.B * L.ngroups * L.CH;
+  L.ncta = (int)(L.total < hm_num_sms() ? L.total : hm_num_sms());
+  const long long minu = L.total / L.ncta;               // >= 1
+  L.J = (int)((L.CH + minu - 1) / minu) + 1;
   auto align = [](size_t x) { return (x + 31) & ~(size_t)31; };
   L.gw_stride = (size_t)(3 + 2 * L.P) * L.nMp;          // w1, w2, s_p [P], d_p [P], r2
   L.scal_offset = align(L.B * L.gw_stride);
   L.tscal_offset = align(L.scal_offset + L.B * HM_GNSCAL);
   L.partial_offset = align(L.tscal_offset + L.B * (size_t)L.P * HM_GNTS);
-  L.total_bytes = (L.partial_offset + L.B * (size_t)L.nparts * L.NW * (size_t)pr->nk) * sizeof(double);
+  L.total_bytes = (L.partial_offset + L.B * (size_t)L.ngroups * L.J * L.NW * HM_GRK) * sizeof(double);
   return L;
 }
 
@@ -172,365 +173,244 @@ __global__ void __launch_bounds__(256) hm_gram_scalars_kernel(const hm_gram_warg
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Work decomposition of the Gram kernel.  A "group" is HM_GRK consecutive wavenumbers of one model, a "unit" one
+// 16-mass chunk of a group; the B * ngroups * CH units are cut into ncta equal contiguous ranges (one per persistent
+// CTA, stream-K style), so every SM gets the same number of chunks whatever the shape.  A CTA's range touches a few
+// groups; it writes one partial result per group it touches into slot j = cta - (first CTA of the group), and the
+// epilogue adds a group's slots in CTA order (fixed => bitwise reproducible).
+// ---------------------------------------------------------------------------------------------------------------
 struct hm_gram_args {
-  int nk, nM, nMp, P, NB, PT, NW, F, ntiles, nparts, MP;
-  long long nitems;
+  int nk, nM, nMp, P, NW, F, ngroups, CH, ncta, J;
+  long long total;          // units
   size_t gw_stride;
   const double* grid[HM_GMAXP];
   const double* gw;
-  double* partial;          // [B][nparts][NW][nk]
+  double* partial;          // [B * ngroups][J][NW][HM_GRK]
 };
+
+__host__ __device__ __forceinline__ long long hm_gram_ubeg(long long c, long long total, int ncta) { return c * total / ncta; }
+__host__ __device__ __forceinline__ int hm_gram_cta_of(long long unit, long long total, int ncta) {
+  int c = (int)(unit * ncta / total);
+  while (c + 1 < ncta && hm_gram_ubeg(c + 1, total, ncta) <= unit) ++c;
+  while (c > 0 && hm_gram_ubeg(c, total, ncta) > unit) --c;
+  return c;
+}
 
 __device__ __forceinline__ void hm_dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-
-struct hm_gram_cursor {      // (item, chunk) iterator over the contiguous item range of a persistent CTA
-  int item, ch, nch_item;
-  int b, smp, row0, mbeg, mend;
-};
-
-template <int RK>
-__device__ __forceinline__ void hm_gram_decode(hm_gram_cursor& c, const hm_gram_args& a) {
-  int it = c.item;
-  const int part = it % a.nparts; it /= a.nparts;
-  const int tile = it % a.ntiles;
-  c.b = it / a.ntiles;
-  c.smp = c.b / a.F;
-  c.row0 = tile * RK;
-  c.mbeg = part * a.MP;
-  c.mend = (c.mbeg + a.MP < a.nM) ? c.mbeg + a.MP : a.nM;
-  c.nch_item = (c.mend - c.mbeg + HM_GMCH - 1) / HM_GMCH;
-}
-
-// ---- DMMA over the fragments one warp owns -------------------------------------------------------------------
-// Fragment ownership (8x8 blocks of the upper triangle of the NBT x NBT block grid): warp pair WQ = warp/2 owns
-// block rows I1 = WQ and I2 = NBT-1-WQ (together NBT+1 fragments) and, within the pair, warp E = warp%2 takes
-// the block columns j = 2jj+E.  Everything is a template parameter, so DMMAs are unconditional, accumulators
-// are statically indexed registers and the balance is 4-5 fragments per warp at NBT = 8.
-template <int NBT, int WQ, int E>
-struct hm_gram_frag {
-  static constexpr int I1 = WQ, I2 = NBT - 1 - WQ;
-  static constexpr bool ROW1 = I1 <= I2, ROW2 = I1 < I2;
-  __host__ __device__ static constexpr bool v1(int jj) { return ROW1 && (2 * jj + E) >= I1 && (2 * jj + E) < NBT; }
-  __host__ __device__ static constexpr bool v2(int jj) { return ROW2 && (2 * jj + E) >= I2 && (2 * jj + E) < NBT; }
-};
-
-template <int RK, int NBT, int WQ, int E, int JJ, int HALF>
-__device__ __forceinline__ void hm_gram_mma_jj(double (&acc)[RK][2][4][2], int r, const double2& a1, const double2& a2,
-                                               const double2& bb) {
-  using F = hm_gram_frag<NBT, WQ, E>;
-  if constexpr (F::v1(JJ)) hm_dmma884(acc[r][0][JJ][0], acc[r][0][JJ][1], HALF ? a1.y : a1.x, HALF ? bb.y : bb.x);
-  if constexpr (F::v2(JJ)) hm_dmma884(acc[r][1][JJ][0], acc[r][1][JJ][1], HALF ? a2.y : a2.x, HALF ? bb.y : bb.x);
-}
-
-// C[u,v] += sum_m Y_u Y_v over one staged 64-mass tile (Y = sqrt(w1) W: the weight is folded into both operands).  Two k4-steps per 16-byte fragment load: within an
-// 8-mass block step 0 takes masses {0,2,4,6} and step 1 {1,3,5,7} (any assignment works as long as A, B and w1
-// agree: the sum over masses is order-free).
-template <int RK, int NBT, int WQ, int E>
-__device__ __forceinline__ void hm_gram_mma(double (&acc)[RK][2][4][2], const double* __restrict__ Yt, int fr, int fk) {
-  using F = hm_gram_frag<NBT, WQ, E>;
-  constexpr int PT = 8 * NBT;
-  if constexpr (!F::ROW1) return;
-  const double* Yb = Yt + 2 * fk + (size_t)fr * HM_GLD;
-#pragma unroll 2
-  for (int blk = 0; blk < HM_GMCH / 8; ++blk) {
-#pragma unroll
-    for (int r = 0; r < RK; ++r) {
-      const double* Yr = Yb + (size_t)r * PT * HM_GLD + 8 * blk;
-      const double2 a1 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * F::I1) * HM_GLD);
-      double2 a2 = make_double2(0., 0.);
-      if constexpr (F::ROW2) a2 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * F::I2) * HM_GLD);
-      double2 b0 = make_double2(0., 0.), b1 = b0, b2 = b0, b3 = b0;
-      if constexpr (F::v1(0) || F::v2(0)) b0 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * (0 + E)) * HM_GLD);
-      if constexpr (F::v1(1) || F::v2(1)) b1 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * (2 + E)) * HM_GLD);
-      if constexpr (F::v1(2) || F::v2(2)) b2 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * (4 + E)) * HM_GLD);
-      if constexpr (F::v1(3) || F::v2(3)) b3 = *reinterpret_cast<const double2*>(Yr + (size_t)(8 * (6 + E)) * HM_GLD);
-      hm_gram_mma_jj<RK, NBT, WQ, E, 0, 0>(acc, r, a1, a2, b0);
-      hm_gram_mma_jj<RK, NBT, WQ, E, 1, 0>(acc, r, a1, a2, b1);
-      hm_gram_mma_jj<RK, NBT, WQ, E, 2, 0>(acc, r, a1, a2, b2);
-      hm_gram_mma_jj<RK, NBT, WQ, E, 3, 0>(acc, r, a1, a2, b3);
-      hm_gram_mma_jj<RK, NBT, WQ, E, 0, 1>(acc, r, a1, a2, b0);
-      hm_gram_mma_jj<RK, NBT, WQ, E, 1, 1>(acc, r, a1, a2, b1);
-      hm_gram_mma_jj<RK, NBT, WQ, E, 2, 1>(acc, r, a1, a2, b2);
-      hm_gram_mma_jj<RK, NBT, WQ, E, 3, 1>(acc, r, a1, a2, b3);
-    }
+// Persistent, warp-specialised CTA (one per SM, 12 warps):
+//   producer warps 8..11  stream the raw tracer rows of the next chunks -- HM_GRK wavenumbers x PT tracers x 32 masses,
+//                         64 KB at 64 tracers -- with cp.async (LDGSTS, 256-byte row segments) into a ring of three
+//                         stages; completion is signalled on the stage's mbarrier by the copies themselves
+//                         (cp.async.mbarrier.arrive.noinc), so the role never waits for data.  They give most of their
+//                         registers back first (setmaxnreg), which lets the MMA warps run at 232.
+//   MMA warps 0..7        warps 2r and 2r + 1 own wavenumber r of the group and one half each of the upper triangle of
+//                         its Gram matrix: block rows are paired (I, NBT - 1 - I) -- NBT + 1 blocks per pair -- and the
+//                         pairs dealt alternately, 18 8x8 accumulator blocks per warp at 64 tracers.  The m8n8k4 A
+//                         fragment of block row I and the B fragment of block column I are the same register (lane
+//                         (fr, fk) holds Y[8 I + fr][mass fk]), so per four masses eight fragments feed 18 DMMAs, and
+//                         there is no second pass over shared memory: the staged tile is the raw grid, and the lane
+//                         scales its own fragments, Y = s_p * grid with s_p = sqrt(w1) c_p from L1 (the factors are
+//                         shared by the eight warps), and keeps the diagonal work of its block rows (two-halo sums
+//                         sum_m r2 Y_p, auto one-halo sums sum_m d_p grid^2) on them as well.
+// Within an 8-mass block the k4-step "x" takes masses {0,2,4,6} and "y" {1,3,5,7} (16-byte fragment loads; any
+// assignment works as long as A and B agree: the sum over masses is order-free).  Shared-memory rows are 256 bytes (32
+// masses); the 16-byte slot index is XORed with 4 * (tracer & 1), which makes the fragment loads of a quarter warp
+// (two tracer rows x four slots) conflict-free without padding.
+template <int NBT, int H>
+struct hm_gram_own {       // block rows of MMA-warp role H (0 or 1)
+  __host__ __device__ static constexpr bool row(int I) { return (((I < NBT - 1 - I) ? I : NBT - 1 - I) & 1) == H; }
+  __host__ __device__ static constexpr int nblocks() {
+    int n = 0;
+    for (int I = 0; I < NBT; ++I)
+      if (row(I)) n += NBT - I;
+    return n;
   }
-}
+  __host__ __device__ static constexpr int nrows() {
+    int n = 0;
+    for (int I = 0; I < NBT; ++I)
+      if (row(I)) ++n;
+    return n;
+  }
+};
 
-// Write one warp's fragments of a finished item and reset them.
-// C fragment layout (m8n8k4.f64): c0/c1 = C[8i + lane/4][8j + 2*(lane%4) + {0,1}]
-template <int RK, int NBT, int WQ, int E>
-__device__ __forceinline__ void hm_gram_flush(double (&acc)[RK][2][4][2], double* __restrict__ dst, int P, int nk,
-                                              int row0, int fr, int fk) {
-  using F = hm_gram_frag<NBT, WQ, E>;
+template <int NBT, int H>
+__device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const unsigned char* gsm, uint32_t bar_full,
+                                                 uint32_t bar_empty, long long u0, long long u1, int krow, int lane) {
+  using Own = hm_gram_own<NBT, H>;
+  constexpr int PT = 8 * NBT;
+  constexpr int STAGE_BYTES = HM_GRK * PT * HM_GMCH * 8;
+  constexpr int NB = Own::nblocks() > 0 ? Own::nblocks() : 1, NR = Own::nrows() > 0 ? Own::nrows() : 1;
+  const int P = a.P;
+  const int fr = lane >> 2, fk = lane & 3;
+  const uint32_t swz = (uint32_t)(fr & 1) << 2;
+  double acc[NB][2], a2h[NR], a1h[NR];
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
+  for (int t = 0; t < NB; ++t) acc[t][0] = acc[t][1] = 0.;
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const bool valid = (h == 0) ? F::v1(jj) : F::v2(jj);
-      if (valid) {
-        const int u = 8 * (h == 0 ? F::I1 : F::I2) + fr;
+  for (int i = 0; i < NR; ++i) a2h[i] = a1h[i] = 0.;
+  int s = 0;
+  uint32_t parity = 0;
+  for (long long u = u0; u < u1; ++u) {
+    const long long G = u / a.CH;
+    const int ch = (int)(u - G * a.CH);
+    const int b = (int)(G / a.ngroups);
+    const double* __restrict__ gwb = a.gw + (size_t)b * a.gw_stride;
+    hm_mbar_wait(bar_full + 8 * s, parity);             // the chunk has landed
+    const unsigned char* tile = gsm + (size_t)s * STAGE_BYTES + (size_t)krow * PT * (HM_GMCH * 8) + (size_t)fr * (HM_GMCH * 8);
+#pragma unroll 1
+    for (int blk = 0; blk < HM_GMCH / 8; ++blk) {
+      // The factor loads are unconditional -- a branch per tracer row would serialise their latencies: out-of-range
+      // masses and padding tracers read a clamped (finite) entry, and since the staged grid values are zero-filled there,
+      // every product below is an exact zero.
+      const int mm = ch * HM_GMCH + 8 * blk + 2 * fk;
+      const int mc = (mm < a.nMp - 2) ? mm : a.nMp - 2;
+      const double2 r2 = *reinterpret_cast<const double2*>(gwb + (size_t)(2 + 2 * P) * a.nMp + mc);
+      double2 X[NBT], Y[NBT];
 #pragma unroll
-        for (int ee = 0; ee < 2; ++ee) {
-          const int v = 8 * (2 * jj + E) + 2 * fk + ee;
-          if (u < v && v < P) {                        // strict upper triangle, row-major index of (u, v)
-            const size_t idx = (size_t)2 * P + (size_t)u * P - (size_t)u * (u + 1) / 2 + (v - u - 1);
+      for (int I = 0; I < NBT; ++I) {
+        const int p = 8 * I + fr, pc = (p < P) ? p : P - 1;
+        X[I] = *reinterpret_cast<const double2*>(tile + (size_t)I * 8 * (HM_GMCH * 8) + ((((uint32_t)(4 * blk + fk)) ^ swz) << 4));
+        Y[I] = *reinterpret_cast<const double2*>(gwb + (size_t)(2 + pc) * a.nMp + mc);            // s_p for now
+      }
+      {
+        int i = 0;
 #pragma unroll
-            for (int r = 0; r < RK; ++r)
-              if (row0 + r < nk) dst[idx * nk + row0 + r] = acc[r][h][jj][ee];
+        for (int I = 0; I < NBT; ++I) {
+          Y[I] = make_double2(Y[I].x * X[I].x, Y[I].y * X[I].y);                                 // Y = s_p * grid
+          if (Own::row(I)) {
+            const int p = 8 * I + fr, pc = (p < P) ? p : P - 1;
+            const double2 D = *reinterpret_cast<const double2*>(gwb + (size_t)(2 + P + pc) * a.nMp + mc);
+            a2h[i] = fma(r2.x, Y[I].x, fma(r2.y, Y[I].y, a2h[i]));                               // sum_m r2 Y_p = sum_m w2 W_p  (:539)
+            a1h[i] = fma(D.x * X[I].x, X[I].x, fma(D.y * X[I].y, X[I].y, a1h[i]));               // sum_m d_p U^2  (:475-477)
+            ++i;
           }
         }
       }
 #pragma unroll
-      for (int r = 0; r < RK; ++r) acc[r][h][jj][0] = acc[r][h][jj][1] = 0.;
-    }
-}
-
-#define HM_GRAM_WARP_SWITCH(FN, ...)                           \
-  switch (warp) {                                              \
-    case 0: FN<RK, NBT, 0, 0>(__VA_ARGS__); break;             \
-    case 1: FN<RK, NBT, 0, 1>(__VA_ARGS__); break;             \
-    case 2: FN<RK, NBT, 1, 0>(__VA_ARGS__); break;             \
-    case 3: FN<RK, NBT, 1, 1>(__VA_ARGS__); break;             \
-    case 4: FN<RK, NBT, 2, 0>(__VA_ARGS__); break;             \
-    case 5: FN<RK, NBT, 2, 1>(__VA_ARGS__); break;             \
-    case 6: FN<RK, NBT, 3, 0>(__VA_ARGS__); break;             \
-    default: FN<RK, NBT, 3, 1>(__VA_ARGS__); break;            \
-  }
-
-// ---- named barriers between the two warp roles (ids 1..10; 0 is __syncthreads) --------------------------------
-#define HM_GBAR_FULL 1                   // + buf: prep warps arrive, MMA warps wait
-#define HM_GBAR_EMPTY (1 + HM_GNBUF)     // + buf: MMA warps arrive, prep warps wait
-
-// v[0..16) per lane -> the lane whose low four bits are j holds the sum of v[j] over the 16 lanes of its half warp
-__device__ __forceinline__ double hm_half_transpose_sum16(double (&v)[16], int lane) {
+      for (int half = 0; half < 2; ++half) {
+        int t = 0;
 #pragma unroll
-  for (int off = 8; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
+        for (int I = 0; I < NBT; ++I)
+          if (Own::row(I)) {
 #pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const double send = upper ? v[i] : v[i + off];
-      const double keep = upper ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            for (int Jb = I; Jb < NBT; ++Jb) {
+              hm_dmma884(acc[t][0], acc[t][1], half ? Y[I].y : Y[I].x, half ? Y[Jb].y : Y[Jb].x);
+              ++t;
+            }
+          }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) hm_mbar_arrive(bar_empty + 8 * s);   // my reads of the stage have been consumed
+    if (++s == HM_GNS) { s = 0; parity ^= 1u; }
+
+    if (ch == a.CH - 1 || u == u1 - 1) {                // the group ends here for this CTA: write my part of its partial result
+      const int j = (int)blockIdx.x - hm_gram_cta_of(G * a.CH, a.total, a.ncta);
+      double* dst = a.partial + ((size_t)G * a.J + j) * (size_t)a.NW * HM_GRK + krow;
+      // C fragment layout (m8n8k4.f64): c0/c1 = C[8 I + lane/4][8 J + 2 (lane%4) + {0,1}]
+      int t = 0, i = 0;
+#pragma unroll
+      for (int I = 0; I < NBT; ++I)
+        if (Own::row(I)) {
+#pragma unroll
+          for (int Jb = I; Jb < NBT; ++Jb) {
+            const int uu = 8 * I + fr;
+#pragma unroll
+            for (int ee = 0; ee < 2; ++ee) {
+              const int vv = 8 * Jb + 2 * fk + ee;
+              if (uu < vv && vv < P) {                  // strict upper triangle, row-major index of (u, v)
+                const size_t idx = (size_t)2 * P + (size_t)uu * P - (size_t)uu * (uu + 1) / 2 + (vv - uu - 1);
+                dst[idx * HM_GRK] = acc[t][ee];
+              }
+              acc[t][ee] = 0.;
+            }
+            ++t;
+          }
+          // the four lanes of a tracer row hold its masses 2 fk, 2 fk + 1 (mod 8)
+          double v2 = a2h[i], v1 = a1h[i];
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 1); v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+          v2 += __shfl_xor_sync(0xffffffffu, v2, 2); v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+          const int p = 8 * I + fr;
+          if (fk == 0 && p < P) {
+            dst[(size_t)p * HM_GRK] = v2;
+            dst[(size_t)(P + p) * HM_GRK] = v1;
+          }
+          a2h[i] = a1h[i] = 0.;
+          ++i;
+        }
     }
   }
-  return v[0];
-}
-#define HM_GTHREADS (64 * HM_GWARPS)
-__device__ __forceinline__ void hm_bar_sync(int id) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(HM_GTHREADS) : "memory");
-}
-__device__ __forceinline__ void hm_bar_arrive(int id) {
-  asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(HM_GTHREADS) : "memory");
 }
 
-__device__ __forceinline__ bool hm_gram_advance(hm_gram_cursor& c, long long it1) {   // false when the range is done
-  if (++c.ch < c.nch_item) return true;
-  c.ch = 0;
-  return ++c.item < (int)it1;
-}
-
-// Persistent, warp-specialised CTA (one per SM, 16 warps):
-//   prep warps 8..15  stream the tracer rows of 32-mass chunks from HBM with cp.async (LDGSTS, no registers held by
-//                     loads in flight) into a ring of HM_GNBUF tile buffers, HM_GDEPTH chunks (120 KB per SM) ahead of
-//                     the chunk being worked on -- with a single chunk in flight the role ran at 2.8 TB/s and bounded
-//                     the kernel (measured with the DMMAs compiled out: 102 of 147 us); scale the landed tile in place
-//                     to Y = s_p * grid (s_p = sqrt(w1) c_p, so the contraction needs no weight) and accumulate the
-//                     diagonal work -- two-halo sums sum_m w2 W_p and auto one-halo sums sum_m d_p grid_p^2 -- in
-//                     registers, reduced once per item;
-//   MMA warps 0..7    run DMMA over their fragments of the staged tile.
-// The roles hand tiles over with named barriers (bar.arrive / bar.sync), so loads, staging and tensor work of
-// different chunks overlap and there is no CTA-wide synchronisation.
-template <int RK, int NBT>
+template <int NBT>
 __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_args a) {
-  static_assert(RK == 2 && HM_GMCH == 32, "a prep lane owns one mass pair of the chunk for both wavenumber rows");
-  static_assert(2 * NBT <= 16, "the diagonal sums of a prep lane fit one 16-value reduction");
-  extern __shared__ __align__(16) double gsm[];
+  extern __shared__ __align__(128) unsigned char gsm[];
   constexpr int PT = 8 * NBT;
-  constexpr size_t tile_doubles = (size_t)RK * PT * HM_GLD;
-  double* Ys = gsm;                                     // [HM_GNBUF][RK][PT][HM_GLD]  tiles (raw grid rows until scaled)
+  constexpr int STAGE_BYTES = HM_GRK * PT * HM_GMCH * 8;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gsm + (size_t)HM_GNS * STAGE_BYTES);
+  const uint32_t ring = hm_smem_addr(gsm), bar_full = hm_smem_addr(bars), bar_empty = hm_smem_addr(bars + HM_GNS);
   const int P = a.P;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform: role dispatch does not diverge
+  if (tid == 0) {
+    for (int s = 0; s < HM_GNS; ++s) {
+      hm_mbar_init(bar_full + 8 * s, 32 * HM_GPROD_WARPS);    // one cp.async-driven arrival per producer thread
+      hm_mbar_init(bar_empty + 8 * s, HM_GMMA_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long u0 = hm_gram_ubeg(blockIdx.x, a.total, a.ncta), u1 = hm_gram_ubeg(blockIdx.x + 1, a.total, a.ncta);
 
-  const long long per = (a.nitems + gridDim.x - 1) / gridDim.x;
-  const long long it0 = (long long)blockIdx.x * per;
-  const long long it1 = (it0 + per < a.nitems) ? it0 + per : a.nitems;
-  if (it0 >= it1) return;
-
-  hm_gram_cursor cur;
-  cur.item = (int)it0; cur.ch = 0;
-  hm_gram_decode<RK>(cur, a);
-
-  if (warp >= HM_GWARPS) {
-    // =============================== prep warps ===============================
-    // Warp pw owns tracers pw, pw + 8, ...; inside it a lane owns one mass pair of the 32-mass chunk (mp) for BOTH
-    // wavenumber rows and every second one of the warp's tracers (th), so the per-(tracer, mass) factors s_p, d_p are
-    // loaded once for the two rows.  They come from L2 (~1000 cycles under load): the factors of chunk n + 1 are
-    // loaded while chunk n is scaled, a full iteration before they are used.
-    static_assert(NBT % 2 == 0, "the two lane halves split the warp's tracers");
-    constexpr int TL = NBT / 2;                         // tracers per lane
-    const int pw = warp - HM_GWARPS;
-    const int mp = lane & 15, th = lane >> 4;
-    const double2 zero = make_double2(0., 0.);
-    double vals[16];                                    // diagonal sums of the current item: [tt][row][2h, auto 1h]
+  if (warp >= HM_GMMA_WARPS) {
+    // =============================== producer warps ===============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HM_GPROD_REGS));
+    const int pt = tid - 32 * HM_GMMA_WARPS;
+    const int c = pt & 15, pq = pt >> 4;                // 16-byte slot of a 256-byte row segment; tracer within a group of 8
+    int s = 0;
+    uint32_t parity = 0;
+    for (long long u = u0; u < u1; ++u) {
+      const long long G = u / a.CH;
+      const int ch = (int)(u - G * a.CH);
+      const int b = (int)(G / a.ngroups), g = (int)(G - (long long)b * a.ngroups);
+      const int smp = b / a.F, row0 = g * HM_GRK;
+      const int m = ch * HM_GMCH + 2 * c;
+      const bool in = m < a.nM;                         // nM is even: the two masses of a slot are in or out together
+      hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);     // the MMA warps are done with the stage
+      const uint32_t dst0 = ring + (uint32_t)s * STAGE_BYTES;
+#pragma unroll 1
+      for (int r = 0; r < HM_GRK; ++r) {
+        const int row = (row0 + r < a.nk) ? row0 + r : a.nk - 1;           // clamp: duplicates are never written
+        const size_t off = ((size_t)smp * a.nk + row) * (size_t)a.nM + (in ? m : 0);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) vals[i] = 0.;
-
-    auto issue = [&](const hm_gram_cursor& c, int buf) {
-      const int m = c.mbeg + c.ch * HM_GMCH + 2 * mp;
-      const bool in = m < c.mend;
-      const int mc = in ? m : 0;                        // keep the (unread) source address inside the row
-      const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(Ys + (size_t)buf * tile_doubles + 2 * mp);
-#pragma unroll
-      for (int r = 0; r < RK; ++r) {
-        const int row = (c.row0 + r < a.nk) ? c.row0 + r : a.nk - 1;         // clamp: duplicates are never written
-        const size_t off = ((size_t)c.smp * a.nk + row) * (size_t)a.nM + mc;
-#pragma unroll
-        for (int tt = 0; tt < TL; ++tt) {
-          const int p = pw + 8 * (2 * tt + th);
+        for (int pg = 0; pg < PT / 8; ++pg) {
+          const int p = pg * 8 + pq;
           const bool on = in && p < P;
           const double* src = a.grid[on ? p : 0] + off;
-          const uint32_t dst = dst0 + (uint32_t)(((size_t)r * PT + p) * HM_GLD * sizeof(double));
+          const uint32_t dst = dst0 + (uint32_t)(((r * PT + p) * 16 + (c ^ ((p & 1) << 2))) * 16);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(on ? 16 : 0) : "memory");
         }
       }
-    };
-    double2 cc[TL], dd[TL], w2v;                        // s_p, d_p of my tracers and r2 at my mass pair, for chunk `cur`
-    auto load_factors = [&](const hm_gram_cursor& c) {
-      const int m = c.mbeg + c.ch * HM_GMCH + 2 * mp;
-      const bool in = m < c.mend;                       // nM and MP are even: a lane's two masses are in or out together
-      const double* __restrict__ gw = a.gw + (size_t)c.b * a.gw_stride;
-#pragma unroll
-      for (int tt = 0; tt < TL; ++tt) {
-        const int p = pw + 8 * (2 * tt + th);
-        const bool on = in && p < P;
-        cc[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + p) * a.nMp + m) : zero;
-        dd[tt] = on ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + P + p) * a.nMp + m) : zero;
-      }
-      w2v = in ? *reinterpret_cast<const double2*>(gw + (size_t)(2 + 2 * P) * a.nMp + m) : zero;    // r2
-    };
-
-    hm_gram_cursor fill = cur;                          // `fill` runs HM_GDEPTH chunks ahead of `cur`
-    bool more = true;
-#pragma unroll
-    for (int d = 0; d < HM_GDEPTH; ++d) {               // one cp.async group per chunk, empty when there is none
-      if (more) {
-        issue(fill, d);
-        more = hm_gram_advance(fill, it1);
-        if (more && fill.ch == 0) hm_gram_decode<RK>(fill, a);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    load_factors(cur);
-    int n = 0;
-    while (true) {
-      const int buf = n % HM_GNBUF;
-      if (more) {                                       // chunk n + DEPTH goes into the buffer chunk n + DEPTH - NBUF used,
-        const int nb = (n + HM_GDEPTH) % HM_GNBUF;      // once the MMA warps are done with that one
-        if (n + HM_GDEPTH >= HM_GNBUF) hm_bar_sync(HM_GBAR_EMPTY + nb);
-        issue(fill, nb);
-        more = hm_gram_advance(fill, it1);
-        if (more && fill.ch == 0) hm_gram_decode<RK>(fill, a);
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group %0;" ::"n"(HM_GDEPTH) : "memory");      // my copies of chunk n have landed
-      double* Y = Ys + (size_t)buf * tile_doubles + 2 * mp;
-      double2 xv[TL][RK];
-#ifdef HM_GRAM_DEBUG_NO_SCALE
-#pragma unroll
-      for (int tt = 0; tt < TL; ++tt)
-#pragma unroll
-        for (int r = 0; r < RK; ++r) xv[tt][r] = zero;
-      if (false)
-#endif
-#pragma unroll
-      for (int tt = 0; tt < TL; ++tt)
-#pragma unroll
-        for (int r = 0; r < RK; ++r) {
-          const int p = pw + 8 * (2 * tt + th);
-          double2* cell = reinterpret_cast<double2*>(Y + ((size_t)r * PT + p) * HM_GLD);
-          xv[tt][r] = *cell;                            // raw grid values (zero-filled where off)
-          const double2 y = make_double2(cc[tt].x * xv[tt][r].x, cc[tt].y * xv[tt][r].y);
-          *cell = y;                                    // Y = s_p * grid, in place
-#ifndef HM_GRAM_DEBUG_NO_DIAG
-          double& v2h = vals[(tt * RK + r) * 2];
-          v2h = fma(w2v.x, y.x, fma(w2v.y, y.y, v2h));                                             // sum_m r2 Y_p = sum_m w2 W_p  (:539)
-#endif
-        }
-      // No __threadfence_block() here: bar.arrive orders this thread's shared-memory stores before the barrier completes
-      // for the threads that bar.sync on it, and a CTA-scope fence would also wait for the cp.async copies of the NEXT
-      // chunks still in flight -- it turned the ring into one DRAM round trip per chunk (prep role alone: 100 us).
-      hm_bar_arrive(HM_GBAR_FULL + buf);                // the tile is staged: the rest of the iteration is off the MMA warps' path
-#ifndef HM_GRAM_DEBUG_NO_DIAG
-#pragma unroll
-      for (int tt = 0; tt < TL; ++tt)
-#pragma unroll
-        for (int r = 0; r < RK; ++r) {
-          double& v1h = vals[(tt * RK + r) * 2 + 1];
-          v1h = fma(dd[tt].x * xv[tt][r].x, xv[tt][r].x, fma(dd[tt].y * xv[tt][r].y, xv[tt][r].y, v1h));   // sum_m d_p U^2  (:475-477)
-        }
-#endif
-      const bool item_done = cur.ch + 1 == cur.nch_item;
-      const hm_gram_cursor done = cur;
-      ++n;
-      const bool go_on = hm_gram_advance(cur, it1);
-      if (go_on) {
-        if (cur.item != done.item) hm_gram_decode<RK>(cur, a);
-        load_factors(cur);                              // for the next iteration: a whole iteration of latency hiding
-      }
-      if (item_done) {                                  // item finished: reduce and write my tracers' diagonal sums
-        const int part = done.item % a.nparts;
-        double* dst = a.partial + ((size_t)done.b * a.nparts + part) * (size_t)a.NW * a.nk;
-        const double tot = hm_half_transpose_sum16(vals, lane);          // lane (th, j) now holds value j of its half
-        const int tt = mp >> 2, r = (mp >> 1) & 1, kind = mp & 1, p = pw + 8 * (2 * tt + th);
-        if (tt < TL && p < P && done.row0 + r < a.nk) dst[(size_t)(kind * P + p) * a.nk + done.row0 + r] = tot;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) vals[i] = 0.;
-      }
-      if (!go_on) break;
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full + 8 * s) : "memory");
+      if (++s == HM_GNS) { s = 0; parity ^= 1u; }
     }
     return;
   }
 
   // ================================ MMA warps ================================
-  double acc[RK][2][4][2];
-#pragma unroll
-  for (int r = 0; r < RK; ++r)
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) acc[r][h][jj][0] = acc[r][h][jj][1] = 0.;
-  const int fr = lane >> 2, fk = lane & 3;
-  int n = 0;
-  while (true) {
-    const int buf = n % HM_GNBUF;
-    hm_bar_sync(HM_GBAR_FULL + buf);                    // the W tile of this chunk is staged
-    {
-#ifndef HM_GRAM_DEBUG_NO_MMA
-      const double* Yt = Ys + (size_t)buf * tile_doubles;
-      HM_GRAM_WARP_SWITCH(hm_gram_mma, acc, Yt, fr, fk)
-#endif
-    }
-    hm_bar_arrive(HM_GBAR_EMPTY + buf);                 // all my reads of the tile have been consumed by DMMAs
-    if (cur.ch + 1 == cur.nch_item) {                   // item finished: write and reset my fragments
-      const int part = cur.item % a.nparts;
-      double* dst = a.partial + ((size_t)cur.b * a.nparts + part) * (size_t)a.NW * a.nk;
-      HM_GRAM_WARP_SWITCH(hm_gram_flush, acc, dst, P, a.nk, cur.row0, fr, fk)
-    }
-    ++n;
-    const int prev_item = cur.item;
-    if (!hm_gram_advance(cur, it1)) break;
-    if (cur.item != prev_item) hm_gram_decode<RK>(cur, a);
-  }
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(HM_GMMA_REGS));
+  if (warp & 1) hm_gram_mma_role<NBT, 1>(a, gsm, bar_full, bar_empty, u0, u1, warp >> 1, lane);
+  else hm_gram_mma_role<NBT, 0>(a, gsm, bar_full, bar_empty, u0, u1, warp >> 1, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 struct hm_gram_eargs {
-  int nk, nM, nMp, P, S, NW, F, nparts, B;
+  int nk, nM, nMp, P, S, NW, F, B, ngroups, CH, ncta, J;
+  long long total;
   int simple_twohalo, subtract_shotnoise, correct_discrete, fence_out;
   double k_trunc;
   size_t gw_stride;
@@ -565,11 +445,14 @@ __global__ void __launch_bounds__(256) hm_gram_epilogue_kernel(const hm_gram_ear
   const size_t i1h = (u == v) ? (size_t)(P + u)
                               : (size_t)2 * P + (size_t)u * P - (size_t)u * (u + 1) / 2 + (v - u - 1);
   double fu = 0., fv = 0., f1 = 0.;
-  for (int j = 0; j < a.nparts; ++j) {
-    const double* pp = a.partial + ((size_t)b * a.nparts + j) * (size_t)a.NW * a.nk + row;
-    fu += pp[(size_t)u * a.nk];
-    fv += pp[(size_t)v * a.nk];
-    f1 += pp[i1h * a.nk];
+  // the partial results of my wavenumber's group, one per CTA that worked on it, added in CTA order
+  const long long G = (long long)b * a.ngroups + row / HM_GRK;
+  const int c_lo = hm_gram_cta_of(G * a.CH, a.total, a.ncta), c_hi = hm_gram_cta_of((G + 1) * a.CH - 1, a.total, a.ncta);
+  for (int j = 0; j <= c_hi - c_lo; ++j) {
+    const double* pp = a.partial + ((size_t)G * a.J + j) * (size_t)a.NW * HM_GRK + (row % HM_GRK);
+    fu += pp[(size_t)u * HM_GRK];
+    fv += pp[(size_t)v * HM_GRK];
+    f1 += pp[i1h * HM_GRK];
   }
   const double* gw = a.gw + (size_t)b * a.gw_stride;
   const double Aterm = A / a.M[0];
@@ -673,33 +556,30 @@ extern "C" int hm_gram_power_spectrum_stages(const hm_gram_problem* pr, double* 
   }
 
   hm_gram_args g;
-  g.nk = pr->nk; g.nM = pr->nM; g.nMp = L.nMp; g.P = L.P; g.NB = L.NB; g.PT = L.PT; g.NW = L.NW;
-  g.F = pr->models_per_sample; g.ntiles = L.ntiles; g.nparts = L.nparts; g.MP = L.MP; g.gw_stride = L.gw_stride;
+  g.nk = pr->nk; g.nM = pr->nM; g.nMp = L.nMp; g.P = L.P; g.NW = L.NW; g.F = pr->models_per_sample;
+  g.ngroups = L.ngroups; g.CH = L.CH; g.ncta = L.ncta; g.J = L.J; g.total = L.total; g.gw_stride = L.gw_stride;
   for (int p = 0; p < HM_GMAXP; ++p) g.grid[p] = (p < L.P) ? pr->tracers[p].grid_dev : nullptr;
   g.gw = wsd; g.partial = wsd + L.partial_offset;
   // the kernel is instantiated for block grids of 2, 4 and 8 (16, 32, 64 tracer rows); pad up to the next one
   const int NBT = (L.NB <= 2) ? 2 : (L.NB <= 4) ? 4 : 8;
-  const size_t smem = (size_t)HM_GNBUF * L.RK * (8 * NBT) * HM_GLD * sizeof(double);
+  const size_t smem = (size_t)HM_GNS * HM_GRK * (8 * NBT) * HM_GMCH * sizeof(double) + 64;
   static hm_once_per_device once;
   if (once.needed()) {
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   }
-  g.nitems = (long long)L.B * L.ntiles * L.nparts;
-  HM_REQUIRE(g.nitems < (1LL << 31), "too many work items for one launch");
-  const long long grid = g.nitems < hm_num_sms() ? g.nitems : hm_num_sms();
   if (stages & 2) {
-    if (NBT == 2) hm_gram_kernel<2, 2><<<(unsigned)grid, HM_GTHREADS, smem, st>>>(g);
-    else if (NBT == 4) hm_gram_kernel<2, 4><<<(unsigned)grid, HM_GTHREADS, smem, st>>>(g);
-    else hm_gram_kernel<2, 8><<<(unsigned)grid, HM_GTHREADS, smem, st>>>(g);
+    if (NBT == 2) hm_gram_kernel<2><<<(unsigned)L.ncta, HM_GTHREADS, smem, st>>>(g);
+    else if (NBT == 4) hm_gram_kernel<4><<<(unsigned)L.ncta, HM_GTHREADS, smem, st>>>(g);
+    else hm_gram_kernel<8><<<(unsigned)L.ncta, HM_GTHREADS, smem, st>>>(g);
     HM_LAUNCH_CHECK();
   }
   if (!(stages & 4)) return HM_OK;
 
   hm_gram_eargs e;
   e.nk = pr->nk; e.nM = pr->nM; e.nMp = L.nMp; e.P = L.P; e.S = L.S; e.NW = L.NW; e.F = pr->models_per_sample;
-  e.nparts = L.nparts; e.B = (int)L.B;
+  e.B = (int)L.B; e.ngroups = L.ngroups; e.CH = L.CH; e.ncta = L.ncta; e.J = L.J; e.total = L.total;
   e.simple_twohalo = pr->simple_twohalo; e.subtract_shotnoise = pr->subtract_shotnoise;
   e.correct_discrete = pr->correct_discrete; e.k_trunc = pr->k_trunc; e.gw_stride = L.gw_stride;
   e.fence_out = pr->output_is_peer;
