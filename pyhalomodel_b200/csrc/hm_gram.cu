@@ -254,42 +254,71 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
   for (int i = 0; i < NR; ++i) a2h[i] = a1h[i] = 0.;
   int s = 0;
   uint32_t parity = 0;
-  for (long long u = u0; u < u1; ++u) {
-    const long long G = u / a.CH;
-    const int ch = (int)(u - G * a.CH);
-    const int b = (int)(G / a.ngroups);
-    const double* __restrict__ gwb = a.gw + (size_t)b * a.gw_stride;
+  // The per-(tracer, mass) factors come from L1/L2 and do not depend on the ring: they are loaded ONE 8-mass block
+  // ahead (also across chunk boundaries), so their latency hides behind the DMMAs of the current block.  The loads
+  // are unconditional -- a branch per tracer row would serialise their latencies: out-of-range masses and padding
+  // tracers read a clamped (finite) entry, and since the staged grid values are zero-filled there, every product
+  // below is an exact zero.
+  // Index arithmetic is kept off the critical path: 32-bit row offsets of my tracers' factor vectors once per kernel, and
+  // (group, chunk) cursors advanced by increments instead of 64-bit divisions per unit.
+  double2 Sn[NBT], Dn[NR], r2n;
+  int rowS[NBT];
+#pragma unroll
+  for (int I = 0; I < NBT; ++I) {
+    const int p = 8 * I + fr;
+    rowS[I] = (2 + ((p < P) ? p : P - 1)) * a.nMp;
+  }
+  const int rowD = P * a.nMp, rowR = (2 + 2 * P) * a.nMp;
+  long long G = u0 / a.CH;                              // group of the current unit, its chunk and its model's factors
+  int ch = (int)(u0 - G * a.CH);
+  int gin = (int)(G % a.ngroups);
+  const double* __restrict__ gwb = a.gw + (size_t)(G / a.ngroups) * a.gw_stride;
+  const int nunits = (int)(u1 - u0);
+  auto load_factors = [&](const double* __restrict__ gw, int chn, int blk) {
+    const int mm = chn * HM_GMCH + 8 * blk + 2 * fk;
+    const int mc = (mm < a.nMp - 2) ? mm : a.nMp - 2;
+    r2n = *reinterpret_cast<const double2*>(gw + (rowR + mc));
+    int i = 0;
+#pragma unroll
+    for (int I = 0; I < NBT; ++I) {
+      Sn[I] = *reinterpret_cast<const double2*>(gw + (rowS[I] + mc));
+      if (Own::row(I)) Dn[i++] = *reinterpret_cast<const double2*>(gw + (rowS[I] + rowD + mc));
+    }
+  };
+  load_factors(gwb, ch, 0);
+  for (int n = 0; n < nunits; ++n) {
+    // the unit after this one (for the factor prefetch and the end-of-group test)
+    int chN = ch + 1, ginN = gin;
+    const double* __restrict__ gwN = gwb;
+    if (chN == a.CH) {
+      chN = 0;
+      if (++ginN == a.ngroups) { ginN = 0; gwN += a.gw_stride; }
+    }
+    const bool last_unit = n == nunits - 1;
     hm_mbar_wait(bar_full + 8 * s, parity);             // the chunk has landed
     const unsigned char* tile = gsm + (size_t)s * STAGE_BYTES + (size_t)krow * PT * (HM_GMCH * 8) + (size_t)fr * (HM_GMCH * 8);
 #pragma unroll 1
     for (int blk = 0; blk < HM_GMCH / 8; ++blk) {
-      // The factor loads are unconditional -- a branch per tracer row would serialise their latencies: out-of-range
-      // masses and padding tracers read a clamped (finite) entry, and since the staged grid values are zero-filled there,
-      // every product below is an exact zero.
-      const int mm = ch * HM_GMCH + 8 * blk + 2 * fk;
-      const int mc = (mm < a.nMp - 2) ? mm : a.nMp - 2;
-      const double2 r2 = *reinterpret_cast<const double2*>(gwb + (size_t)(2 + 2 * P) * a.nMp + mc);
       double2 X[NBT], Y[NBT];
 #pragma unroll
-      for (int I = 0; I < NBT; ++I) {
-        const int p = 8 * I + fr, pc = (p < P) ? p : P - 1;
+      for (int I = 0; I < NBT; ++I)
         X[I] = *reinterpret_cast<const double2*>(tile + (size_t)I * 8 * (HM_GMCH * 8) + ((((uint32_t)(4 * blk + fk)) ^ swz) << 4));
-        Y[I] = *reinterpret_cast<const double2*>(gwb + (size_t)(2 + pc) * a.nMp + mc);            // s_p for now
-      }
       {
         int i = 0;
 #pragma unroll
         for (int I = 0; I < NBT; ++I) {
-          Y[I] = make_double2(Y[I].x * X[I].x, Y[I].y * X[I].y);                                 // Y = s_p * grid
+          Y[I] = make_double2(Sn[I].x * X[I].x, Sn[I].y * X[I].y);                               // Y = s_p * grid
           if (Own::row(I)) {
-            const int p = 8 * I + fr, pc = (p < P) ? p : P - 1;
-            const double2 D = *reinterpret_cast<const double2*>(gwb + (size_t)(2 + P + pc) * a.nMp + mc);
-            a2h[i] = fma(r2.x, Y[I].x, fma(r2.y, Y[I].y, a2h[i]));                               // sum_m r2 Y_p = sum_m w2 W_p  (:539)
-            a1h[i] = fma(D.x * X[I].x, X[I].x, fma(D.y * X[I].y, X[I].y, a1h[i]));               // sum_m d_p U^2  (:475-477)
+            a2h[i] = fma(r2n.x, Y[I].x, fma(r2n.y, Y[I].y, a2h[i]));                             // sum_m r2 Y_p = sum_m w2 W_p  (:539)
+            a1h[i] = fma(Dn[i].x * X[I].x, X[I].x, fma(Dn[i].y * X[I].y, X[I].y, a1h[i]));       // sum_m d_p U^2  (:475-477)
             ++i;
           }
         }
       }
+      // the factors have been used: fetch those of the next block (or of the first block of the next chunk) behind the
+      // DMMAs below
+      if (blk < HM_GMCH / 8 - 1) load_factors(gwb, ch, blk + 1);
+      else if (!last_unit) load_factors(gwN, chN, 0);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         int t = 0;
@@ -308,7 +337,7 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
     if (lane == 0) hm_mbar_arrive(bar_empty + 8 * s);   // my reads of the stage have been consumed
     if (++s == HM_GNS) { s = 0; parity ^= 1u; }
 
-    if (ch == a.CH - 1 || u == u1 - 1) {                // the group ends here for this CTA: write my part of its partial result
+    if (ch == a.CH - 1 || last_unit) {                  // the group ends here for this CTA: write my part of its partial result
       const int j = (int)blockIdx.x - hm_gram_cta_of(G * a.CH, a.total, a.ncta);
       double* dst = a.partial + ((size_t)G * a.J + j) * (size_t)a.NW * HM_GRK + krow;
       // C fragment layout (m8n8k4.f64): c0/c1 = C[8 I + lane/4][8 J + 2 (lane%4) + {0,1}]
@@ -343,6 +372,8 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
           ++i;
         }
     }
+    if (chN == 0) ++G;
+    ch = chN; gin = ginN; gwb = gwN;
   }
 }
 
