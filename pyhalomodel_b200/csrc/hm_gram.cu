@@ -70,6 +70,7 @@ static hm_gram_layout hm_gram_make_layout(const hm_gram_problem* pr) {
 struct hm_gram_wargs {
   int nM, nMp, P, F;
   int correct_discrete;
+  int need_integrals;                 // the shot-noise / simple two-halo integrals enter the spectra (non-default flags)
   size_t gw_stride;
   const double* M;
   const double* sigma;
@@ -155,6 +156,14 @@ __global__ void __launch_bounds__(256) hm_gram_scalars_kernel(const hm_gram_warg
   const size_t aoff = a.amp_stride_is_grid[p] ? (size_t)s * a.grid_sample_stride : (size_t)s * a.nM;
   const double norm = a.norm[p][b];
   double sn = 0., si = 0.;
+  if (!a.need_integrals) {            // default flags: only c_p[M0] is read (hm_gram_epilogue_kernel)
+    if (threadIdx.x == 0) {
+      double* t = a.tscal + ((size_t)b * a.P + p) * HM_GNTS;
+      t[0] = t[1] = 0.;
+      t[2] = (a.mode[p] == HM_GRID_UK) ? a.amplitude[p][aoff] / norm : 1.;
+    }
+    return;
+  }
   for (int m = threadIdx.x; m < a.nM; m += blockDim.x) {
     const double amp = a.amplitude[p][aoff + m];
     sn += gw[m] * (amp / (norm * norm));
@@ -457,56 +466,87 @@ struct hm_gram_eargs {
   double* out;              // [B][S][3][nk]
 };
 
-// thread per (model, unique pair, wavenumber), wavenumber fastest => coalesced reads of the partial sums and writes
-__global__ void __launch_bounds__(256) hm_gram_epilogue_kernel(const hm_gram_eargs a) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long per_model = (long long)a.S * a.nk;
-  if (gid < per_model * a.B) {
-  const int b = (int)(gid / per_model);
-  const long long rem = gid - (long long)b * per_model;
-  const int s = (int)(rem / a.nk), row = (int)(rem - (long long)s * a.nk);
-  const int smp = b / a.F, P = a.P;
-  // pair s -> (u, v), u <= v, row-major: rows start at off(u) = u P - u(u-1)/2; invert with a float guess + fix-up
-  int u = (int)(((2. * P + 1.) - sqrt((2. * P + 1.) * (2. * P + 1.) - 8. * (double)s)) * 0.5);
-  u = u < 0 ? 0 : (u > P - 1 ? P - 1 : u);
-  while (u > 0 && u * P - u * (u - 1) / 2 > s) --u;
-  while ((u + 1) * P - (u + 1) * u / 2 <= s) ++u;
-  const int v = u + (s - (u * P - u * (u - 1) / 2));
-  const double A = a.scal[(size_t)b * HM_GNSCAL], rhom = a.scal[(size_t)b * HM_GNSCAL + 1];
-  const size_t i1h = (u == v) ? (size_t)(P + u)
-                              : (size_t)2 * P + (size_t)u * P - (size_t)u * (u + 1) / 2 + (v - u - 1);
-  double fu = 0., fv = 0., f1 = 0.;
-  // the partial results of my wavenumber's group, one per CTA that worked on it, added in CTA order
-  const long long G = (long long)b * a.ngroups + row / HM_GRK;
-  const int c_lo = hm_gram_cta_of(G * a.CH, a.total, a.ncta), c_hi = hm_gram_cta_of((G + 1) * a.CH - 1, a.total, a.ncta);
-  for (int j = 0; j <= c_hi - c_lo; ++j) {
-    const double* pp = a.partial + ((size_t)G * a.J + j) * (size_t)a.NW * HM_GRK + (row % HM_GRK);
-    fu += pp[(size_t)u * HM_GRK];
-    fv += pp[(size_t)v * HM_GRK];
-    f1 += pp[i1h * HM_GRK];
-  }
-  const double* gw = a.gw + (size_t)b * a.gw_stride;
-  const double Aterm = A / a.M[0];
-  const size_t goff = ((size_t)smp * a.nk + row) * (size_t)a.nM;     // W_p(k, M[0]) = c_p[0] * grid_p[k, 0]  (:541-542)
-  if (a.mass[u]) fu += Aterm * (a.tscal[((size_t)b * P + u) * HM_GNTS + 2] * a.grid[u][goff]);
-  if (a.mass[v]) fv += Aterm * (a.tscal[((size_t)b * P + v) * HM_GNTS + 2] * a.grid[v][goff]);
-  const double Iu = a.simple_twohalo ? a.tscal[((size_t)b * P + u) * HM_GNTS + 1] : fu * rhom;
-  const double Iv = a.simple_twohalo ? a.tscal[((size_t)b * P + v) * HM_GNTS + 1] : fv * rhom;
-  const double p2h = __dmul_rn(__dadd_rn(__dmul_rn(Iu, Iv), 0.), a.Pk_lin[(size_t)smp * a.nk + row]);   // :524
-  double p1h = f1 * rhom;                                                                              // :532
-  if (u == v && a.discrete[u]) {                                                                       // :484-491
+// CTA = 32 consecutive unique pairs x 8 consecutive groups of HM_GRK wavenumbers of one model; thread (pair, group).
+// A thread finishes its pair for the four wavenumbers of its group with 32-byte reads of the partial results
+// ([slot][sum][4 wavenumbers]): consecutive lanes read consecutive cross sums, the same two-halo sum of tracer u and
+// consecutive ones of tracer v.  The 32 pairs x 3 terms x 32 wavenumbers of the CTA go through shared memory so that
+// every store instruction writes 256 contiguous bytes of one output row.
+#define HM_GE_PAIRS 32
+#define HM_GE_GROUPS 8
+__global__ void __launch_bounds__(HM_GE_PAIRS * HM_GE_GROUPS) hm_gram_epilogue_kernel(const hm_gram_eargs a) {
+  static_assert(HM_GRK == 4, "a thread handles the four wavenumbers of a group as two double2");
+  constexpr int ROWS = HM_GE_GROUPS * HM_GRK;                         // wavenumbers per CTA
+  __shared__ double so[HM_GE_PAIRS * 3][ROWS + 1];
+  const int P = a.P;
+  const int sl = threadIdx.x % HM_GE_PAIRS, gl = threadIdx.x / HM_GE_PAIRS;
+  const int gtiles = (a.ngroups + HM_GE_GROUPS - 1) / HM_GE_GROUPS;
+  const int b = blockIdx.y / gtiles, g0 = (blockIdx.y - b * gtiles) * HM_GE_GROUPS;
+  const int s0 = blockIdx.x * HM_GE_PAIRS, s = s0 + sl, g = g0 + gl;
+  const int smp = b / a.F;
+  if (s < a.S && g < a.ngroups) {
+    const long long G = (long long)b * a.ngroups + g;
+    const int row0 = g * HM_GRK;
+    // pair s -> (u, v), u <= v, row-major: rows start at off(u) = u P - u(u-1)/2; invert with a float guess + fix-up
+    int u = (int)(((2. * P + 1.) - sqrt((2. * P + 1.) * (2. * P + 1.) - 8. * (double)s)) * 0.5);
+    u = u < 0 ? 0 : (u > P - 1 ? P - 1 : u);
+    while (u > 0 && u * P - u * (u - 1) / 2 > s) --u;
+    while ((u + 1) * P - (u + 1) * u / 2 <= s) ++u;
+    const int v = u + (s - (u * P - u * (u - 1) / 2));
+    const double A = a.scal[(size_t)b * HM_GNSCAL], rhom = a.scal[(size_t)b * HM_GNSCAL + 1];
+    const size_t i1h = (u == v) ? (size_t)(P + u)
+                                : (size_t)2 * P + (size_t)u * P - (size_t)u * (u + 1) / 2 + (v - u - 1);
+    double fu[HM_GRK], fv[HM_GRK], f1[HM_GRK];
+#pragma unroll
+    for (int r = 0; r < HM_GRK; ++r) fu[r] = fv[r] = f1[r] = 0.;
+    // the partial results of the group, one per CTA that worked on it, added in CTA order
+    const int c_lo = hm_gram_cta_of(G * a.CH, a.total, a.ncta), c_hi = hm_gram_cta_of((G + 1) * a.CH - 1, a.total, a.ncta);
+    for (int j = 0; j <= c_hi - c_lo; ++j) {
+      const double2* pp = reinterpret_cast<const double2*>(a.partial + ((size_t)G * a.J + j) * (size_t)a.NW * HM_GRK);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const double2 xu = pp[(size_t)u * 2 + h], xv = pp[(size_t)v * 2 + h], x1 = pp[i1h * 2 + h];
+        fu[2 * h] += xu.x; fu[2 * h + 1] += xu.y;
+        fv[2 * h] += xv.x; fv[2 * h + 1] += xv.y;
+        f1[2 * h] += x1.x; f1[2 * h + 1] += x1.y;
+      }
+    }
+    const double Aterm = A / a.M[0];
+    const double cu0 = a.tscal[((size_t)b * P + u) * HM_GNTS + 2], cv0 = a.tscal[((size_t)b * P + v) * HM_GNTS + 2];
+    const double Iu_simple = a.tscal[((size_t)b * P + u) * HM_GNTS + 1], Iv_simple = a.tscal[((size_t)b * P + v) * HM_GNTS + 1];
     const double sn = a.tscal[((size_t)b * P + u) * HM_GNTS];
-    if (a.correct_discrete && !a.subtract_shotnoise) p1h += sn;
-    else if (!a.correct_discrete && a.subtract_shotnoise) p1h -= sn;
+#pragma unroll
+    for (int r = 0; r < HM_GRK; ++r) {
+      const int row = (row0 + r < a.nk) ? row0 + r : a.nk - 1;
+      const size_t goff = ((size_t)smp * a.nk + row) * (size_t)a.nM;     // W_p(k, M[0]) = c_p[0] * grid_p[k, 0]  (:541-542)
+      double xu = fu[r], xv = fv[r];
+      if (a.mass[u]) xu += Aterm * (cu0 * a.grid[u][goff]);
+      if (a.mass[v]) xv += Aterm * (cv0 * a.grid[v][goff]);
+      const double Iu = a.simple_twohalo ? Iu_simple : xu * rhom;
+      const double Iv = a.simple_twohalo ? Iv_simple : xv * rhom;
+      const double p2h = __dmul_rn(__dadd_rn(__dmul_rn(Iu, Iv), 0.), a.Pk_lin[(size_t)smp * a.nk + row]);   // :524
+      double p1h = f1[r] * rhom;                                                                           // :532
+      if (u == v && a.discrete[u]) {                                                                       // :484-491
+        if (a.correct_discrete && !a.subtract_shotnoise) p1h += sn;
+        else if (!a.correct_discrete && a.subtract_shotnoise) p1h -= sn;
+      }
+      if (a.k_trunc > 0.) {                                                                                // :494-495
+        const double q = a.k[row] / a.k_trunc;
+        p1h *= 1. - exp(-(q * q));
+      }
+      so[sl * 3 + 0][gl * HM_GRK + r] = p2h;
+      so[sl * 3 + 1][gl * HM_GRK + r] = p1h;
+      so[sl * 3 + 2][gl * HM_GRK + r] = __dadd_rn(p2h, p1h);                                               // :500-501
+    }
   }
-  if (a.k_trunc > 0.) {                                                                                // :494-495
-    const double q = a.k[row] / a.k_trunc;
-    p1h *= 1. - exp(-(q * q));
-  }
-  double* o = a.out + ((size_t)b * a.S + s) * 3 * a.nk + row;
-  o[0] = p2h;
-  o[a.nk] = p1h;
-  o[2 * (size_t)a.nk] = __dadd_rn(p2h, p1h);                                                           // :500-501
+  __syncthreads();
+  // coalesced stores: one (pair, term) output row segment of ROWS wavenumbers per warp instruction
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = g0 * HM_GRK + lane;
+    for (int q = warp; q < HM_GE_PAIRS * 3; q += HM_GE_GROUPS) {
+      const int sp = s0 + q / 3;
+      if (sp < a.S && row < a.nk) a.out[(((size_t)b * a.S + sp) * 3 + q % 3) * (size_t)a.nk + row] = so[q][lane];
+    }
   }
   if (a.fence_out) {           // `out` is a peer GPU's buffer (fused gather): one cumulative system-scope fence
     __syncthreads();           // per CTA, see hm_epilogue_kernel
@@ -576,6 +616,7 @@ extern "C" int hm_gram_power_spectrum_stages(const hm_gram_problem* pr, double* 
     w.mass[p] = on ? (signed char)(t->mass_tracer != 0) : 0;
     w.discrete[p] = on ? (signed char)(t->discrete_tracer != 0) : 0;
   }
+  w.need_integrals = pr->simple_twohalo || ((pr->correct_discrete != 0) != (pr->subtract_shotnoise != 0));
   w.gw = wsd; w.scal = wsd + L.scal_offset; w.tscal = wsd + L.tscal_offset; w.lowmass = lowmass_dev;
   if (stages & 1) {
     hm_gram_weights_kernel<<<dim3(L.nchunks, (unsigned)L.B), 256, 0, st>>>(w);
@@ -622,8 +663,8 @@ extern "C" int hm_gram_power_spectrum_stages(const hm_gram_problem* pr, double* 
     e.discrete[p] = w.discrete[p];
   }
   e.out = out_dev;
-  const long long nthreads = (long long)L.B * L.S * pr->nk;
-  hm_gram_epilogue_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(e);
+  const int gtiles = (L.ngroups + HM_GE_GROUPS - 1) / HM_GE_GROUPS;
+  hm_gram_epilogue_kernel<<<dim3((L.S + HM_GE_PAIRS - 1) / HM_GE_PAIRS, (unsigned)(L.B * gtiles)), HM_GE_PAIRS * HM_GE_GROUPS, 0, st>>>(e);
   HM_LAUNCH_CHECK();
   return HM_OK;
 }
