@@ -420,6 +420,10 @@ def main():
             gather_ok = bool(torch.equal(gathered.reshape(ref_all.shape), ref_all))
             if not gather_ok:
                 log('gather mismatch')
+        # NCCL raised cudaLimitStackSize when it created its communicator, which alone costs the HBM-bound kernels
+        # 2-3.5 % (tools/dev_stack_probe.py): put it back for the legs below
+        stack_after_nccl = engine.stack_limit(engine.DEFAULT_STACK_LIMIT)
+        log('cudaLimitStackSize after the NCCL gather: %d B, reset to %d' % (stack_after_nccl, engine.DEFAULT_STACK_LIMIT))
 
     # ---- configs block --------------------------------------------------------------------------------------------
     configs = {}

@@ -64,7 +64,12 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
 #define HM_ROWS_CS 32        // row-per-lane kernel: mass columns per stage (four per consumer warp)
 #define HM_ROWS_THREADS (32 * (HM_CONSUMER_WARPS + 4))   // two consumer warpgroups + the producer's warpgroup (setmaxnreg)
 #define HM_ROWS_PRODUCER_REGS 24
+#ifndef HM_ROWS_LAUNCH_THREADS
+#define HM_ROWS_LAUNCH_THREADS HM_ROWS_THREADS   // (experiment: 512 makes ptxas launch the CTA with 128 registers per thread,
+#endif                                           //  which leaves room for a co-resident weights CTA)
+#ifndef HM_ROWS_CONSUMER_REGS
 #define HM_ROWS_CONSUMER_REGS 232
+#endif
 #define HM_ROWS_MAXF 5       // ... for 2..5 models per sample on one or two tracers
 
 struct hm_layout {
@@ -865,7 +870,7 @@ struct hm_rows_cfg {
 };
 
 template <int P, int FM, bool FUSED>
-__global__ void __launch_bounds__(HM_ROWS_THREADS, 1) hm_quad_rows_kernel(const hm_quad_args a,
+__global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel(const hm_quad_args a,
                                                                           const __grid_constant__ CUtensorMap tmG0,
                                                                           const __grid_constant__ CUtensorMap tmG1,
                                                                           const __grid_constant__ CUtensorMap tmW) {

@@ -30,6 +30,36 @@ def device():
     return torch.device('cuda', torch.cuda.current_device())
 
 
+_CUDART = None
+DEFAULT_STACK_LIMIT = 1024
+
+
+def stack_limit(nbytes=None):
+    """Get (and with `nbytes`, set) cudaLimitStackSize of the current device.  NCCL raises it (1024 -> 1872 bytes on this
+    stack) when its first communicator is created, and the driver raises it whenever a kernel needs more; a raised
+    limit costs the HBM-bound quadrature kernels 2-3.5 % (tools/dev_stack_probe.py) and it is
+    never lowered again on its own.  Sweeps that mix collectives with the quadrature call
+    `stack_limit(DEFAULT_STACK_LIMIT)` after the collective; a later kernel that needs more stack gets it again."""
+    global _CUDART
+    if _CUDART is None:
+        for name in ('libcudart.so.12', 'libcudart.so'):
+            try:
+                _CUDART = C.CDLL(name)
+                break
+            except OSError:
+                continue
+        if _CUDART is None:
+            raise HaloB200Error('libcudart is not loadable: cannot query cudaLimitStackSize')
+    old = C.c_size_t(0)
+    if _CUDART.cudaDeviceGetLimit(C.byref(old), 0) != 0:
+        raise HaloB200Error('cudaDeviceGetLimit(cudaLimitStackSize) failed')
+    if nbytes is not None and int(nbytes) != old.value:
+        torch.cuda.synchronize()
+        if _CUDART.cudaDeviceSetLimit(0, C.c_size_t(int(nbytes))) != 0:
+            raise HaloB200Error('cudaDeviceSetLimit(cudaLimitStackSize, %d) failed' % int(nbytes))
+    return old.value
+
+
 def is_host(x):
     """True if `x` lives on the host (numpy array, scalar, list, CPU tensor)."""
     return not (isinstance(x, torch.Tensor) and x.is_cuda)

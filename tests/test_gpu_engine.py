@@ -96,3 +96,19 @@ def test_host_sweep_front_end_vs_public_api_and_oracle():
                 for t in range(3):
                     np.testing.assert_allclose(out[i*5+f, s, t], api[t][key], rtol=1e-12, err_msg=str((i, name, key, t)))
                     assert_spectra_close(out[i*5+f, s, t], want[t][key], rtol=1e-10, what='%d %s %s %d' % (i, name, key, t))
+
+
+def test_stack_limit_round_trip():
+    """engine.stack_limit reads and sets cudaLimitStackSize (the knob NCCL raises at communicator creation, which costs
+    the HBM-bound kernels 2-3.5 %: tools/dev_stack_probe.py); a plan still runs, bit for bit, at either setting."""
+    from pyhalomodel_b200 import engine, workloads
+    old = engine.stack_limit()
+    plan = workloads.build(2, 40, 128, ('m', 'g')).plan()
+    ref = plan.run()[0].clone()
+    try:
+        assert engine.stack_limit(2048) == old
+        assert engine.stack_limit() == 2048
+        assert torch.equal(plan.run()[0], ref)
+    finally:
+        engine.stack_limit(old)
+    assert engine.stack_limit() == old

@@ -405,6 +405,46 @@ def test_config3_full_shape_sweep_vs_oracle(halo):
                                          what='C3 sample %d %s %s term %d' % (g, name, key, t))
 
 
+@pytest.mark.parametrize('names,nk,nM', [([orc.PS74, orc.DESPALI16], 70, 200), ([orc.ST99, orc.SMT01, orc.TINKER10, orc.PS74], 129, 94)])
+def test_sweep_kernel_wk_grid_tracer_and_ragged_shapes_vs_oracle(halo, names, nk, nM):
+    """The row-per-lane sweep kernel with its factored weights on what the config-3 workload does not exercise: a tracer
+    given as a W(k, M) grid (profile.Fourier with amplitude=None, pyhalomodel.py:877-881: the amplitude comes from the
+    k -> 0 row and the per-mass factors are 1 and 1/amplitude^2), row tiles and mass stages that are only partly filled
+    (nk not a multiple of 64, nM not a multiple of 32), two and four mass functions per sample -- against the ORACLE, per
+    sample and mass function, under default flags (fused epilogue) and with k_trunc / no shot-noise subtraction."""
+    from pyhalomodel_b200 import _lib, engine
+    cases = [_synthetic_case(nk, nM, z=z, Om_m=Om) for z, Om in [(0.2, 0.31), (1.1, 0.26)]]
+    k, M = cases[0]['k'], cases[0]['M']
+    G, F = len(cases), len(names)
+    grids_m, grids_p, models, norm_m, want = [], [], [], [], {}
+    for g, cs in enumerate(cases):
+        for f, name in enumerate(names):
+            om = orc.make_model(cs['z'], cs['Om_m'], name=name, Dv=cs['Dv'], dc=cs['dc'])
+            hmod = halo.model(cs['z'], cs['Om_m'], name=name, Dv=cs['Dv'], dc=cs['dc'])
+            rv, c = orc.virial_radius(M, om.Om_m, om.Dv), orc.concentration(M, om.z, halo_definition='Mvir')
+            Wp = syn.pressure_profile(k, M, rv)
+            oprofs = {'m': orc.matter_profile(k, M, rv, c, om.Om_m), 'p': orc.Profile.Fourier(k, M, Wp)}
+            for i, kw in enumerate(({}, dict(k_trunc=0.3, subtract_shotnoise=False))):
+                want[g, f, i] = orc.power_spectrum(om, k, cs['Pk_lin'], M, cs['sigmaM'], oprofs, **kw)
+            models.append(hmod.descriptor())
+            norm_m.append(hmod.rhom)
+        grids_m.append(engine.window_nfw(engine.to_dev(k), engine.to_dev(rv)[None], engine.to_dev(c)[None])[0])
+        grids_p.append(engine.to_dev(Wp))
+    tr = [engine.Tracer(torch.stack(grids_m), engine.to_dev(np.tile(M, (G, 1))), np.array(norm_m), mode=_lib.GRID_UK,
+                        mass_tracer=True),
+          engine.Tracer(torch.stack(grids_p), None, np.ones(G*F), mode=_lib.GRID_WK)]
+    for i, kw in enumerate(({}, dict(k_trunc=0.3, subtract_shotnoise=False))):
+        plan = engine.PowerSpectrumPlan(k, np.stack([c['Pk_lin'] for c in cases]), M, np.stack([c['sigmaM'] for c in cases]),
+                                        tr, models, models_per_sample=F, **kw)
+        out = plan.run()[0].cpu().numpy().reshape(G, F, 3, 3, nk)
+        for g in range(G):
+            for f in range(F):
+                for s, key in enumerate(['m-m', 'm-p', 'p-p']):
+                    for t in range(3):
+                        assert_spectra_close(out[g, f, s, t], want[g, f, i][t][key], rtol=RTOL,
+                                             what='sample %d %s %s term %d %s' % (g, names[f], key, t, kw))
+
+
 def test_error_behaviour(halo):
     g = load_golden('power_c1.npz')
     hmod = halo.model(0., 0.3, name=orc.ST99, Dv=330.)
