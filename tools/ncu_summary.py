@@ -28,14 +28,23 @@ def launches(src, dst):
         f.write('%-44s %8s %12s %10s %8s\n' % ('kernel', 'launches', 'total_us', 'mean_us', 'share'))
         for name, v in sorted(per.items(), key=lambda kv: -sum(kv[1])):
             f.write('%-44s %8d %12.1f %10.2f %7.1f%%\n' % (name[:44], len(v), sum(v)/1e3, sum(v)/len(v)/1e3, 100*sum(v)/tot))
-        # share inside one timed batch step: the (weights, stream, epilogue) triple with the longest stream kernel
-        trip = [o for o in order if any(t in o[1] for t in ('hm_weights', 'hm_quad_stream', 'hm_epilogue'))]
-        cands = [i for i in range(len(trip)-2) if 'hm_weights' in trip[i][1] and 'hm_quad_stream' in trip[i+1][1]
-                 and 'hm_epilogue' in trip[i+2][1]]
-        best = max(cands, key=lambda i: trip[i+1][2])
-        step = trip[best:best+3]
+        # share inside one timed step: the config-3 sweep pair (weights_sweep -> rows) when the run has it, else the
+        # config-2 triple (weights, stream, epilogue) with the longest stream kernel
+        if any('hm_quad_rows' in o[1] for o in order):
+            seq = [o for o in order if 'hm_weights_sweep' in o[1] or 'hm_quad_rows' in o[1]]
+            cands = [i for i in range(len(seq)-1) if 'hm_weights_sweep' in seq[i][1] and 'hm_quad_rows' in seq[i+1][1]]
+            if not cands:
+                return print(open(dst).read())
+            best = max(cands, key=lambda i: seq[i+1][2])
+            step, label = seq[best:best+2], 'one sweep sub-batch (weights -> row-per-lane sweep kernel)'
+        else:
+            trip = [o for o in order if any(t in o[1] for t in ('hm_weights', 'hm_quad_stream', 'hm_epilogue'))]
+            cands = [i for i in range(len(trip)-2) if 'hm_weights' in trip[i][1] and 'hm_quad_stream' in trip[i+1][1]
+                     and 'hm_epilogue' in trip[i+2][1]]
+            best = max(cands, key=lambda i: trip[i+1][2])
+            step, label = trip[best:best+3], 'one batch step (weights -> stream -> epilogue)'
         st = sum(o[2] for o in step)
-        f.write('\n# one batch step (weights -> stream -> epilogue): %.1f us\n' % (st/1e3))
+        f.write('\n# %s: %.1f us\n' % (label, st/1e3))
         for _, name, ns in step:
             f.write('%-44s %10.2f us %7.1f%%\n' % (name[:44], ns/1e3, 100*ns/st))
     print(open(dst).read())
