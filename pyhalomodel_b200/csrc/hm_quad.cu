@@ -76,7 +76,7 @@ struct hm_layout {
   int P, S, NW, nMp, nchunks, nslices, nparts, MC;
   int NVEC;                  // row-per-lane sweeps: factored weight vectors per SAMPLE (2 F + 2 P)
   bool stream, rows;
-  size_t B, scal_offset, cpart_offset, partial_offset, inl_offset, total_bytes;
+  size_t B, scal_offset, cpart_offset, partial_offset, inl_offset, counter_offset, total_bytes;
 };
 
 static bool hm_can_stream(const hm_problem* pr) {
@@ -119,7 +119,8 @@ static hm_layout hm_make_layout(const hm_problem* pr) {
   L.cpart_offset = align(L.scal_offset + L.B * HM_NSCAL);
   L.partial_offset = align(L.cpart_offset + L.B * (size_t)(L.nchunks + 1) * 2 * HM_MAXP);
   L.inl_offset = align(L.partial_offset + L.B * (size_t)L.nparts * L.NW * (size_t)pr->nk);
-  L.total_bytes = (L.inl_offset + (pr->beta_dev ? L.B * (size_t)L.S * pr->nk : 0)) * sizeof(double);
+  L.counter_offset = align(L.inl_offset + (pr->beta_dev ? L.B * (size_t)L.S * pr->nk : 0));      // sweep kernel: item queue
+  L.total_bytes = (L.counter_offset + 32) * sizeof(double);
   return L;
 }
 
@@ -516,6 +517,7 @@ struct hm_quad_args {
   const double* scal;                // [B][HM_NSCAL]
   const double* Pk_lin;              // [G][nk]
   double* out;                       // [B][S][3][nk]
+  int* item_counter;                 // row-per-lane kernel: items handed out beyond the first one per CTA (zeroed per launch)
 };
 
 // acc[r*NW + i] += w_i * (grid values the weight vector i multiplies), for one mass column.
@@ -858,7 +860,7 @@ struct hm_rows_cfg {
 #else
   static constexpr int COMB_BYTES = 4 * COMB_DOUBLES * 8;
 #endif
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int BAR_BYTES = 384;                       // mbarriers (2 NS + 16) and the ring of item descriptors (8 ints)
   static constexpr int BUDGET = 227 * 1024 - BAR_BYTES - COMB_BYTES - 1024;   // 1024: alignment slack of the ring
 #ifndef HM_ROWS_NS_MAX
 #define HM_ROWS_NS_MAX 8
@@ -884,6 +886,7 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
   const uint32_t ring = hm_smem_addr(smem_raw);
   const uint32_t bar_full = hm_smem_addr(bars), bar_empty = hm_smem_addr(bars + NS);
   const uint32_t bar_pfull = hm_smem_addr(bars + 2 * NS), bar_pempty = hm_smem_addr(bars + 2 * NS + 8);   // per writer warp
+  volatile int* desc = reinterpret_cast<volatile int*>(bars + 2 * NS + 16);                               // item queue, see below
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -899,11 +902,14 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
   }
   __syncthreads();
 
-  // (sample, row tile) items dealt round-robin over the CTAs; every item walks the whole mass axis
-  const int it0 = blockIdx.x, it1 = (int)a.nitems;            // (host: nitems < 2^31)
-  const int istep = gridDim.x, step_smp = istep / a.ntiles, step_tile = istep - step_smp * a.ntiles;
+  // (sample, row tile) items, each walking the whole mass axis, are handed out DYNAMICALLY: CTA c starts with item c and
+  // draws the next ones from a global counter, so SMs that run slower (or share their cycles with another kernel) take
+  // fewer items and the launch has no long tail.  Consecutive items are the tiles of one sample, so its weight vectors
+  // still come from L2 for all but the first.  The producer publishes the item of the stages it is about to fill in a
+  // small ring of descriptors BEFORE it arrives on the first stage's barrier; consumers read it after their wait on that
+  // barrier (release/acquire through the mbarrier).  -1 ends the kernel.
+  const int nitems = (int)a.nitems;                           // (host: nitems < 2^31)
   const int nstages = (a.nM + CS - 1) / CS;
-  int smp = it0 / a.ntiles, tile = it0 - smp * a.ntiles;
   int s = 0;
   uint32_t parity = 0;
 
@@ -914,12 +920,21 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
     // room for the 100 accumulators plus the operands of the next column pair in flight.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HM_ROWS_PRODUCER_REGS));
     if (warp == HM_CONSUMER_WARPS && lane == 0) {
-      for (int it = it0; it < it1; it += istep) {
+      int it = blockIdx.x;
+      for (uint32_t seq = 0;; ++seq) {
+        const bool done = it >= nitems;
+        hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);       // slot drained by all consumer warps (first stage of the item)
+        desc[seq & 7u] = done ? -1 : it;
+        if (done) {
+          hm_mbar_arrive(bar_full + 8 * s);                 // an empty stage that carries the end marker
+          break;
+        }
+        const int smp = it / a.ntiles, tile = it - smp * a.ntiles;
         const int row = smp * a.nk + tile * RT;             // first row of the item in the [G*nk][nM] tensors
         const int wrow = smp * C::NVEC;                     // first of its weight vectors in the [G*NVEC][nMp] tensor
         for (int st = 0; st < nstages; ++st) {
           const int m0 = st * CS;
-          hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);     // slot drained by all consumer warps
+          if (st > 0) hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);
           hm_mbar_arrive_expect_tx(bar_full + 8 * s, (uint32_t)C::TX_BYTES);   // OOB parts of a box count as well
           const uint32_t dst = ring + (uint32_t)s * C::STAGE_BYTES;
 #pragma unroll
@@ -931,8 +946,7 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
           hm_tma_2d(dst + (uint32_t)C::DATA_BYTES, &tmW, m0, wrow, bar_full + 8 * s);
           if (++s == NS) { s = 0; parity ^= 1u; }
         }
-        smp += step_smp; tile += step_tile;
-        if (tile >= a.ntiles) { tile -= a.ntiles; ++smp; }
+        it = (int)gridDim.x + atomicAdd(a.item_counter, 1);
       }
     }
     return;
@@ -946,9 +960,13 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
   const uint32_t q0 = 2u * (warp & 3), sw = lane & 7u;
   const uint32_t xo0 = boxoff + (((q0) ^ sw) << 4), xo1 = boxoff + (((q0 + 1u) ^ sw) << 4);
   const uint32_t wcol = 4u * warp * 8u;                            // byte offset of my columns in a weight row
-  uint32_t item_no = 0;
   uint32_t landed = 0;                                        // the early probe of the current stage's barrier succeeded
-  for (int it = it0; it < it1; it += istep, ++item_no) {
+  for (uint32_t item_no = 0;; ++item_no) {
+    if (!landed) hm_mbar_wait(bar_full + 8 * s, parity);      // first stage of the next item, or the end marker
+    landed = 1;
+    const int it = desc[item_no & 7u];
+    if (it < 0) break;
+    const int smp = it / a.ntiles, tile = it - smp * a.ntiles;
     double acc[2][NV];
 #pragma unroll
     for (int r = 0; r < 2; ++r)
@@ -1136,8 +1154,6 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
         }
       }
     }
-    smp += step_smp; tile += step_tile;
-    if (tile >= a.ntiles) { tile -= a.ntiles; ++smp; }
   }
 }
 
@@ -1581,6 +1597,7 @@ static int hm_launch_rows(hm_quad_args& a, bool fused, cudaStream_t st) {
     return rc;
   long long grid = hm_num_sms();
   if (grid > a.nitems) grid = a.nitems;
+  HM_CUDA_TRY(cudaMemsetAsync(a.item_counter, 0, sizeof(int), st));
   if (fused) hm_quad_rows_kernel<P, FM, true><<<(int)grid, HM_ROWS_THREADS, C::SMEM_BYTES, st>>>(a, tmG[0], tmG[1], tmW);
   else hm_quad_rows_kernel<P, FM, false><<<(int)grid, HM_ROWS_THREADS, C::SMEM_BYTES, st>>>(a, tmG[0], tmG[1], tmW);
   HM_LAUNCH_CHECK();
@@ -1645,6 +1662,7 @@ extern "C" int hm_mass_quadrature_stages(const hm_problem* pr, double* out_dev, 
   const bool fused = allow_fused && L.rows && !pr->simple_twohalo && !(pr->k_trunc > 0.) && !pr->beta_dev &&
                      !hm_needs_cpart(pr) && !pr->output_is_peer;
   a.scal = (const double*)ws + L.scal_offset; a.Pk_lin = pr->Pk_lin_dev; a.out = out_dev;
+  a.item_counter = (int*)((double*)ws + L.counter_offset);
   hm_epi_args e;
   e.nk = pr->nk; e.B = (int)L.B; e.F = pr->models_per_sample; e.P = L.P; e.NW = L.NW; e.S = L.S;
   e.nparts = L.nparts; e.nchunks = L.nchunks + 1; e.rows_layout = L.rows; e.use_cpart = hm_needs_cpart(pr);
