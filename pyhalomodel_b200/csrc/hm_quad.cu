@@ -183,16 +183,16 @@ __global__ void __launch_bounds__(HM_WCHUNK, (PT <= 2) ? HM_WMINB : (PT <= 4 ? 3
     for (int f = warp; f < a.F; f += HM_WCHUNK / 32) {
       const int b = s * a.F + f;
       const hm_model_desc d = a.models ? a.models[b] : a.single;
+      const hm_family_consts c = hm_make_family_consts(d);
       const double nu = d.dc / sg0;
       double part = 0.;
 #pragma unroll 1
-      for (int j = 0; j < HM_GL_NODES / 32; ++j) part += hm_lowmass_node(d, nu, lane + 32 * j);
+      for (int j = 0; j < HM_GL_NODES / 32; ++j) part += hm_lowmass_node_shared(d, c, nu, lane + 32 * j);
       const double A = 1. - hm_warp_sum(part);
       if (lane == 0) {
         const double Aterm = A / M0;                    // multiplies W(k, M[0]) for mass tracers (:541-542)
         const double nu_hi = d.dc / sg1;
         const double tw = 0.5 * (nu_hi - nu);
-        const hm_family_consts c = hm_make_family_consts(d);
         double g, bg;
         hm_gb_nu_shared(d, c, nu, log(nu), g, bg);      // the same arithmetic as the other masses' weights
         const double w2_plain = tw * (bg * (1. / M0));
@@ -385,16 +385,16 @@ __global__ void __launch_bounds__(HM_WS_THREADS, 7) hm_weights_sweep_kernel(cons
     for (int f = warp; f < a.F; f += HM_WS_THREADS / 32) {
       const int b = s * a.F + f;
       const hm_model_desc d = a.models ? a.models[b] : a.single;
+      const hm_family_consts c = hm_make_family_consts(d);
       const double nu = d.dc / sg0;
       double part = 0.;
 #pragma unroll 1
-      for (int j = 0; j < HM_GL_NODES / 32; ++j) part += hm_lowmass_node(d, nu, lane + 32 * j);
+      for (int j = 0; j < HM_GL_NODES / 32; ++j) part += hm_lowmass_node_shared(d, c, nu, lane + 32 * j);
       const double A = 1. - hm_warp_sum(part);
       if (lane == 0) {
         const double Aterm = A / M0;                    // multiplies W(k, M[0]) for mass tracers (:541-542)
         const double nu_hi = d.dc / sg1;
         const double tw = 0.5 * (nu_hi - nu);
-        const hm_family_consts c = hm_make_family_consts(d);
         double g, bg;
         hm_gb_nu_shared(d, c, nu, log(nu), g, bg);
         double* sc = a.scal + (size_t)b * HM_NSCAL;
