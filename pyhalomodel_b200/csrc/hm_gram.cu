@@ -7,16 +7,17 @@
 // intensity (~6 flop/B at P=64) is beyond what the streaming-quadrature kernel's per-pair register accumulators
 // can hold, so this path tiles it for mma.sync.m8n8k4.f64 (SASS DMMA; there is no tcgen05 FP64 MMA):
 //
-//   hm_gram_weights_kernel  w1, w2 and r2 = w2/sqrt(w1) per mass; A
-//   hm_gram_tracer_kernel   s_p = sqrt(w1) c_p (the staged tile is Y = s_p*grid, so that the contraction needs no weight:
-//                           sum_m w1 W_u W_v = sum_m Y_u Y_v with W = c_p*grid) and d_p (auto one-halo weight)
-//   hm_gram_scalars_kernel  shot noise and simple-two-halo integrals per (tracer, model)
-//   hm_gram_kernel<RK,NBT>  persistent warp-specialised CTA per SM over (model, RK wavenumbers, mass part) items:
-//                           prep warps stream the tracer rows of the next 64-mass chunk with cp.async into one of
-//                           three W-tile buffers, scale them in place to W and keep the diagonal work (two-halo
-//                           sums sum_m w2 W_p, auto one-halo sums sum_m d_p grid_p^2) in registers; MMA warps run
-//                           DMMA over statically owned 8x8 upper-triangle fragments; named barriers hand tiles over.
-//   hm_gram_epilogue_kernel adds the mass parts and finishes P_2h, P_1h, P_hm for every unique pair (:456-501)
+//   hm_gram_weights_kernel  w1, w2 and r2 = w2/sqrt(w1) per mass; A; per (tracer, mass) s_p = sqrt(w1) c_p (the MMA operand
+//                           is Y = s_p*grid, so that the contraction needs no weight: sum_m w1 W_u W_v = sum_m Y_u Y_v
+//                           with W = c_p*grid) and d_p (auto one-halo weight)
+//   hm_gram_scalars_kernel  shot noise and simple-two-halo integrals per (tracer, model); non-default flags only
+//   hm_gram_kernel<NBT>     persistent warp-specialised CTA per SM over equal contiguous ranges of (group of 4 wavenumbers,
+//                           32-mass chunk) units: producer warps stream the raw tracer rows with cp.async into a three-
+//                           stage ring (mbarrier completion); each pair of MMA warps owns one wavenumber's whole upper
+//                           triangle (18 8x8 DMMA accumulator blocks per warp), scales its fragments in registers and
+//                           keeps the diagonal work (two-halo sums, auto one-halo sums) on them.
+//   hm_gram_epilogue_kernel adds the partial results of the CTAs that shared a group and finishes P_2h, P_1h, P_hm for
+//                           every unique pair (:456-501)
 //
 // The diagonal (auto) terms are NOT Gram entries: they use Uk, amplitude, variance (pyhalomodel.py:465-477).
 #include "hm_common.cuh"
@@ -88,13 +89,17 @@ struct hm_gram_wargs {
   double* lowmass;
 };
 
+// grid (mass chunk, 1 + P, model): CTA row 0 writes w1, w2, r2 and integrates A; CTA row 1 + p writes tracer p's factors
+// s_p = sqrt(w1) c_p (W = c_p * grid, Y = s_p * grid) and d_p (auto one-halo weight).  Every row recomputes w1 for its
+// masses (one g(nu) per thread, identical code => identical bits), which keeps the whole preparation in ONE launch.
 __global__ void __launch_bounds__(256) hm_gram_weights_kernel(const hm_gram_wargs a) {
   __shared__ double scratch[32];
-  const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.z, chunk = blockIdx.x, tid = threadIdx.x;
+  const int role = blockIdx.y;                       // 0: mass-function weights; 1 + p: tracer p
   const int s = b / a.F;
   const hm_model_desc d = a.models ? a.models[b] : a.single;
   const double* sig = a.sigma + (size_t)s * a.nM;
-  if (chunk == 0) {   // A = 1 - int g b dnu (pyhalomodel.py:413-414)
+  if (role == 0 && chunk == 0) {   // A = 1 - int g b dnu (pyhalomodel.py:413-414)
     const double tot = hm_block_sum(hm_lowmass_node(d, d.dc / sig[0], tid), scratch);
     if (tid == 0) {
       a.scal[(size_t)b * HM_GNSCAL] = 1. - tot;
@@ -105,33 +110,24 @@ __global__ void __launch_bounds__(256) hm_gram_weights_kernel(const hm_gram_warg
   double* gw = a.gw + (size_t)b * a.gw_stride;
   const int m = chunk * 256 + tid;
   if (m >= a.nMp) return;
-  if (m >= a.nM) {
-    gw[m] = 0.;
-    gw[(size_t)a.nMp + m] = 0.;
-    gw[(size_t)(2 + 2 * a.P) * a.nMp + m] = 0.;
+  double w1 = 0., w2 = 0.;
+  if (m < a.nM) {
+    const double nu = d.dc / sig[m];
+    const double nu_hi = (m + 1 < a.nM) ? d.dc / sig[m + 1] : nu;
+    const double nu_lo = (m > 0) ? d.dc / sig[m - 1] : nu;
+    const double tw = 0.5 * (nu_hi - nu_lo);
+    const double g = hm_g_nu(d, nu);
+    const double Mm = a.M[m];
+    w1 = tw * (g / Mm);             // one-halo weight (:530)
+    if (role == 0) w2 = tw * ((hm_b_nu(d, nu) * g) / Mm);    // two-halo weight (:539)
+  }
+  if (role == 0) {
+    gw[m] = w1;
+    gw[(size_t)a.nMp + m] = w2;
+    gw[(size_t)(2 + 2 * a.P) * a.nMp + m] = (w1 > 0.) ? w2 / sqrt(w1) : 0.;   // sum_m w2 W_p = sum_m r2 Y_p  (:539)
     return;
   }
-  const double nu = d.dc / sig[m];
-  const double nu_hi = (m + 1 < a.nM) ? d.dc / sig[m + 1] : nu;
-  const double nu_lo = (m > 0) ? d.dc / sig[m - 1] : nu;
-  const double tw = 0.5 * (nu_hi - nu_lo);
-  const double g = hm_g_nu(d, nu);
-  const double bias = hm_b_nu(d, nu);
-  const double Mm = a.M[m];
-  const double w1 = tw * (g / Mm);             // one-halo weight (:530)
-  const double w2 = tw * ((bias * g) / Mm);    // two-halo weight (:539)
-  gw[m] = w1;
-  gw[(size_t)a.nMp + m] = w2;
-  gw[(size_t)(2 + 2 * a.P) * a.nMp + m] = (w1 > 0.) ? w2 / sqrt(w1) : 0.;   // sum_m w2 W_p = sum_m r2 Y_p  (:539)
-}
-
-// per-(tracer, mass) factors: s_p = sqrt(w1) c_p (W = c_p * grid, Y = s_p * grid) and d_p (auto one-halo weight);
-// grid = (mass chunk, tracer, model)
-__global__ void __launch_bounds__(256) hm_gram_tracer_kernel(const hm_gram_wargs a) {
-  const int p = blockIdx.y, b = blockIdx.z, s = b / a.F;
-  const int m = blockIdx.x * 256 + threadIdx.x;
-  if (m >= a.nMp) return;
-  double* gw = a.gw + (size_t)b * a.gw_stride;
+  const int p = role - 1;
   double c = 0., dw = 0.;
   if (m < a.nM) {
     const size_t aoff = a.amp_stride_is_grid[p] ? (size_t)s * a.grid_sample_stride : (size_t)s * a.nM;
@@ -142,9 +138,14 @@ __global__ void __launch_bounds__(256) hm_gram_tracer_kernel(const hm_gram_wargs
     double uS;
     if (a.mode[p] == HM_GRID_UK) { c = amp / norm; uS = 1. / norm; }
     else { c = 1.; uS = 1. / (amp * norm); }                                        // HM_GRID_WK
-    dw = __dmul_rn(__dmul_rn(gw[m], fac), uS * uS);                                 // d_p = w1 fac uS^2 (:475-477)
+    dw = __dmul_rn(__dmul_rn(w1, fac), uS * uS);                                    // d_p = w1 fac uS^2 (:475-477)
+    if (m == 0 && !a.need_integrals) {            // default flags: only c_p[M0] is read from the per-tracer scalars
+      double* t = a.tscal + ((size_t)b * a.P + p) * HM_GNTS;
+      t[0] = t[1] = 0.;
+      t[2] = c;                                   // the low-mass term of the epilogue
+    }
   }
-  gw[(size_t)(2 + p) * a.nMp + m] = (m < a.nM) ? sqrt(gw[m]) * c : 0.;
+  gw[(size_t)(2 + p) * a.nMp + m] = (m < a.nM) ? sqrt(w1) * c : 0.;
   gw[(size_t)(2 + a.P + p) * a.nMp + m] = dw;
 }
 
@@ -156,14 +157,6 @@ __global__ void __launch_bounds__(256) hm_gram_scalars_kernel(const hm_gram_warg
   const size_t aoff = a.amp_stride_is_grid[p] ? (size_t)s * a.grid_sample_stride : (size_t)s * a.nM;
   const double norm = a.norm[p][b];
   double sn = 0., si = 0.;
-  if (!a.need_integrals) {            // default flags: only c_p[M0] is read (hm_gram_epilogue_kernel)
-    if (threadIdx.x == 0) {
-      double* t = a.tscal + ((size_t)b * a.P + p) * HM_GNTS;
-      t[0] = t[1] = 0.;
-      t[2] = (a.mode[p] == HM_GRID_UK) ? a.amplitude[p][aoff] / norm : 1.;
-    }
-    return;
-  }
   for (int m = threadIdx.x; m < a.nM; m += blockDim.x) {
     const double amp = a.amplitude[p][aoff + m];
     sn += gw[m] * (amp / (norm * norm));
@@ -619,12 +612,12 @@ extern "C" int hm_gram_power_spectrum_stages(const hm_gram_problem* pr, double* 
   w.need_integrals = pr->simple_twohalo || ((pr->correct_discrete != 0) != (pr->subtract_shotnoise != 0));
   w.gw = wsd; w.scal = wsd + L.scal_offset; w.tscal = wsd + L.tscal_offset; w.lowmass = lowmass_dev;
   if (stages & 1) {
-    hm_gram_weights_kernel<<<dim3(L.nchunks, (unsigned)L.B), 256, 0, st>>>(w);
+    hm_gram_weights_kernel<<<dim3(L.nchunks, 1 + L.P, (unsigned)L.B), 256, 0, st>>>(w);
     HM_LAUNCH_CHECK();
-    hm_gram_tracer_kernel<<<dim3(L.nchunks, L.P, (unsigned)L.B), 256, 0, st>>>(w);
-    HM_LAUNCH_CHECK();
-    hm_gram_scalars_kernel<<<dim3(L.P, (unsigned)L.B), 256, 0, st>>>(w);
-    HM_LAUNCH_CHECK();
+    if (w.need_integrals) {      // shot noise / simple two-halo integrals: only non-default flags read them
+      hm_gram_scalars_kernel<<<dim3(L.P, (unsigned)L.B), 256, 0, st>>>(w);
+      HM_LAUNCH_CHECK();
+    }
   }
 
   hm_gram_args g;

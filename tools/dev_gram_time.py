@@ -20,5 +20,5 @@ def t(fn, reps=30):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1)/reps*1e3
 us, gus = t(plan.run), t(plan.gram_only)
-print('P=%d nk=%d nM=%d: %.1f us per call (5 kernels), Gram kernel alone %.1f us -> %.2f TFLOP/s useful, %.0f GB/s algorithmic'
+print('P=%d nk=%d nM=%d: %.1f us per call (3 kernels), Gram kernel alone %.1f us -> %.2f TFLOP/s useful, %.0f GB/s algorithmic'
       % (P, nk, nM, us, gus, plan.gram_flops()/gus/1e6, plan.algorithmic_bytes()/gus/1e3))
