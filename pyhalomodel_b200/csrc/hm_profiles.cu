@@ -36,11 +36,17 @@ __device__ __forceinline__ void hm_sici_load_tables(hm_sici_tables& T) {
 //   x >  4: f = A(t)/x, g = B(t)/x^2, t affine in 1/x^2;  Si = pi/2 - f cos x - g sin x, Ci = f sin x - g cos x
 // One Clenshaw loop serves every interval, so mixed warps do not diverge.  Max error vs mpmath on [1e-9,1e3]:
 // Si 4.4e-16 relative, Ci 3.6e-15 absolute -- the same class as scipy's routine (tools/gen_tables.py, tests/).
-__device__ __forceinline__ void hm_sici_eval(double xin, const hm_sici_tables& T, double& si, double& ci) {
+// WANT_CI = false skips what only Ci needs (the logarithm of the small-argument branch); HAVE_SC = true takes sin x and
+// cos x from the caller (sx, cx: of |x|) instead of calling sincos; rx returns 1/|x| (large-argument branch only).
+template <bool WANT_CI, bool HAVE_SC>
+__device__ __forceinline__ void hm_sici_core(double xin, const hm_sici_tables& T, double sx, double cx, double& si, double& ci,
+                                             double& rx) {
   const double x = fabs(xin);
   const int iv = (x <= 4.) ? 0 : (x <= 6.) ? 1 : (x <= 10.) ? 2 : (x <= 20.) ? 3 : 4;
   const double x2 = x * x;
-  const double u = (iv == 0) ? x2 : 1. / x2;
+  rx = 1. / x;                                       // one division serves 1/x, 1/x^2 and the caller
+  const double r2 = rx * rx;
+  const double u = (iv == 0) ? x2 : r2;
   const double t = T.map[0][iv] * u + T.map[1][iv];
   const double t2 = 2. * t;
   double a1 = 0., a2 = 0., b1 = 0., b2 = 0.;
@@ -53,19 +59,25 @@ __device__ __forceinline__ void hm_sici_eval(double xin, const hm_sici_tables& T
   }
   const double Av = fma(t, a1, T.A[0][iv] - a2);
   const double Bv = fma(t, b1, T.B[0][iv] - b2);
+  ci = 0.;
   if (iv == 0) {
     si = x * Av;
-    ci = 0.57721566490153286061 + log(x) + x2 * Bv;   // -inf at x = 0
+    if (WANT_CI) ci = 0.57721566490153286061 + log(x) + x2 * Bv;   // -inf at x = 0
   } else {
-    double s, c;
-    sincos(x, &s, &c);
-    const double f = Av / x, g = Bv / x2;
+    double s = sx, c = cx;
+    if (!HAVE_SC) sincos(x, &s, &c);
+    const double f = Av * rx, g = Bv * r2;
     si = M_PI_2 - f * c - g * s;
-    ci = f * s - g * c;
+    if (WANT_CI) ci = f * s - g * c;
     if (isinf(x)) { si = M_PI_2; ci = 0.; }
   }
   if (xin < 0.) si = -si;
   if (isnan(xin)) { si = xin; ci = xin; }
+}
+
+__device__ __forceinline__ void hm_sici_eval(double xin, const hm_sici_tables& T, double& si, double& ci) {
+  double rx;
+  hm_sici_core<true, false>(xin, T, 0., 0., si, ci, rx);
 }
 
 __global__ void __launch_bounds__(256) hm_sici_kernel(const double* __restrict__ x, long long n,
@@ -81,29 +93,39 @@ __global__ void __launch_bounds__(256) hm_sici_kernel(const double* __restrict__
 }
 
 // U_NFW(k, M) = [cos(ks)(Ci(ks+kv)-Ci(ks)) + sin(ks)(Si(ks+kv)-Si(ks)) - sin(kv)/(ks+kv)] / (ln(1+c) - c/(1+c))
+// CTA = (sample, 256 masses); a thread keeps its mass and walks the wavenumbers, so r_s, the NFW factor and its
+// reciprocal are computed once per thread instead of once per element, and the stores stay coalesced along M.  Two
+// sincos per element serve both Si/Ci evaluations (round 1 called sincos up to three times and sin once).
 __global__ void __launch_bounds__(256) hm_window_nfw_kernel(const double* __restrict__ k, const double* __restrict__ rv,
                                                             const double* __restrict__ conc, int nk, int nM,
                                                             long long total, double* __restrict__ out) {
   __shared__ hm_sici_tables T;
   hm_sici_load_tables(T);
-  const long long per_sample = (long long)nk * nM;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long gs = i / per_sample;
-    const long long rem = i - gs * per_sample;
-    const int ik = (int)(rem / nM), m = (int)(rem - (long long)ik * nM);
-    const double r_v = rv[gs * nM + m], c = conc[gs * nM + m];
-    const double r_s = r_v / c;                       // :1045
+  const int mblocks = (nM + 255) / 256;
+  const long long gs = blockIdx.x / mblocks;
+  const int m = (int)(blockIdx.x - gs * mblocks) * 256 + threadIdx.x;
+  if (m >= nM || gs * (long long)nk * nM >= total) return;
+  const double r_v = rv[gs * nM + m], c = conc[gs * nM + m];
+  const double r_s = r_v / c;                         // :1045
+  const double f4 = log(1. + c) - c / (1. + c);       // :1062
+  const double rf4 = 1. / f4;
+  double* o = out + gs * (long long)nk * nM + m;
+  const int kper = (nk + (int)gridDim.y - 1) / (int)gridDim.y;        // wavenumbers per CTA row (small batches split k too)
+  const int k0 = (int)blockIdx.y * kper, k1 = (k0 + kper < nk) ? k0 + kper : nk;
+#pragma unroll 2
+  for (int ik = k0; ik < k1; ++ik) {
     const double kk = k[ik];
     const double kv = kk * r_v, ks = kk * r_s;        // :1046-1047
-    double Si_sv, Ci_sv, Si_s, Ci_s, sn, cs;
-    hm_sici_eval(ks + kv, T, Si_sv, Ci_sv);           // :1048
-    hm_sici_eval(ks, T, Si_s, Ci_s);                  // :1049
-    sincos(ks, &sn, &cs);
-    const double f1 = cs * (Ci_sv - Ci_s);
-    const double f2 = sn * (Si_sv - Si_s);
-    const double f3 = sin(kv) / (ks + kv);
-    const double f4 = log(1. + c) - c / (1. + c);     // :1062
-    out[i] = (f1 + f2 - f3) / f4;
+    const double ksv = ks + kv;
+    double s1, c1, s12, c12, Si_sv, Ci_sv, Si_s, Ci_s, r12, r1;
+    sincos(ks, &s1, &c1);
+    sincos(ksv, &s12, &c12);
+    hm_sici_core<true, true>(ksv, T, s12, c12, Si_sv, Ci_sv, r12);      // :1048
+    hm_sici_core<true, true>(ks, T, s1, c1, Si_s, Ci_s, r1);            // :1049
+    const double f1 = c1 * (Ci_sv - Ci_s);
+    const double f2 = s1 * (Si_sv - Si_s);
+    const double f3 = sin(kv) / ksv;                  // (an angle-subtraction sin(kv) costs 1e-11 where U cancels to 3e-5)
+    o[(size_t)ik * nM] = (f1 + f2 - f3) * rf4;
   }
 }
 
@@ -111,16 +133,31 @@ __global__ void __launch_bounds__(256) hm_window_iso_kernel(const double* __rest
                                                             int nk, int nM, long long total, double* __restrict__ out) {
   __shared__ hm_sici_tables T;
   hm_sici_load_tables(T);
-  const long long per_sample = (long long)nk * nM;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long gs = i / per_sample;
-    const long long rem = i - gs * per_sample;
-    const int ik = (int)(rem / nM), m = (int)(rem - (long long)ik * nM);
-    const double kv = k[ik] * rv[gs * nM + m];
-    double si, ci;
-    hm_sici_eval(kv, T, si, ci);
-    out[i] = si / kv;                                 // :1036
+  const int mblocks = (nM + 255) / 256;
+  const long long gs = blockIdx.x / mblocks;
+  const int m = (int)(blockIdx.x - gs * mblocks) * 256 + threadIdx.x;
+  if (m >= nM || gs * (long long)nk * nM >= total) return;
+  const double r_v = rv[gs * nM + m];
+  double* o = out + gs * (long long)nk * nM + m;
+  const int kper = (nk + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int k0 = (int)blockIdx.y * kper, k1 = (k0 + kper < nk) ? k0 + kper : nk;
+#pragma unroll 2
+  for (int ik = k0; ik < k1; ++ik) {
+    const double kv = k[ik] * r_v;
+    double si, ci, rx;
+    hm_sici_core<false, false>(kv, T, 0., 0., si, ci, rx);
+    o[(size_t)ik * nM] = si / kv;                     // :1036
   }
+}
+
+// (sample, 256-mass block) CTAs along x; the wavenumber axis is split along y only as far as needed to fill the GPU, so
+// that big batches keep a thread's per-mass constants for all wavenumbers
+static dim3 hm_window_grid(int nk, int nM, int G) {
+  const long long bx = (long long)G * ((nM + 255) / 256);
+  long long by = ((long long)hm_num_sms() * 4 + bx - 1) / bx;
+  if (by > nk) by = nk;
+  if (by < 1) by = 1;
+  return dim3((unsigned)bx, (unsigned)by);
 }
 
 static int hm_grid_for(long long n) {
@@ -146,7 +183,7 @@ extern "C" int hm_window_nfw(const double* k_dev, const double* rv_dev, const do
   HM_REQUIRE(k_dev && rv_dev && c_dev && out_dev, "NULL pointer");
   HM_REQUIRE(nk > 0 && nM > 0 && G > 0, "empty grid");
   const long long total = (long long)G * nk * nM;
-  hm_window_nfw_kernel<<<hm_grid_for(total), 256, 0, (cudaStream_t)stream>>>(k_dev, rv_dev, c_dev, nk, nM, total, out_dev);
+  hm_window_nfw_kernel<<<hm_window_grid(nk, nM, G), 256, 0, (cudaStream_t)stream>>>(k_dev, rv_dev, c_dev, nk, nM, total, out_dev);
   HM_LAUNCH_CHECK();
   return HM_OK;
 }
@@ -158,7 +195,7 @@ extern "C" int hm_window_isothermal(const double* k_dev, const double* rv_dev, i
   HM_REQUIRE(k_dev && rv_dev && out_dev, "NULL pointer");
   HM_REQUIRE(nk > 0 && nM > 0 && G > 0, "empty grid");
   const long long total = (long long)G * nk * nM;
-  hm_window_iso_kernel<<<hm_grid_for(total), 256, 0, (cudaStream_t)stream>>>(k_dev, rv_dev, nk, nM, total, out_dev);
+  hm_window_iso_kernel<<<hm_window_grid(nk, nM, G), 256, 0, (cudaStream_t)stream>>>(k_dev, rv_dev, nk, nM, total, out_dev);
   HM_LAUNCH_CHECK();
   return HM_OK;
 }
