@@ -10,30 +10,46 @@ __constant__ double c_sici_map[HM_SICI_NI][2] = HM_SICI_MAP_INIT;
 __constant__ double c_sici_A[HM_SICI_NI][HM_SICI_NT] = HM_SICI_A_INIT;
 __constant__ double c_sici_B[HM_SICI_NI][HM_SICI_NT] = HM_SICI_B_INIT;
 
-// Shared-memory copy of the tables, transposed to [term][interval] (padded to 8) so that lanes whose arguments
+// Shared-memory copy of the tables, transposed to [term][interval] (padded to 32) so that lanes whose arguments
 // fall in different intervals read different banks and lanes in the same interval broadcast.
+#define HM_SICI_PAD 32
+static_assert(HM_SICI_NI == 24, "hm_sici_interval decodes the 24 intervals tools/gen_tables.py lays out");
 struct hm_sici_tables {
-  double A[HM_SICI_NT][8];
-  double B[HM_SICI_NT][8];
-  double map[2][8];
+  double A[HM_SICI_NT][HM_SICI_PAD];
+  double B[HM_SICI_NT][HM_SICI_PAD];
+  double map[2][HM_SICI_PAD];
 };
 
 __device__ __forceinline__ void hm_sici_load_tables(hm_sici_tables& T) {
-  for (int i = threadIdx.x; i < HM_SICI_NT * 8; i += blockDim.x) {
-    const int n = i >> 3, iv = i & 7;
+  for (int i = threadIdx.x; i < HM_SICI_NT * HM_SICI_PAD; i += blockDim.x) {
+    const int n = i / HM_SICI_PAD, iv = i % HM_SICI_PAD;
     T.A[n][iv] = (iv < HM_SICI_NI) ? c_sici_A[iv][n] : 0.;
     T.B[n][iv] = (iv < HM_SICI_NI) ? c_sici_B[iv][n] : 0.;
   }
-  for (int i = threadIdx.x; i < 16; i += blockDim.x) {
-    const int j = i >> 3, iv = i & 7;
+  for (int i = threadIdx.x; i < 2 * HM_SICI_PAD; i += blockDim.x) {
+    const int j = i / HM_SICI_PAD, iv = i % HM_SICI_PAD;
     T.map[j][iv] = (iv < HM_SICI_NI) ? c_sici_map[iv][j] : 0.;
   }
   __syncthreads();
 }
 
+// Interval of x >= 0: [0, 4] | eight of width 1/2 in (4, 8) | eight of width 1 in [8, 16) | four of width 4 in [16, 32) |
+// [32, 64) | [64, 128) | [128, inf) -- the edges sit on the binary exponent and the leading mantissa bits of x, so the
+// index comes from the high word instead of a chain of comparisons (the finer the intervals, the shorter the series:
+// 12 terms instead of the 20 a single [4, 6] interval needs).
+__device__ __forceinline__ int hm_sici_interval(double x) {
+  if (x <= 4.) return 0;
+  const int hi = __double2hiint(x);
+  const int e = (hi >> 20) - 1023;                   // 2 for [4, 8), ... (x > 4 here; inf and nan give 1024)
+  if (e == 2) return 1 + ((hi >> 17) & 7);
+  if (e == 3) return 9 + ((hi >> 17) & 7);
+  if (e == 4) return 17 + ((hi >> 18) & 3);
+  return (e == 5) ? 21 : (e == 6) ? 22 : 23;
+}
+
 // Si(x), Ci(x) for x >= 0 (odd / even continuation for x < 0, like Cephes).
 //   x <= 4: Si = x A(t), Ci = gamma + ln x + x^2 B(t), t affine in x^2
-//   x >  4: f = A(t)/x, g = B(t)/x^2, t affine in 1/x^2;  Si = pi/2 - f cos x - g sin x, Ci = f sin x - g cos x
+//   x >  4: f = A(t)/x, g = B(t)/x^2, t affine in 1/x^2 on 23 intervals;  Si = pi/2 - f cos x - g sin x, Ci = f sin x - g cos x
 // One Clenshaw loop serves every interval, so mixed warps do not diverge.  Max error vs mpmath on [1e-9,1e3]:
 // Si 4.4e-16 relative, Ci 3.6e-15 absolute -- the same class as scipy's routine (tools/gen_tables.py, tests/).
 // WANT_CI = false skips what only Ci needs (the logarithm of the small-argument branch); HAVE_SC = true takes sin x and
@@ -42,7 +58,7 @@ template <bool WANT_CI, bool HAVE_SC>
 __device__ __forceinline__ void hm_sici_core(double xin, const hm_sici_tables& T, double sx, double cx, double& si, double& ci,
                                              double& rx) {
   const double x = fabs(xin);
-  const int iv = (x <= 4.) ? 0 : (x <= 6.) ? 1 : (x <= 10.) ? 2 : (x <= 20.) ? 3 : 4;
+  const int iv = hm_sici_interval(x);
   const double x2 = x * x;
   rx = 1. / x;                                       // one division serves 1/x, 1/x^2 and the caller
   const double r2 = rx * rx;
@@ -124,7 +140,8 @@ __global__ void __launch_bounds__(256) hm_window_nfw_kernel(const double* __rest
     hm_sici_core<true, true>(ks, T, s1, c1, Si_s, Ci_s, r1);            // :1049
     const double f1 = c1 * (Ci_sv - Ci_s);
     const double f2 = s1 * (Si_sv - Si_s);
-    const double f3 = sin(kv) / ksv;                  // (an angle-subtraction sin(kv) costs 1e-11 where U cancels to 3e-5)
+    const double f3 = sin(kv) * r12;                  // sin(kv)/(ks+kv) with the reciprocal of the Si/Ci evaluation (an
+                                                      // angle-subtraction sin(kv) costs 1e-11 where U cancels to 3e-5)
     o[(size_t)ik * nM] = (f1 + f2 - f3) * rf4;
   }
 }

@@ -78,6 +78,22 @@ def test_sici_and_windows(halo):
         halo.window_function(k, rv, profile='bogus')
 
 
+def test_sici_interval_edges_and_dense_points():
+    """The device Si/Ci picks one of 24 Chebyshev intervals from the bits of x (hm_sici_interval): both sides of every
+    interval edge and a dense random set up to x = 300 against scipy.special.sici, at the tolerances of the golden test."""
+    from scipy import special
+    from pyhalomodel_b200 import engine
+    edges = np.array([4, 4.5, 5, 5.5, 6, 6.5, 7, 7.5, 8, 9, 10, 11, 12, 13, 14, 15, 16, 20, 24, 28, 32, 64, 128], dtype=float)
+    rng = np.random.default_rng(5)
+    x = np.concatenate([edges, np.nextafter(edges, 0.), np.nextafter(edges, 1e9), edges*(1.+1e-12), edges*(1.-1e-12),
+                        rng.uniform(3.5, 40., 20000), np.exp(rng.uniform(np.log(30.), np.log(300.), 5000))])
+    si, ci = engine.sici(x)
+    si, ci = engine.to_host(si), engine.to_host(ci)
+    rsi, rci = special.sici(x)
+    np.testing.assert_allclose(si, rsi, rtol=2e-15, atol=0)
+    np.testing.assert_allclose(ci, rci, rtol=0, atol=2e-15)
+
+
 def test_sigmaR(halo):
     from pyhalomodel_b200 import cosmology
     g = load_golden('sigma.npz')
