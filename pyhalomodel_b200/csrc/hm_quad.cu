@@ -369,9 +369,12 @@ __global__ void __launch_bounds__(HM_WCHUNK, (PT <= 2) ? HM_WMINB : (PT <= 4 ? 3
 // CTAs are small (128 threads, 512 masses): 1024 of them for 512 samples spread evenly over the SMs in one wave.
 // grid (ceil(nMp / 512) + 1, G); the last CTA of a sample integrates the low-mass corrections (as in hm_weights_kernel).
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef HM_WS_THREADS
 #define HM_WS_THREADS 128
 #define HM_WS_PER 4
-__global__ void __launch_bounds__(HM_WS_THREADS, 7) hm_weights_sweep_kernel(const hm_weights_args a) {
+#define HM_WS_MINB 7
+#endif
+__global__ void __launch_bounds__(HM_WS_THREADS, HM_WS_MINB) hm_weights_sweep_kernel(const hm_weights_args a) {
   constexpr int PT = 2;
   __shared__ hm_fam_consts<PT> sfc[HM_ROWS_MAXF];
   const int s = blockIdx.y, chunk = blockIdx.x;
@@ -872,7 +875,11 @@ struct hm_rows_cfg {
 };
 
 template <int P, int FM, bool FUSED>
+#ifdef HM_ROWS_LAUNCH_REGS      // (experiment: a smaller register allocation at launch leaves room for a co-resident weights CTA)
+__global__ void __maxnreg__(HM_ROWS_LAUNCH_REGS) hm_quad_rows_kernel(const hm_quad_args a,
+#else
 __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel(const hm_quad_args a,
+#endif
                                                                           const __grid_constant__ CUtensorMap tmG0,
                                                                           const __grid_constant__ CUtensorMap tmG1,
                                                                           const __grid_constant__ CUtensorMap tmW) {
