@@ -30,7 +30,9 @@
 #define HM_GPROD_WARPS 4
 #define HM_GTHREADS (32 * (HM_GMMA_WARPS + HM_GPROD_WARPS))
 #define HM_GPROD_REGS 40
-#define HM_GMMA_REGS 232
+#define HM_GMMA_REGS 232           // (split-triangle layout)
+#define HM_GMMA_ALL_REGS 248       // whole-triangle MMA warps: 144 accumulator registers
+#define HM_GDIAG_REGS 152          // diagonal-work warps
 #define HM_GNSCAL 4
 #define HM_GNTS 3                  // per (model, tracer) scalars: shot noise, simple two-halo integral, c_p[M0]
 
@@ -223,18 +225,22 @@ __device__ __forceinline__ void hm_dmma884(double& c0, double& c1, double a, dou
 // masses); the 16-byte slot index is XORed with 4 * (tracer & 1), which makes the fragment loads of a quarter warp
 // (two tracer rows x four slots) conflict-free without padding.
 template <int NBT, int H>
-struct hm_gram_own {       // block rows of MMA-warp role H (0 or 1)
-  __host__ __device__ static constexpr bool row(int I) { return (((I < NBT - 1 - I) ? I : NBT - 1 - I) & 1) == H; }
+struct hm_gram_own {       // what MMA-group warp role H does: H = 0, 1: half of the triangle and its diagonal work (block rows
+                           // paired (I, NBT - 1 - I), pairs dealt alternately); H = 2: the whole triangle, no diagonal work;
+                           // H = 3: the diagonal work of every block row, no DMMA
+  __host__ __device__ static constexpr bool half(int I) { return (((I < NBT - 1 - I) ? I : NBT - 1 - I) & 1) == H; }
+  __host__ __device__ static constexpr bool mma(int I) { return H == 2 || (H < 2 && half(I)); }
+  __host__ __device__ static constexpr bool diag(int I) { return H == 3 || (H < 2 && half(I)); }
   __host__ __device__ static constexpr int nblocks() {
     int n = 0;
     for (int I = 0; I < NBT; ++I)
-      if (row(I)) n += NBT - I;
+      if (mma(I)) n += NBT - I;
     return n;
   }
   __host__ __device__ static constexpr int nrows() {
     int n = 0;
     for (int I = 0; I < NBT; ++I)
-      if (row(I)) ++n;
+      if (diag(I)) ++n;
     return n;
   }
 };
@@ -279,12 +285,12 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
   auto load_factors = [&](const double* __restrict__ gw, int chn, int blk) {
     const int mm = chn * HM_GMCH + 8 * blk + 2 * fk;
     const int mc = (mm < a.nMp - 2) ? mm : a.nMp - 2;
-    r2n = *reinterpret_cast<const double2*>(gw + (rowR + mc));
+    if (Own::nrows() > 0) r2n = *reinterpret_cast<const double2*>(gw + (rowR + mc));
     int i = 0;
 #pragma unroll
     for (int I = 0; I < NBT; ++I) {
       Sn[I] = *reinterpret_cast<const double2*>(gw + (rowS[I] + mc));
-      if (Own::row(I)) Dn[i++] = *reinterpret_cast<const double2*>(gw + (rowS[I] + rowD + mc));
+      if (Own::diag(I)) Dn[i++] = *reinterpret_cast<const double2*>(gw + (rowS[I] + rowD + mc));
     }
   };
   load_factors(gwb, ch, 0);
@@ -299,7 +305,11 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
     const bool last_unit = n == nunits - 1;
     hm_mbar_wait(bar_full + 8 * s, parity);             // the chunk has landed
     const unsigned char* tile = gsm + (size_t)s * STAGE_BYTES + (size_t)krow * PT * (HM_GMCH * 8) + (size_t)fr * (HM_GMCH * 8);
-#pragma unroll 1
+#ifndef HM_GRAM_BLK_UNROLL
+#define HM_GRAM_BLK_UNROLL 1
+#endif
+    constexpr int BLKU = HM_GRAM_BLK_UNROLL;
+#pragma unroll BLKU
     for (int blk = 0; blk < HM_GMCH / 8; ++blk) {
       double2 X[NBT], Y[NBT];
 #pragma unroll
@@ -310,7 +320,7 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
 #pragma unroll
         for (int I = 0; I < NBT; ++I) {
           Y[I] = make_double2(Sn[I].x * X[I].x, Sn[I].y * X[I].y);                               // Y = s_p * grid
-          if (Own::row(I)) {
+          if (Own::diag(I)) {
             a2h[i] = fma(r2n.x, Y[I].x, fma(r2n.y, Y[I].y, a2h[i]));                             // sum_m r2 Y_p = sum_m w2 W_p  (:539)
             a1h[i] = fma(Dn[i].x * X[I].x, X[I].x, fma(Dn[i].y * X[I].y, X[I].y, a1h[i]));       // sum_m d_p U^2  (:475-477)
             ++i;
@@ -326,7 +336,7 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
         int t = 0;
 #pragma unroll
         for (int I = 0; I < NBT; ++I)
-          if (Own::row(I)) {
+          if (Own::mma(I)) {
 #pragma unroll
             for (int Jb = I; Jb < NBT; ++Jb) {
               hm_dmma884(acc[t][0], acc[t][1], half ? Y[I].y : Y[I].x, half ? Y[Jb].y : Y[Jb].x);
@@ -345,8 +355,8 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
       // C fragment layout (m8n8k4.f64): c0/c1 = C[8 I + lane/4][8 J + 2 (lane%4) + {0,1}]
       int t = 0, i = 0;
 #pragma unroll
-      for (int I = 0; I < NBT; ++I)
-        if (Own::row(I)) {
+      for (int I = 0; I < NBT; ++I) {
+        if (Own::mma(I)) {
 #pragma unroll
           for (int Jb = I; Jb < NBT; ++Jb) {
             const int uu = 8 * I + fr;
@@ -361,6 +371,8 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
             }
             ++t;
           }
+        }
+        if (Own::diag(I)) {
           // the four lanes of a tracer row hold its masses 2 fk, 2 fk + 1 (mod 8)
           double v2 = a2h[i], v1 = a1h[i];
           v2 += __shfl_xor_sync(0xffffffffu, v2, 1); v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
@@ -373,6 +385,7 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
           a2h[i] = a1h[i] = 0.;
           ++i;
         }
+      }
     }
     if (chN == 0) ++G;
     ch = chN; gin = ginN; gwb = gwN;
@@ -434,10 +447,26 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
     return;
   }
 
-  // ================================ MMA warps ================================
+  // ================================ MMA-group warps ================================
+#ifndef HM_GRAM_WHOLE_TRIANGLE
+  // warps 2r and 2r + 1 share wavenumber r: half of the triangle and of the diagonal work each
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(HM_GMMA_REGS));
   if (warp & 1) hm_gram_mma_role<NBT, 1>(a, gsm, bar_full, bar_empty, u0, u1, warp >> 1, lane);
   else hm_gram_mma_role<NBT, 0>(a, gsm, bar_full, bar_empty, u0, u1, warp >> 1, lane);
+#else
+  // (experiment, 127 against 122 us on config 4) warp r (0..3) runs the DMMAs of wavenumber r's whole triangle and nothing
+  // else on the FP64 pipe but the scaling of its fragments; warp 4 + r, on the same scheduler, does the diagonal work of
+  // that wavenumber from the same staged tile.  The MMA warp then issues DMMAs 63 % of its time instead of 35 %, but it is
+  // alone on its scheduler's tensor pipe, and unrolling its block loop to overlap the next block's loads spills (248
+  // registers: 144 of them accumulators).
+  if (warp < HM_GRK) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(HM_GMMA_ALL_REGS));
+    hm_gram_mma_role<NBT, 2>(a, gsm, bar_full, bar_empty, u0, u1, warp, lane);
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HM_GDIAG_REGS));
+    hm_gram_mma_role<NBT, 3>(a, gsm, bar_full, bar_empty, u0, u1, warp - HM_GRK, lane);
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------------------------
