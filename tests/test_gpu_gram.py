@@ -171,3 +171,52 @@ def test_gram_config4_size_vs_oracle_subsets_and_streaming_path(halo):
             for u in names:
                 for v in names:
                     assert_spectra_close(got[t][u+'-'+v], ref[t][u+'-'+v], rtol=1e-12, what='%s-%s term %d' % (u, v, t))
+
+
+def test_gram_batched_models_vs_single_calls(halo):
+    """Several samples x mass functions in ONE Gram plan (the stream-K unit ranges of the Gram kernel then cross group AND
+    model boundaries, and the epilogue adds partial slots of groups that belong to different models): every model of the
+    batch against the single-model API call (which the tests above hold to the oracle), with ragged shapes."""
+    from pyhalomodel_b200 import _lib, engine
+    nk, nM, ntr = 23, 150, 11
+    names = [orc.TINKER10, orc.ST99, orc.DESPALI16]
+    cases = [_synthetic_case(nk, nM, z=z, Om_m=Om) for z, Om in [(0.1, 0.3), (0.9, 0.28)]]
+    k, M = cases[0]['k'], cases[0]['M']
+    rng = np.random.default_rng(42)
+    hods = [syn.draw_hod(rng) for _ in range(ntr-1)]
+    G, F = len(cases), len(names)
+    singles, models = [], []
+    grids = [[] for _ in range(ntr)]
+    amps, vars_ = [[] for _ in range(ntr)], [[] for _ in range(ntr)]
+    norms = [[] for _ in range(ntr)]
+    for gi, cs in enumerate(cases):
+        for name in names:
+            hmod = halo.model(cs['z'], cs['Om_m'], name=name, Dv=cs['Dv'], dc=cs['dc'])
+            profs = _tracers(halo, hmod, cs, hods, True, False, True)
+            singles.append(hmod.power_spectrum(k, cs['Pk_lin'], M, cs['sigmaM'], profs))
+            models.append(hmod.descriptor())
+            for p, key in enumerate(profs):
+                norms[p].append(profs[key].normalisation)
+        for p, key in enumerate(profs):              # the grids, amplitudes and variances are per sample
+            pr = profs[key]
+            grids[p].append(engine.to_dev(pr.Uk))
+            amps[p].append(engine.to_dev(pr.amplitude))
+            vars_[p].append(engine.to_dev(pr.variance) if pr.variance is not None else None)
+    keys = list(profs.keys())
+    tr = []
+    for p, key in enumerate(keys):
+        var = torch.stack(vars_[p]) if vars_[p][0] is not None else None
+        tr.append(engine.Tracer(torch.stack(grids[p]).contiguous(), torch.stack(amps[p]), np.array(norms[p], dtype=float),
+                                variance=var, mode=_lib.GRID_UK, mass_tracer=profs[key].mass_tracer,
+                                discrete_tracer=profs[key].discrete_tracer))
+    plan = engine.GramPlan(k, np.stack([c['Pk_lin'] for c in cases]), M, np.stack([c['sigmaM'] for c in cases]), tr, models,
+                           models_per_sample=F)
+    out = plan.run()[0].cpu().numpy()
+    s = 0
+    for iu in range(ntr):
+        for iv in range(iu, ntr):
+            key = '%s-%s' % (keys[iu], keys[iv])
+            for b, single in enumerate(singles):
+                for t in range(3):
+                    np.testing.assert_allclose(out[b, s, t], single[t][key], rtol=1e-12, atol=0., err_msg=str((b, key, t)))
+            s += 1
