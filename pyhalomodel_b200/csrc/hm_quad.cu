@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(HM_WCHUNK, (PT <= 2) ? HM_WMINB : (PT <= 4 ? 3
 // each family body runs as a loop (fetched once, executed four times), the constants are prepared by the first F
 // threads WHILE the others do the family-independent part (nu, ln nu, the trapezoid weight, the tracer vectors), and
 // CTAs are small (128 threads, 512 masses): 1024 of them for 512 samples spread evenly over the SMs in one wave.
-// grid (ceil(nMp / 512) + 1, G); the last CTA of a sample integrates the low-mass corrections (as in hm_weights_kernel).
+// grid (ceil(nMp / 512), G); the warps of a sample's CTAs share out its low-mass corrections once their masses are done.
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef HM_WS_THREADS
 #define HM_WS_THREADS 128
@@ -381,48 +381,6 @@ __global__ void __launch_bounds__(HM_WS_THREADS, HM_WS_MINB) hm_weights_sweep_ke
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* sig = a.sigma + (size_t)s * a.nM;
   const double M0 = a.M[0];
-
-  if (chunk == (int)gridDim.x - 1) {
-    // ---- low-mass CTA: warp w integrates model w, w + 4, ... (pyhalomodel.py:413-414) and writes the model's scalars
-    const double sg0 = sig[0], sg1 = sig[1];
-    for (int f = warp; f < a.F; f += HM_WS_THREADS / 32) {
-      const int b = s * a.F + f;
-      const hm_model_desc d = a.models ? a.models[b] : a.single;
-      const hm_family_consts c = hm_make_family_consts(d);
-      const double nu = d.dc / sg0;
-      double part = 0.;
-#pragma unroll 1
-      for (int j = 0; j < HM_GL_NODES / 32; ++j) part += hm_lowmass_node_shared(d, c, nu, lane + 32 * j);
-      const double A = 1. - hm_warp_sum(part);
-      if (lane == 0) {
-        const double Aterm = A / M0;                    // multiplies W(k, M[0]) for mass tracers (:541-542)
-        const double nu_hi = d.dc / sg1;
-        const double tw = 0.5 * (nu_hi - nu);
-        double g, bg;
-        hm_gb_nu_shared(d, c, nu, log(nu), g, bg);
-        double* sc = a.scal + (size_t)b * HM_NSCAL;
-        for (int p = 0; p < HM_MAXP; ++p) {
-          double cW = 0.;
-          if (p < a.P) {
-            const double rn = 1. / a.norm[p][b];
-            const double an = a.amplitude[p][(size_t)s * a.amp_stride[p]] * rn;
-            cW = (a.mode[p] == HM_GRID_UK) ? an : 1.;
-            if (p < 2) {
-              sc[HM_RSCAL + p] = (a.mode[p] == HM_GRID_UK) ? rn : 1.;       // s_p
-              sc[HM_RSCAL + 2 + p] = rn * rn;                               // rn_p^2
-              sc[HM_RSCAL + 4 + p] = a.mass[p] ? Aterm * cW : 0.;           // multiplies G_p(k, M0) in I_p
-            }
-          }
-          sc[4 + p] = cW;
-        }
-        sc[0] = A;
-        sc[1] = d.rhom;
-        sc[2] = tw * (bg * (1. / M0));
-        if (a.lowmass) a.lowmass[b] = A;
-      }
-    }
-    return;
-  }
 
   if (tid < a.F) {                                      // per-model constants: ready when the others reach the barrier
     const hm_model_desc dm = a.models ? a.models[s * a.F + tid] : a.single;
@@ -501,6 +459,48 @@ __global__ void __launch_bounds__(HM_WS_THREADS, HM_WS_MINB) hm_weights_sweep_ke
         wrow[(size_t)a.F * a.nMp + m] = twM * g;                         // w1: one-halo weight  (:530)
       } else if (m < a.nMp) {
         wrow[m] = 0.; wrow[(size_t)a.F * a.nMp + m] = 0.;
+      }
+    }
+  }
+  // ---- low-mass corrections A = 1 - int g b dnu (pyhalomodel.py:413-414) and the per-model scalars: the sample's models are
+  // dealt over the warps of its chunk CTAs (warp w of chunk c takes models w * nchunks + c, + 4 nchunks, ...), so the launch
+  // has no separate low-mass CTAs -- 1024 instead of 1536 CTAs for 512 samples, all resident at once ----
+  {
+    const double sg0 = sig[0], sg1 = sig[1];
+    for (int f = warp * (int)gridDim.x + chunk; f < a.F; f += (HM_WS_THREADS / 32) * (int)gridDim.x) {
+      const int b = s * a.F + f;
+      const hm_model_desc d = a.models ? a.models[b] : a.single;
+      const hm_family_consts c = hm_make_family_consts(d);
+      const double nu = d.dc / sg0;
+      double part = 0.;
+#pragma unroll 1
+      for (int j = 0; j < HM_GL_NODES / 32; ++j) part += hm_lowmass_node_shared(d, c, nu, lane + 32 * j);
+      const double A = 1. - hm_warp_sum(part);
+      if (lane == 0) {
+        const double Aterm = A / M0;                    // multiplies W(k, M[0]) for mass tracers (:541-542)
+        const double nu_hi = d.dc / sg1;
+        const double tw = 0.5 * (nu_hi - nu);
+        double g, bg;
+        hm_gb_nu_shared(d, c, nu, log(nu), g, bg);
+        double* sc = a.scal + (size_t)b * HM_NSCAL;
+        for (int p = 0; p < HM_MAXP; ++p) {
+          double cW = 0.;
+          if (p < a.P) {
+            const double rn = 1. / a.norm[p][b];
+            const double an = a.amplitude[p][(size_t)s * a.amp_stride[p]] * rn;
+            cW = (a.mode[p] == HM_GRID_UK) ? an : 1.;
+            if (p < 2) {
+              sc[HM_RSCAL + p] = (a.mode[p] == HM_GRID_UK) ? rn : 1.;       // s_p
+              sc[HM_RSCAL + 2 + p] = rn * rn;                               // rn_p^2
+              sc[HM_RSCAL + 4 + p] = a.mass[p] ? Aterm * cW : 0.;           // multiplies G_p(k, M0) in I_p
+            }
+          }
+          sc[4 + p] = cW;
+        }
+        sc[0] = A;
+        sc[1] = d.rhom;
+        sc[2] = tw * (bg * (1. / M0));
+        if (a.lowmass) a.lowmass[b] = A;
       }
     }
   }
@@ -1492,7 +1492,7 @@ extern "C" int hm_halo_weights(const hm_problem* pr, double* lowmass_dev, void* 
   } while (0)
   static const bool no_sweep_kernel = getenv("HALOB200_NO_SWEEP_WEIGHTS") != nullptr;      // (A/B switch for timing runs)
   if (L.rows && !red && !no_sweep_kernel) {
-    dim3 gs((L.nMp + HM_WS_THREADS * HM_WS_PER - 1) / (HM_WS_THREADS * HM_WS_PER) + 1, (unsigned)pr->n_samples);
+    dim3 gs((L.nMp + HM_WS_THREADS * HM_WS_PER - 1) / (HM_WS_THREADS * HM_WS_PER), (unsigned)pr->n_samples);
     hm_weights_sweep_kernel<<<gs, HM_WS_THREADS, 0, st>>>(a);
   } else if (L.rows) HM_WLAUNCH(2, true);
   else if (L.P <= 2) HM_WLAUNCH(2, false);
