@@ -25,7 +25,11 @@
 #define HM_GMAXP HM_GRAM_MAX_TRACERS
 #define HM_GMCH 32                 // masses per chunk = one stage of the ring (256-byte row segments)
 #define HM_GRK 4                   // wavenumbers per group; two MMA warps share a wavenumber
+#ifdef HM_GRAM_SIXTEEN_WARPS       // (layout experiment) 8 DMMA-only warps + 4 diagonal-work warps + 4 producer warps
+#define HM_GMMA_WARPS (3 * HM_GRK)
+#else
 #define HM_GMMA_WARPS (2 * HM_GRK)
+#endif
 #define HM_GNS 3                   // stages (64 KB each at 64 tracers)
 #define HM_GPROD_WARPS 4
 #define HM_GTHREADS (32 * (HM_GMMA_WARPS + HM_GPROD_WARPS))
@@ -33,6 +37,8 @@
 #define HM_GMMA_REGS 232           // (split-triangle layout)
 #define HM_GMMA_ALL_REGS 248       // whole-triangle MMA warps: 144 accumulator registers
 #define HM_GDIAG_REGS 152          // diagonal-work warps
+#define HM_G16_MMA_REGS 160        // sixteen-warp layout: launch at 128, DMMA warps 160, diagonal-work warps 112
+#define HM_G16_DIAG_REGS 112
 #define HM_GNSCAL 4
 #define HM_GNTS 3                  // per (model, tracer) scalars: shot noise, simple two-halo integral, c_p[M0]
 
@@ -228,9 +234,9 @@ template <int NBT, int H>
 struct hm_gram_own {       // what MMA-group warp role H does: H = 0, 1: half of the triangle and its diagonal work (block rows
                            // paired (I, NBT - 1 - I), pairs dealt alternately); H = 2: the whole triangle, no diagonal work;
                            // H = 3: the diagonal work of every block row, no DMMA
-  __host__ __device__ static constexpr bool half(int I) { return (((I < NBT - 1 - I) ? I : NBT - 1 - I) & 1) == H; }
-  __host__ __device__ static constexpr bool mma(int I) { return H == 2 || (H < 2 && half(I)); }
-  __host__ __device__ static constexpr bool diag(int I) { return H == 3 || (H < 2 && half(I)); }
+  __host__ __device__ static constexpr bool half(int I) { return (((I < NBT - 1 - I) ? I : NBT - 1 - I) & 1) == (H & 1); }
+  __host__ __device__ static constexpr bool mma(int I) { return H == 2 || ((H < 2 || H >= 4) && half(I)); }    // H = 4, 5: half
+  __host__ __device__ static constexpr bool diag(int I) { return H == 3 || (H < 2 && half(I)); }               // triangle, no diagonal work
   __host__ __device__ static constexpr int nblocks() {
     int n = 0;
     for (int I = 0; I < NBT; ++I)
@@ -419,16 +425,21 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
     const int c = pt & 15, pq = pt >> 4;                // 16-byte slot of a 256-byte row segment; tracer within a group of 8
     int s = 0;
     uint32_t parity = 0;
-    for (long long u = u0; u < u1; ++u) {
-      const long long G = u / a.CH;
-      const int ch = (int)(u - G * a.CH);
-      const int b = (int)(G / a.ngroups), g = (int)(G - (long long)b * a.ngroups);
+    // (group, chunk) cursor advanced by increments: no 64-bit divisions per unit (they made the role spend half its time
+    // on index arithmetic, and the MMA warps wait for its copies at the start of a kernel and after every group change)
+    long long G = u0 / a.CH;
+    int ch = (int)(u0 - G * a.CH);
+    int g = (int)(G % a.ngroups), b = (int)(G / a.ngroups);
+    const int nunits = (int)(u1 - u0);
+    // my 16-byte slots of a stage: (wavenumber r, tracer pg * 8 + pq), slot c XOR-swizzled by the tracer's parity
+    const uint32_t dst_thread = (uint32_t)((pq * 16 + (c ^ ((pq & 1) << 2))) * 16);
+    for (int n = 0; n < nunits; ++n) {
       const int smp = b / a.F, row0 = g * HM_GRK;
       const int m = ch * HM_GMCH + 2 * c;
       const bool in = m < a.nM;                         // nM is even: the two masses of a slot are in or out together
       hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);     // the MMA warps are done with the stage
-      const uint32_t dst0 = ring + (uint32_t)s * STAGE_BYTES;
-#pragma unroll 1
+      const uint32_t dst0 = ring + (uint32_t)s * STAGE_BYTES + dst_thread;
+#pragma unroll
       for (int r = 0; r < HM_GRK; ++r) {
         const int row = (row0 + r < a.nk) ? row0 + r : a.nk - 1;           // clamp: duplicates are never written
         const size_t off = ((size_t)smp * a.nk + row) * (size_t)a.nM + (in ? m : 0);
@@ -437,18 +448,33 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
           const int p = pg * 8 + pq;
           const bool on = in && p < P;
           const double* src = a.grid[on ? p : 0] + off;
-          const uint32_t dst = dst0 + (uint32_t)(((r * PT + p) * 16 + (c ^ ((p & 1) << 2))) * 16);
+          const uint32_t dst = dst0 + (uint32_t)((r * PT + pg * 8) * 16 * 16);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(on ? 16 : 0) : "memory");
         }
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full + 8 * s) : "memory");
       if (++s == HM_GNS) { s = 0; parity ^= 1u; }
+      if (++ch == a.CH) {
+        ch = 0;
+        if (++g == a.ngroups) { g = 0; ++b; }
+      }
     }
     return;
   }
 
   // ================================ MMA-group warps ================================
-#ifndef HM_GRAM_WHOLE_TRIANGLE
+#if defined(HM_GRAM_SIXTEEN_WARPS)
+  // (experiment) warps 2r, 2r + 1 (r = 0..3): the two halves of wavenumber r's triangle, DMMAs and fragment scaling only;
+  // warp 8 + r: the diagonal work of wavenumber r.  Two DMMA-only warps per scheduler.
+  if (warp < 2 * HM_GRK) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(HM_G16_MMA_REGS));
+    if (warp & 1) hm_gram_mma_role<NBT, 5>(a, gsm, bar_full, bar_empty, u0, u1, warp >> 1, lane);
+    else hm_gram_mma_role<NBT, 4>(a, gsm, bar_full, bar_empty, u0, u1, warp >> 1, lane);
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HM_G16_DIAG_REGS));
+    hm_gram_mma_role<NBT, 3>(a, gsm, bar_full, bar_empty, u0, u1, warp - 2 * HM_GRK, lane);
+  }
+#elif !defined(HM_GRAM_WHOLE_TRIANGLE)
   // warps 2r and 2r + 1 share wavenumber r: half of the triangle and of the diagonal work each
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(HM_GMMA_REGS));
   if (warp & 1) hm_gram_mma_role<NBT, 1>(a, gsm, bar_full, bar_empty, u0, u1, warp >> 1, lane);
