@@ -100,8 +100,9 @@ def build(G, nk, nM, tracers=('m', 'g', 'p'), families=(TINKER10,), seed=1234, f
                 N.append(Nc+Ns)
                 V.append(Vc+Vs)
             N, V = engine.to_dev(np.stack(N)), engine.to_dev(np.stack(V))
-            norm = torch.stack([engine.average(m.descriptor(), b.M, b.sigma[i//b.F], N[i//b.F])[0]
-                                for i, m in enumerate(b.models)])
+            # <N> under every model of the batch in one launch (the same kernel arithmetic as model.average, bit for bit)
+            norm = engine.average_batch(engine.pack_models([m.descriptor() for m in b.models]), b.M, b.sigma, N,
+                                        models_per_sample=b.F)
             b.tracers.append(engine.Tracer(engine.window_isothermal(b.k, b.rv), N, norm, variance=V,
                                            mode=_lib.GRID_UK, discrete_tracer=True))
         elif name == 'p':      # synthetic dimensionful pressure profile, amplitude=None (pyhalomodel.py:874-878)
