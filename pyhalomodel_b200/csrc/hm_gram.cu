@@ -23,14 +23,18 @@
 #include "hm_common.cuh"
 
 #define HM_GMAXP HM_GRAM_MAX_TRACERS
+#ifndef HM_GMCH
 #define HM_GMCH 32                 // masses per chunk = one stage of the ring (256-byte row segments)
+#endif
 #define HM_GRK 4                   // wavenumbers per group; two MMA warps share a wavenumber
 #ifdef HM_GRAM_SIXTEEN_WARPS       // (layout experiment) 8 DMMA-only warps + 4 diagonal-work warps + 4 producer warps
 #define HM_GMMA_WARPS (3 * HM_GRK)
 #else
 #define HM_GMMA_WARPS (2 * HM_GRK)
 #endif
+#ifndef HM_GNS
 #define HM_GNS 3                   // stages (64 KB each at 64 tracers)
+#endif
 #define HM_GPROD_WARPS 4
 #define HM_GTHREADS (32 * (HM_GMMA_WARPS + HM_GPROD_WARPS))
 #define HM_GPROD_REGS 40
@@ -422,7 +426,8 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
     // =============================== producer warps ===============================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HM_GPROD_REGS));
     const int pt = tid - 32 * HM_GMMA_WARPS;
-    const int c = pt & 15, pq = pt >> 4;                // 16-byte slot of a 256-byte row segment; tracer within a group of 8
+    constexpr int SLOTS = HM_GMCH / 2, TPG = 32 * HM_GPROD_WARPS / SLOTS;     // 16-byte slots of a row segment; tracers per pass
+    const int c = pt % SLOTS, pq = pt / SLOTS;          // my slot of a row segment; my tracer within a group of TPG
     int s = 0;
     uint32_t parity = 0;
     // (group, chunk) cursor advanced by increments: no 64-bit divisions per unit (they made the role spend half its time
@@ -432,7 +437,7 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
     int g = (int)(G % a.ngroups), b = (int)(G / a.ngroups);
     const int nunits = (int)(u1 - u0);
     // my 16-byte slots of a stage: (wavenumber r, tracer pg * 8 + pq), slot c XOR-swizzled by the tracer's parity
-    const uint32_t dst_thread = (uint32_t)((pq * 16 + (c ^ ((pq & 1) << 2))) * 16);
+    const uint32_t dst_thread = (uint32_t)((pq * SLOTS + (c ^ ((pq & 1) << 2))) * 16);
     for (int n = 0; n < nunits; ++n) {
       const int smp = b / a.F, row0 = g * HM_GRK;
       const int m = ch * HM_GMCH + 2 * c;
@@ -444,11 +449,11 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
         const int row = (row0 + r < a.nk) ? row0 + r : a.nk - 1;           // clamp: duplicates are never written
         const size_t off = ((size_t)smp * a.nk + row) * (size_t)a.nM + (in ? m : 0);
 #pragma unroll
-        for (int pg = 0; pg < PT / 8; ++pg) {
-          const int p = pg * 8 + pq;
+        for (int pg = 0; pg < PT / TPG; ++pg) {
+          const int p = pg * TPG + pq;
           const bool on = in && p < P;
           const double* src = a.grid[on ? p : 0] + off;
-          const uint32_t dst = dst0 + (uint32_t)((r * PT + pg * 8) * 16 * 16);
+          const uint32_t dst = dst0 + (uint32_t)((r * PT + pg * TPG) * SLOTS * 16);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(on ? 16 : 0) : "memory");
         }
       }
