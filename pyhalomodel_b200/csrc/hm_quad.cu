@@ -54,7 +54,7 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
 //   partial [B][nparts][nk][NW]     partial row sums over mass sub-ranges written by the quadrature kernel
 //                                   (streaming kernel: one part per consumer warp per 512-mass slice)
 // ---------------------------------------------------------------------------------------------------------------
-#define HM_NSCAL 20          // per model: A, rhom, w2[0], -, c_p[0] (8); row-per-lane sweeps: s_p (2), rn_p^2 (2), low-mass term (2), - (2)
+#define HM_NSCAL 24          // per model: A, rhom, w2[0], -, c_p[0] (8); row-per-lane sweeps: s_p (3), rn_p^2 (3), low-mass term (3), - (3)
 #define HM_RSCAL 12          // first of the row-per-lane kernel's per-(model, tracer) scalars
 #define HM_WCHUNK 256        // masses per CTA of the weights kernel
 #define HM_MC 512            // masses per slice of the streaming kernel per pair of columns a consumer thread owns
@@ -70,7 +70,8 @@ __global__ void hm_lowmass_kernel(const hm_model_desc* __restrict__ models, cons
 #ifndef HM_ROWS_CONSUMER_REGS
 #define HM_ROWS_CONSUMER_REGS 232
 #endif
-#define HM_ROWS_MAXF 5       // ... for 2..5 models per sample on one or two tracers
+#define HM_ROWS_MAXF 5       // ... for 2..5 models per sample on one to three tracers
+#define HM_ROWS_MAXP 3
 
 struct hm_layout {
   int P, S, NW, nMp, nchunks, nslices, nparts, MC;
@@ -104,9 +105,9 @@ static hm_layout hm_make_layout(const hm_problem* pr) {
   L.stream = hm_can_stream(pr);
   // wide slices (4 mass columns per consumer thread) halve the partial sums and the reductions per byte; they fit
   // the register budget up to 3 tracers and are used when the mass axis is long enough to fill them
-  // two to five mass functions per sample on one or two tracers (BASELINE config 3 has five): the row-per-lane
+  // two to five mass functions per sample on one to three tracers (BASELINE config 3 has five on two): the row-per-lane
   // kernel reads the shared grids once for all of them and combines its column groups itself (one part)
-  L.rows = L.stream && pr->models_per_sample >= 2 && pr->models_per_sample <= HM_ROWS_MAXF && L.P <= 2 && !pr->beta_dev;
+  L.rows = L.stream && pr->models_per_sample >= 2 && pr->models_per_sample <= HM_ROWS_MAXF && L.P <= HM_ROWS_MAXP && !pr->beta_dev;
   L.NVEC = 2 * pr->models_per_sample + 2 * L.P;
   L.MC = (pr->nM >= 2 * HM_MC && L.P <= 3 && !L.rows) ? 2 * HM_MC : HM_MC;
   L.nslices = L.stream ? (pr->nM + L.MC - 1) / L.MC : 1;
@@ -206,11 +207,11 @@ __global__ void __launch_bounds__(HM_WCHUNK, (PT <= 2) ? HM_WMINB : (PT <= 4 ? 3
             cW = (a.mode[p] == HM_GRID_UK) ? an : 1.;
             if (!ROWS) wout[(size_t)p * a.nMp] = a.mass[p] ? (w2_plain + Aterm) * cW : w2_plain * cW;   // e_p[0]
             if (a.mass[p]) low = Aterm * an;
-            if (ROWS && p < 2) {
+            if (ROWS && p < HM_ROWS_MAXP) {
               const double rn = 1. / a.norm[p][b];
               sc[HM_RSCAL + p] = (a.mode[p] == HM_GRID_UK) ? rn : 1.;       // s_p
-              sc[HM_RSCAL + 2 + p] = rn * rn;                               // rn_p^2
-              sc[HM_RSCAL + 4 + p] = a.mass[p] ? Aterm * cW : 0.;           // multiplies G_p(k, M0) in I_p
+              sc[HM_RSCAL + HM_ROWS_MAXP + p] = rn * rn;                               // rn_p^2
+              sc[HM_RSCAL + 2 * HM_ROWS_MAXP + p] = a.mass[p] ? Aterm * cW : 0.;           // multiplies G_p(k, M0) in I_p
             }
           }
           sc[4 + p] = cW;                               // w2[0] and c_p[0]: edge terms of the beta_NL integral
@@ -375,7 +376,7 @@ __global__ void __launch_bounds__(HM_WCHUNK, (PT <= 2) ? HM_WMINB : (PT <= 4 ? 3
 #define HM_WS_MINB 7
 #endif
 __global__ void __launch_bounds__(HM_WS_THREADS, HM_WS_MINB) hm_weights_sweep_kernel(const hm_weights_args a) {
-  constexpr int PT = 2;
+  constexpr int PT = HM_ROWS_MAXP;
   __shared__ hm_fam_consts<PT> sfc[HM_ROWS_MAXF];
   const int s = blockIdx.y, chunk = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -489,10 +490,10 @@ __global__ void __launch_bounds__(HM_WS_THREADS, HM_WS_MINB) hm_weights_sweep_ke
             const double rn = 1. / a.norm[p][b];
             const double an = a.amplitude[p][(size_t)s * a.amp_stride[p]] * rn;
             cW = (a.mode[p] == HM_GRID_UK) ? an : 1.;
-            if (p < 2) {
+            if (p < HM_ROWS_MAXP) {
               sc[HM_RSCAL + p] = (a.mode[p] == HM_GRID_UK) ? rn : 1.;       // s_p
-              sc[HM_RSCAL + 2 + p] = rn * rn;                               // rn_p^2
-              sc[HM_RSCAL + 4 + p] = a.mass[p] ? Aterm * cW : 0.;           // multiplies G_p(k, M0) in I_p
+              sc[HM_RSCAL + HM_ROWS_MAXP + p] = rn * rn;                               // rn_p^2
+              sc[HM_RSCAL + 2 * HM_ROWS_MAXP + p] = a.mass[p] ? Aterm * cW : 0.;           // multiplies G_p(k, M0) in I_p
             }
           }
           sc[4 + p] = cW;
@@ -851,7 +852,9 @@ struct hm_rows_cfg {
   static constexpr int CS = HM_ROWS_CS;                       // mass columns per stage
   static constexpr int BOXC = 16;                             // columns per grid box: 128 bytes, the swizzle span
   static constexpr int NBOX = CS / BOXC;
-  static constexpr int RT = 64;                               // rows per item
+  static constexpr int NR = (P <= 2) ? 2 : 1;                 // wavenumber rows per lane: 2 NR NV accumulator registers (100 at
+                                                              // P = 2, FM = 5; three tracers have NV = 9 FM sums per row: one row)
+  static constexpr int RT = 32 * NR;                          // rows per item
   static constexpr int BOX_BYTES = RT * BOXC * 8;
   static constexpr int DATA_BYTES = P * NBOX * BOX_BYTES;
   static constexpr int W_BYTES = NVEC * CS * 8;
@@ -882,13 +885,14 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
 #endif
                                                                           const __grid_constant__ CUtensorMap tmG0,
                                                                           const __grid_constant__ CUtensorMap tmG1,
+                                                                          const __grid_constant__ CUtensorMap tmG2,
                                                                           const __grid_constant__ CUtensorMap tmW) {
   using C = hm_rows_cfg<P, FM>;
-  constexpr int NW = C::NW, NV = C::NV, NS = C::NS, RT = C::RT, CS = C::CS;
+  constexpr int NW = C::NW, NV = C::NV, NS = C::NS, RT = C::RT, CS = C::CS, NR = C::NR;
   extern __shared__ unsigned char smem_dyn[];
   // SWIZZLE_128B boxes want 1024-byte aligned destinations
   unsigned char* smem_raw = smem_dyn + ((1024u - (hm_smem_addr(smem_dyn) & 1023u)) & 1023u);
-  double* comb = reinterpret_cast<double*>(smem_raw + (size_t)NS * C::STAGE_BYTES);        // [4 readers][NV][64 rows]
+  double* comb = reinterpret_cast<double*>(smem_raw + (size_t)NS * C::STAGE_BYTES);        // [4 readers][NV][RT rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * C::STAGE_BYTES + C::COMB_BYTES);
   const uint32_t ring = hm_smem_addr(smem_raw);
   const uint32_t bar_full = hm_smem_addr(bars), bar_empty = hm_smem_addr(bars + NS);
@@ -948,7 +952,8 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
           for (int p = 0; p < P; ++p)
 #pragma unroll
             for (int cb = 0; cb < C::NBOX; ++cb)
-              hm_tma_2d(dst + (uint32_t)((p * C::NBOX + cb) * C::BOX_BYTES), p == 0 ? &tmG0 : &tmG1, m0 + cb * C::BOXC, row,
+              hm_tma_2d(dst + (uint32_t)((p * C::NBOX + cb) * C::BOX_BYTES), p == 0 ? &tmG0 : (p == 1 ? &tmG1 : &tmG2), m0 + cb * C::BOXC,
+                        row,
                         bar_full + 8 * s);
           hm_tma_2d(dst + (uint32_t)C::DATA_BYTES, &tmW, m0, wrow, bar_full + 8 * s);
           if (++s == NS) { s = 0; parity ^= 1u; }
@@ -974,9 +979,9 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
     const int it = desc[item_no & 7u];
     if (it < 0) break;
     const int smp = it / a.ntiles, tile = it - smp * a.ntiles;
-    double acc[2][NV];
+    double acc[NR][NV];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
+    for (int r = 0; r < NR; ++r)
 #pragma unroll
       for (int j = 0; j < NV; ++j) acc[r][j] = 0.;
 #pragma unroll 1
@@ -991,22 +996,22 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
         // The barrier probe takes a few hundred cycles to answer even when the data is there: ask about the NEXT stage
         // in the middle of this one (the ring runs on across items; past the last stage the answer is never used)
         if (cp == 1) landed = hm_mbar_test(bar_full + 8 * sn, pn);
-        double2 x[2][P];                                      // [row][tracer] of this column pair
+        double2 x[NR][P];                                      // [row][tracer] of this column pair
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+        for (int r = 0; r < NR; ++r)
 #pragma unroll
           for (int p = 0; p < P; ++p)
             x[r][p] = *reinterpret_cast<const double2*>(stage + (size_t)(p * C::NBOX) * C::BOX_BYTES + r * (32 * 128) +
                                                         (cp == 0 ? xo0 : xo1));
         // basis values of my two rows and two columns, in the order of the sums: A_p G_p, T_p G_p^2, (A_u G_u)(A_v G_v).
         // The tracer factors are lane-uniform: broadcast 16-byte loads, like the mass-function weights below.
-        double2 v[2][NW];
+        double2 v[NR][NW];
 #pragma unroll
         for (int p = 0; p < P; ++p) {
           const double2 Av = *reinterpret_cast<const double2*>(wsm + ((2 * FM + p) * CS + 2 * cp) * 8);
           const double2 Tv = *reinterpret_cast<const double2*>(wsm + ((2 * FM + P + p) * CS + 2 * cp) * 8);
 #pragma unroll
-          for (int r = 0; r < 2; ++r) {
+          for (int r = 0; r < NR; ++r) {
             v[r][p] = make_double2(Av.x * x[r][p].x, Av.y * x[r][p].y);
             // no FMA contraction and T first: T = 0 (e.g. central galaxies) keeps the sum an exact zero
             v[r][P + p] = make_double2(__dmul_rn(__dmul_rn(Tv.x, x[r][p].x), x[r][p].x),
@@ -1020,7 +1025,7 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
 #pragma unroll
             for (int w = u + 1; w < P; ++w) {
 #pragma unroll
-              for (int r = 0; r < 2; ++r) v[r][idx] = make_double2(v[r][u].x * v[r][w].x, v[r][u].y * v[r][w].y);
+              for (int r = 0; r < NR; ++r) v[r][idx] = make_double2(v[r][u].x * v[r][w].x, v[r][u].y * v[r][w].y);
               ++idx;
             }
         }
@@ -1032,7 +1037,7 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
           for (int i = 0; i < NW; ++i) {
             const double2 w = (i < P) ? w2 : w1;
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
+            for (int r = 0; r < NR; ++r) {
               acc[r][f * NW + i] = fma(w.x, v[r][i].x, acc[r][f * NW + i]);
               acc[r][f * NW + i] = fma(w.y, v[r][i].y, acc[r][f * NW + i]);
             }
@@ -1055,11 +1060,13 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
     const int vw = (int)((warp - item_no) & 7u);
     // (fused epilogue) the root warp fetches P_lin of its rows now, so that the loads fly while it waits for the other
     // warps' sums instead of serialising behind the last hand-over
-    double pl[2] = {0., 0.};
+    double pl[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) pl[r] = 0.;
     if constexpr (FUSED) {
       if (vw == 0) {
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < NR; ++r) {
           const int row = tile * RT + r * 32 + lane;
           pl[r] = a.Pk_lin[(size_t)smp * a.nk + (row < a.nk ? row : a.nk - 1)];
         }
@@ -1075,9 +1082,9 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
         hm_mbar_wait(bar_pfull + 8 * xw, ph);
         const double* src = comb + (size_t)vw * C::COMB_DOUBLES + lane;
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+        for (int r = 0; r < NR; ++r)
 #pragma unroll
-          for (int j = 0; j < NV; ++j) acc[r][j] += src[j * 64 + r * 32];
+          for (int j = 0; j < NV; ++j) acc[r][j] += src[j * RT + r * 32];
         __syncwarp();
         if (lane == 0) hm_mbar_arrive(bar_pempty + 8 * xw);
       } else if (vw < 2 * step) {
@@ -1090,9 +1097,9 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
         hm_mbar_wait(bar_pempty + 8 * pred, pph);
         double* dst = comb + (size_t)t * C::COMB_DOUBLES + lane;
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
+        for (int r = 0; r < NR; ++r)
 #pragma unroll
-          for (int j = 0; j < NV; ++j) dst[j * 64 + r * 32] = acc[r][j];
+          for (int j = 0; j < NV; ++j) dst[j * RT + r * 32] = acc[r][j];
         __syncwarp();
         if (lane == 0) hm_mbar_arrive(bar_pfull + 8 * vw);
       }
@@ -1100,9 +1107,9 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
     if (vw == 0) {      // the item's RT x NV sums, coalesced over rows
       constexpr int S = C::S;
       // first mass column of my rows: the low-mass term A W(k, M0) / M0 of mass tracers (:541-542)
-      double g0[2][P];
+      double g0[NR][P];
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
+      for (int r = 0; r < NR; ++r) {
         const int row = tile * RT + r * 32 + lane;
 #pragma unroll
         for (int p = 0; p < P; ++p)
@@ -1115,9 +1122,11 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
         const double rhom = sc[1];
         double sp[P], rn2[P], low[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p) { sp[p] = sc[HM_RSCAL + p]; rn2[p] = sc[HM_RSCAL + 2 + p]; low[p] = sc[HM_RSCAL + 4 + p]; }
+        for (int p = 0; p < P; ++p) {
+          sp[p] = sc[HM_RSCAL + p]; rn2[p] = sc[HM_RSCAL + HM_ROWS_MAXP + p]; low[p] = sc[HM_RSCAL + 2 * HM_ROWS_MAXP + p];
+        }
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < NR; ++r) {
           const int row = tile * RT + r * 32 + lane;
           // the per-(model, tracer) factors the factored weights left out (hm_weights_kernel)
           double* t = &acc[r][f * NW];
@@ -1494,7 +1503,8 @@ extern "C" int hm_halo_weights(const hm_problem* pr, double* lowmass_dev, void* 
   if (L.rows && !red && !no_sweep_kernel) {
     dim3 gs((L.nMp + HM_WS_THREADS * HM_WS_PER - 1) / (HM_WS_THREADS * HM_WS_PER), (unsigned)pr->n_samples);
     hm_weights_sweep_kernel<<<gs, HM_WS_THREADS, 0, st>>>(a);
-  } else if (L.rows) HM_WLAUNCH(2, true);
+  } else if (L.rows && L.P <= 2) HM_WLAUNCH(2, true);
+  else if (L.rows) HM_WLAUNCH(4, true);
   else if (L.P <= 2) HM_WLAUNCH(2, false);
   else if (L.P <= 4) HM_WLAUNCH(4, false);
   else HM_WLAUNCH(8, false);
@@ -1594,9 +1604,9 @@ static int hm_launch_rows(hm_quad_args& a, bool fused, cudaStream_t st) {
   a.ntiles = (a.nk + C::RT - 1) / C::RT;
   const int G = a.B / FM;
   a.nitems = (long long)G * a.ntiles;                          // items enumerate (sample, row tile)
-  CUtensorMap tmG[2], tmW;
+  CUtensorMap tmG[HM_ROWS_MAXP], tmW;
   int rc;
-  for (int p = 0; p < 2; ++p)
+  for (int p = 0; p < HM_ROWS_MAXP; ++p)
     if ((rc = hm_make_tmap_2d(&tmG[p], a.gridW[p < P ? p : 0], (uint64_t)a.nM, (uint64_t)G * a.nk, (uint64_t)a.nM, C::BOXC,
                               C::RT, true)))
       return rc;
@@ -1605,17 +1615,17 @@ static int hm_launch_rows(hm_quad_args& a, bool fused, cudaStream_t st) {
   long long grid = hm_num_sms();
   if (grid > a.nitems) grid = a.nitems;
   HM_CUDA_TRY(cudaMemsetAsync(a.item_counter, 0, sizeof(int), st));
-  if (fused) hm_quad_rows_kernel<P, FM, true><<<(int)grid, HM_ROWS_THREADS, C::SMEM_BYTES, st>>>(a, tmG[0], tmG[1], tmW);
-  else hm_quad_rows_kernel<P, FM, false><<<(int)grid, HM_ROWS_THREADS, C::SMEM_BYTES, st>>>(a, tmG[0], tmG[1], tmW);
+  if (fused) hm_quad_rows_kernel<P, FM, true><<<(int)grid, HM_ROWS_THREADS, C::SMEM_BYTES, st>>>(a, tmG[0], tmG[1], tmG[2], tmW);
+  else hm_quad_rows_kernel<P, FM, false><<<(int)grid, HM_ROWS_THREADS, C::SMEM_BYTES, st>>>(a, tmG[0], tmG[1], tmG[2], tmW);
   HM_LAUNCH_CHECK();
   return HM_OK;
 }
 
 template <int P, int R>
 static int hm_launch_stream(hm_quad_args& a, bool rows, bool fused, cudaStream_t st) {
-  // two to five models per sample on one or two tracers (the five mass functions of BASELINE config 3) take the
+  // two to five models per sample on one to three tracers (the five mass functions of BASELINE config 3) take the
   // row-per-lane kernel, which reads the shared grids once; other combinations read them once per model
-  if constexpr (P <= 2) {
+  if constexpr (P <= HM_ROWS_MAXP) {
     if (rows) switch (a.F) {
       case 2: return hm_launch_rows<P, 2>(a, fused, st);
       case 3: return hm_launch_rows<P, 3>(a, fused, st);

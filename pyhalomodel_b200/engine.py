@@ -413,9 +413,9 @@ class PowerSpectrumPlan:
 
     def weight_vectors(self):
         """Per-mass weight vectors the quadrature kernel reads: P + S per model, or -- sweeps of 2..5 mass functions on
-        one or two tracers, where the weights are kept factored (hm_quad.cu) -- 2 F + 2 P per sample."""
+        one to three tracers, where the weights are kept factored (hm_quad.cu) -- 2 F + 2 P per sample."""
         F = self.B//self.G
-        rows = (2 <= F <= 5 and self.P <= 2 and self.nM % 2 == 0 and self.beta is None
+        rows = (2 <= F <= 5 and self.P <= 3 and self.nM % 2 == 0 and self.beta is None
                 and all(t.mode != _lib.GRID_SEPARATE for t in self.tracers))
         return self.G*(2*F+2*self.P) if rows else self.B*(self.P+self.S)
 

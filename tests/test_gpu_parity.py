@@ -421,6 +421,44 @@ def test_config3_full_shape_sweep_vs_oracle(halo):
                                          what='C3 sample %d %s %s term %d' % (g, name, key, t))
 
 
+@pytest.mark.parametrize('families,G,nk,nM', [(tuple(syn.FAMILY_NAMES), 40, 150, 206),
+                                              ((orc.TINKER10, orc.ST99), 5, 70, 1024),
+                                              ((orc.PS74, orc.SMT01, orc.DESPALI16), 3, 33, 94)])
+def test_three_tracer_sweep_vs_oracle_and_per_family_plans(halo, families, G, nk, nM):
+    """Sweeps of 2..5 mass functions on THREE tracers (matter, galaxies, a W(k, M) pressure grid: the tracers of config 2)
+    take the row-per-lane kernel with one wavenumber row per lane (32-row items, 9 F sums per row): against the ORACLE
+    directly for the first samples under default flags (fused epilogue) and with k_trunc / no shot-noise subtraction
+    (separate epilogue), and -- all samples, more items than SMs in the first case -- against single-family plans, which
+    take the per-model streaming kernel."""
+    from pyhalomodel_b200 import engine, workloads
+    batch = workloads.build(G, nk, nM, ('m', 'g', 'p'), families, seed=5, fiducial_first=True)
+    F, keys = len(families), ['m-m', 'm-g0', 'm-p', 'g0-g0', 'g0-p', 'p-p']
+    k, M = engine.to_host(batch.k), engine.to_host(batch.M)
+    for kw in ({}, dict(k_trunc=0.3, subtract_shotnoise=False)):
+        fused, A = batch.plan(**kw).run()
+        fused, A = fused.cpu().numpy().reshape(G, F, 6, 3, nk), A.cpu().numpy().reshape(G, F)
+        assert np.isfinite(fused).all()
+        for g in range(min(G, 2)):
+            meta = batch.meta[g]
+            sig, Pk = engine.to_host(batch.sigma[g]), engine.to_host(batch.Pk_lin[g])
+            for f, name in enumerate(families):
+                om = orc.make_model(meta['cosmo']['z'], meta['cosmo']['Om_m'], name=name, Dv=meta['Dv'], dc=meta['dc'])
+                want = orc.power_spectrum(om, k, Pk, M, sig, _oracle_profiles(om, dict(k=k, M=M, sigmaM=sig), [meta['hod']], True),
+                                          **kw)
+                for s, key in enumerate(keys):
+                    for t in range(3):
+                        assert_spectra_close(fused[g, f, s, t], want[t][key], rtol=RTOL,
+                                             what='sample %d %s %s term %d %s' % (g, name, key, t, kw))
+        for f in range(F):
+            tracers = [engine.Tracer(t.grid, t.amplitude, engine.to_dev(t.normalisation)[f::F].contiguous(),
+                                     variance=t.variance, mode=t.mode, mass_tracer=t.mass_tracer,
+                                     discrete_tracer=t.discrete_tracer) for t in batch.tracers]
+            models = [m.descriptor() for m in batch.models[f::F]]
+            single, A1 = engine.PowerSpectrumPlan(batch.k, batch.Pk_lin, batch.M, batch.sigma, tracers, models, **kw).run()
+            np.testing.assert_allclose(fused[:, f], single.cpu().numpy(), rtol=1e-12, atol=0., err_msg='%s %s' % (families[f], kw))
+            np.testing.assert_array_equal(A[:, f], A1.cpu().numpy())
+
+
 @pytest.mark.parametrize('names,nk,nM', [([orc.PS74, orc.DESPALI16], 70, 200), ([orc.ST99, orc.SMT01, orc.TINKER10, orc.PS74], 129, 94)])
 def test_sweep_kernel_wk_grid_tracer_and_ragged_shapes_vs_oracle(halo, names, nk, nM):
     """The row-per-lane sweep kernel with its factored weights on what the config-3 workload does not exercise: a tracer
