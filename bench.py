@@ -538,7 +538,19 @@ def measure_other_configs(args, engine, workloads, pipeline, syn, halo, event_ti
                      frac=ab/(q_ms*1e-3)/1e9/hbm_peak, step_frac=p2.algorithmic_bytes()/(st_ms*1e-3)/1e9/hbm_peak, bound='hbm')
     del b2, pp, p2
     torch.cuda.empty_cache()
-    # C4: 64 HOD tracers, 2080 unique spectra, 256 x 2048, Gram contraction on the FP64 tensor cores
+    # the config-3 sweep on config 2's three tracers (not a BASELINE config: the widened sweep kernel, one row per lane)
+    b3 = workloads.build(256, NK, NM, ('m', 'g', 'p'), tuple(syn.FAMILY_NAMES), seed=99)
+    p3 = b3.plan()
+    q_ms, st_ms = event_time(lambda: p3.quadrature(1), 20), event_time(p3.run, 20)
+    ab = p3.stream_kernel_bytes()
+    out['C3_three_tracers'] = dict(workload='256 samples x 5 mass functions, matter + galaxies + pressure, 6 unique spectra per model, '
+                                   '256 k x 1024 M', value=p3.B*p3.S/(st_ms*1e-3), unit=UNIT, ms_per_step=st_ms,
+                                   kernel='hm_quad_rows_kernel<3,5>', kernel_ms=q_ms, algorithmic_bytes=ab,
+                                   frac=ab/(q_ms*1e-3)/1e9/hbm_peak, step_frac=p3.algorithmic_bytes()/(st_ms*1e-3)/1e9/hbm_peak,
+                                   bound='hbm')
+    del b3, p3
+    torch.cuda.empty_cache()
+    # C4:64 HOD tracers, 2080 unique spectra, 256 x 2048, Gram contraction on the FP64 tensor cores
     b4 = workloads.build_many_tracer(64, 256, 2048)
     p4 = b4.gram_plan()
     p4.run()

@@ -2,7 +2,7 @@
 //   hm_sici              : scipy.special.sici as used by the reference (pyhalomodel.py:1033-1035, 1044-1049)
 //   hm_window_nfw        : _win_NFW         (pyhalomodel.py:1040-1062)
 //   hm_window_isothermal : _win_isothermal  (pyhalomodel.py:1029-1037)
-// FP64-ALU bound (two Chebyshev pairs + three sincos per NFW element); writes are coalesced along M.
+// FP64-ALU bound (two pairs of 12-term series + three sincos per NFW element); writes are coalesced along M.
 #include "hm_common.cuh"
 #include "hm_tables.h"
 
@@ -50,7 +50,8 @@ __device__ __forceinline__ int hm_sici_interval(double x) {
 // Si(x), Ci(x) for x >= 0 (odd / even continuation for x < 0, like Cephes).
 //   x <= 4: Si = x A(t), Ci = gamma + ln x + x^2 B(t), t affine in x^2
 //   x >  4: f = A(t)/x, g = B(t)/x^2, t affine in 1/x^2 on 23 intervals;  Si = pi/2 - f cos x - g sin x, Ci = f sin x - g cos x
-// One Clenshaw loop serves every interval, so mixed warps do not diverge.  Max error vs mpmath on [1e-9,1e3]:
+// A(t), B(t) are short power series in t (Chebyshev fits converted exactly, tools/gen_tables.py: as accurate as the
+// Clenshaw sum, half its operations); one Horner loop serves every interval, so mixed warps do not diverge.  Max error vs mpmath on [1e-9,1e3]:
 // Si 4.4e-16 relative, Ci 3.6e-15 absolute -- the same class as scipy's routine (tools/gen_tables.py, tests/).
 // WANT_CI = false skips what only Ci needs (the logarithm of the small-argument branch); HAVE_SC = true takes sin x and
 // cos x from the caller (sx, cx: of |x|) instead of calling sincos; rx returns 1/|x| (large-argument branch only).
@@ -64,17 +65,12 @@ __device__ __forceinline__ void hm_sici_core(double xin, const hm_sici_tables& T
   const double r2 = rx * rx;
   const double u = (iv == 0) ? x2 : r2;
   const double t = T.map[0][iv] * u + T.map[1][iv];
-  const double t2 = 2. * t;
-  double a1 = 0., a2 = 0., b1 = 0., b2 = 0.;
+  double Av = T.A[HM_SICI_NT - 1][iv], Bv = T.B[HM_SICI_NT - 1][iv];
 #pragma unroll
-  for (int n = HM_SICI_NT - 1; n >= 1; --n) {
-    const double a0 = fma(t2, a1, T.A[n][iv] - a2);
-    const double b0 = fma(t2, b1, T.B[n][iv] - b2);
-    a2 = a1; a1 = a0;
-    b2 = b1; b1 = b0;
+  for (int n = HM_SICI_NT - 2; n >= 0; --n) {        // Horner in t: one FMA per term and series
+    Av = fma(Av, t, T.A[n][iv]);
+    Bv = fma(Bv, t, T.B[n][iv]);
   }
-  const double Av = fma(t, a1, T.A[0][iv] - a2);
-  const double Bv = fma(t, b1, T.B[0][iv] - b2);
   ci = 0.;
   if (iv == 0) {
     si = x * Av;
@@ -163,7 +159,7 @@ __global__ void __launch_bounds__(256) hm_window_iso_kernel(const double* __rest
     const double kv = k[ik] * r_v;
     double si, ci, rx;
     hm_sici_core<false, false>(kv, T, 0., 0., si, ci, rx);
-    o[(size_t)ik * nM] = si / kv;                     // :1036
+    o[(size_t)ik * nM] = si * rx;                     // Si(kv) / kv (:1036) with the reciprocal the evaluation already has
   }
 }
 

@@ -891,7 +891,11 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
   constexpr int NW = C::NW, NV = C::NV, NS = C::NS, RT = C::RT, CS = C::CS, NR = C::NR;
   extern __shared__ unsigned char smem_dyn[];
   // SWIZZLE_128B boxes want 1024-byte aligned destinations
-  unsigned char* smem_raw = smem_dyn + ((1024u - (hm_smem_addr(smem_dyn) & 1023u)) & 1023u);
+  // (the padding is made opaque to the compiler, which otherwise recomputes it -- S2UR of the shared window, three integer
+  // operations and a scoreboard wait -- at the top of every stage instead of keeping one register)
+  uint32_t pad = (1024u - (hm_smem_addr(smem_dyn) & 1023u)) & 1023u;
+  asm volatile("" : "+r"(pad));
+  unsigned char* smem_raw = smem_dyn + pad;
   double* comb = reinterpret_cast<double*>(smem_raw + (size_t)NS * C::STAGE_BYTES);        // [4 readers][NV][RT rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)NS * C::STAGE_BYTES + C::COMB_BYTES);
   const uint32_t ring = hm_smem_addr(smem_raw);
@@ -970,8 +974,9 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
   // chunk index is XORed with (row & 7) (SWIZZLE_128B)
   const uint32_t boxoff = (uint32_t)(warp >> 2) * C::BOX_BYTES + (uint32_t)lane * 128u;
   const uint32_t q0 = 2u * (warp & 3), sw = lane & 7u;
-  const uint32_t xo0 = boxoff + (((q0) ^ sw) << 4), xo1 = boxoff + (((q0 + 1u) ^ sw) << 4);
-  const uint32_t wcol = 4u * warp * 8u;                            // byte offset of my columns in a weight row
+  uint32_t xo0 = boxoff + (((q0) ^ sw) << 4), xo1 = boxoff + (((q0 + 1u) ^ sw) << 4);
+  uint32_t wcol = 4u * warp * 8u;                                  // byte offset of my columns in a weight row
+  asm volatile("" : "+r"(xo0), "+r"(xo1), "+r"(wcol));            // (kept in registers: not rebuilt from %tid every stage)
   uint32_t landed = 0;                                        // the early probe of the current stage's barrier succeeded
   for (uint32_t item_no = 0;; ++item_no) {
     if (!landed) hm_mbar_wait(bar_full + 8 * s, parity);      // first stage of the next item, or the end marker
