@@ -45,9 +45,10 @@
 #define HM_G16_DIAG_REGS 112
 #define HM_GNSCAL 4
 #define HM_GNTS 3                  // per (model, tracer) scalars: shot noise, simple two-halo integral, c_p[M0]
+#define HM_GREC(PTK) (2 * (2 * (PTK) + 1))     // doubles per mass-pair record of the factor table: s [PTK], d [PTK], r2, x 2 masses
 
 struct hm_gram_layout {
-  int P, NB, PT, S, NW, nMp, nchunks, ngroups, CH, ncta, J;
+  int P, NB, PT, PTK, S, NW, nMp, nchunks, ngroups, CH, ncta, J;
   long long total;
   size_t B, gw_stride, scal_offset, tscal_offset, partial_offset, total_bytes;
 };
@@ -57,6 +58,7 @@ static hm_gram_layout hm_gram_make_layout(const hm_gram_problem* pr) {
   L.P = pr->n_tracers;
   L.NB = (L.P + 7) / 8;
   L.PT = 8 * L.NB;
+  L.PTK = (L.NB <= 2) ? 16 : (L.NB <= 4) ? 32 : 64;      // tracer rows of the kernel instance that runs (hm_gram_kernel<NBT>)
   L.S = L.P * (L.P + 1) / 2;
   L.NW = L.P + L.S;                       // [2h sums P][auto 1h P][cross 1h P(P-1)/2]
   L.nMp = (pr->nM + 1) & ~1;
@@ -71,7 +73,11 @@ static hm_gram_layout hm_gram_make_layout(const hm_gram_problem* pr) {
   const long long minu = L.total / L.ncta;               // >= 1
   L.J = (int)((L.CH + minu - 1) / minu) + 1;
   auto align = [](size_t x) { return (x + 31) & ~(size_t)31; };
-  L.gw_stride = (size_t)(3 + 2 * L.P) * L.nMp;          // w1, w2, s_p [P], d_p [P], r2
+  // per model: the vectors w1, w2, then one record per PAIR of masses with the factors the Gram kernel's lanes read:
+  // s_p [PTK], d_p [PTK], r2 as double2 over the two masses (HM_GREC doubles).  A lane's factors of a mass pair then sit
+  // at compile-time offsets from ONE address (tracer 8 I + fr is 8 I records on), instead of eight row pointers that the
+  // compiler rebuilt from the thread index for every 8-mass block (18 % of an MMA warp's stall samples).
+  L.gw_stride = (size_t)2 * L.nMp + (size_t)(L.nMp / 2) * HM_GREC(L.PTK);
   L.scal_offset = align(L.B * L.gw_stride);
   L.tscal_offset = align(L.scal_offset + L.B * HM_GNSCAL);
   L.partial_offset = align(L.tscal_offset + L.B * (size_t)L.P * HM_GNTS);
@@ -81,7 +87,7 @@ static hm_gram_layout hm_gram_make_layout(const hm_gram_problem* pr) {
 
 // ---------------------------------------------------------------------------------------------------------------
 struct hm_gram_wargs {
-  int nM, nMp, P, F;
+  int nM, nMp, P, PTK, F;
   int correct_discrete;
   int need_integrals;                 // the shot-noise / simple two-halo integrals enter the spectra (non-default flags)
   size_t gw_stride;
@@ -101,9 +107,10 @@ struct hm_gram_wargs {
   double* lowmass;
 };
 
-// grid (mass chunk, 1 + P, model): CTA row 0 writes w1, w2, r2 and integrates A; CTA row 1 + p writes tracer p's factors
-// s_p = sqrt(w1) c_p (W = c_p * grid, Y = s_p * grid) and d_p (auto one-halo weight).  Every row recomputes w1 for its
-// masses (one g(nu) per thread, identical code => identical bits), which keeps the whole preparation in ONE launch.
+// grid (mass chunk, 1 + PTK, model): CTA row 0 writes w1, w2, r2 and integrates A; CTA row 1 + p writes tracer p's factors
+// s_p = sqrt(w1) c_p (W = c_p * grid, Y = s_p * grid) and d_p (auto one-halo weight) into the mass-pair records (zeros for
+// the padding rows p >= P).  Every row recomputes w1 for its masses (one g(nu) per thread, identical code => identical
+// bits), which keeps the whole preparation in ONE launch.
 __global__ void __launch_bounds__(256) hm_gram_weights_kernel(const hm_gram_wargs a) {
   __shared__ double scratch[32];
   const int b = blockIdx.z, chunk = blockIdx.x, tid = threadIdx.x;
@@ -122,6 +129,12 @@ __global__ void __launch_bounds__(256) hm_gram_weights_kernel(const hm_gram_warg
   double* gw = a.gw + (size_t)b * a.gw_stride;
   const int m = chunk * 256 + tid;
   if (m >= a.nMp) return;
+  double* rec = gw + (size_t)2 * a.nMp + (size_t)(m >> 1) * HM_GREC(a.PTK) + (m & 1);      // my mass in its pair's record
+  if (role > a.P) {                                  // padding tracer row of the kernel instance: zero factors
+    rec[2 * (role - 1)] = 0.;
+    rec[2 * (a.PTK + role - 1)] = 0.;
+    return;
+  }
   double w1 = 0., w2 = 0.;
   if (m < a.nM) {
     const double nu = d.dc / sig[m];
@@ -136,7 +149,7 @@ __global__ void __launch_bounds__(256) hm_gram_weights_kernel(const hm_gram_warg
   if (role == 0) {
     gw[m] = w1;
     gw[(size_t)a.nMp + m] = w2;
-    gw[(size_t)(2 + 2 * a.P) * a.nMp + m] = (w1 > 0.) ? w2 / sqrt(w1) : 0.;   // sum_m w2 W_p = sum_m r2 Y_p  (:539)
+    rec[2 * (2 * a.PTK)] = (w1 > 0.) ? w2 / sqrt(w1) : 0.;                  // r2: sum_m w2 W_p = sum_m r2 Y_p  (:539)
     return;
   }
   const int p = role - 1;
@@ -157,8 +170,8 @@ __global__ void __launch_bounds__(256) hm_gram_weights_kernel(const hm_gram_warg
       t[2] = c;                                   // the low-mass term of the epilogue
     }
   }
-  gw[(size_t)(2 + p) * a.nMp + m] = (m < a.nM) ? sqrt(w1) * c : 0.;
-  gw[(size_t)(2 + a.P + p) * a.nMp + m] = dw;
+  rec[2 * p] = (m < a.nM) ? sqrt(w1) * c : 0.;
+  rec[2 * (a.PTK + p)] = dw;
 }
 
 // shot noise P_SN = rhom trapz((amp/norm^2) g/M) (:423-426) and the simple two-halo integral (:442-446)
@@ -274,19 +287,13 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
   uint32_t parity = 0;
   // The per-(tracer, mass) factors come from L1/L2 and do not depend on the ring: they are loaded ONE 8-mass block
   // ahead (also across chunk boundaries), so their latency hides behind the DMMAs of the current block.  The loads
-  // are unconditional -- a branch per tracer row would serialise their latencies: out-of-range masses and padding
-  // tracers read a clamped (finite) entry, and since the staged grid values are zero-filled there, every product
-  // below is an exact zero.
-  // Index arithmetic is kept off the critical path: 32-bit row offsets of my tracers' factor vectors once per kernel, and
-  // (group, chunk) cursors advanced by increments instead of 64-bit divisions per unit.
+  // are unconditional -- a branch per tracer row would serialise their latencies: out-of-range masses read a clamped
+  // (finite) record and padding tracers zero entries, and since the staged grid values are zero-filled there, every
+  // product below is an exact zero.
+  // Index arithmetic is kept off the critical path: one record address per block with the tracer rows at immediate
+  // offsets, and (group, chunk) cursors advanced by increments instead of 64-bit divisions per unit.
   double2 Sn[NBT], Dn[NR], r2n;
-  int rowS[NBT];
-#pragma unroll
-  for (int I = 0; I < NBT; ++I) {
-    const int p = 8 * I + fr;
-    rowS[I] = (2 + ((p < P) ? p : P - 1)) * a.nMp;
-  }
-  const int rowD = P * a.nMp, rowR = (2 + 2 * P) * a.nMp;
+  const int recbase = 2 * a.nMp + 2 * fr;               // (doubles) first record of a model's factor table, my tracer row
   long long G = u0 / a.CH;                              // group of the current unit, its chunk and its model's factors
   int ch = (int)(u0 - G * a.CH);
   int gin = (int)(G % a.ngroups);
@@ -295,12 +302,14 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
   auto load_factors = [&](const double* __restrict__ gw, int chn, int blk) {
     const int mm = chn * HM_GMCH + 8 * blk + 2 * fk;
     const int mc = (mm < a.nMp - 2) ? mm : a.nMp - 2;
-    if (Own::nrows() > 0) r2n = *reinterpret_cast<const double2*>(gw + (rowR + mc));
+    // the record of my mass pair: s of tracer 8 I + fr at entry 8 I, d at PT + 8 I, r2 at 2 PT (from my row: 2 PT - fr)
+    const double2* rec = reinterpret_cast<const double2*>(gw + (recbase + (mc >> 1) * HM_GREC(PT)));
+    if (Own::nrows() > 0) r2n = rec[2 * PT - fr];
     int i = 0;
 #pragma unroll
     for (int I = 0; I < NBT; ++I) {
-      Sn[I] = *reinterpret_cast<const double2*>(gw + (rowS[I] + mc));
-      if (Own::diag(I)) Dn[i++] = *reinterpret_cast<const double2*>(gw + (rowS[I] + rowD + mc));
+      Sn[I] = rec[8 * I];
+      if (Own::diag(I)) Dn[i++] = rec[PT + 8 * I];
     }
   };
   load_factors(gwb, ch, 0);
@@ -655,7 +664,7 @@ extern "C" int hm_gram_power_spectrum_stages(const hm_gram_problem* pr, double* 
   double* wsd = (double*)ws;
 
   hm_gram_wargs w;
-  w.nM = pr->nM; w.nMp = L.nMp; w.P = L.P; w.F = pr->models_per_sample; w.correct_discrete = pr->correct_discrete;
+  w.nM = pr->nM; w.nMp = L.nMp; w.P = L.P; w.PTK = L.PTK; w.F = pr->models_per_sample; w.correct_discrete = pr->correct_discrete;
   w.gw_stride = L.gw_stride; w.M = pr->M_dev; w.sigma = pr->sigma_dev; w.models = pr->models_dev;
   w.single = pr->model_host; w.grid_sample_stride = (size_t)pr->nk * pr->nM;
   for (int p = 0; p < HM_GMAXP; ++p) {
@@ -672,7 +681,7 @@ extern "C" int hm_gram_power_spectrum_stages(const hm_gram_problem* pr, double* 
   w.need_integrals = pr->simple_twohalo || ((pr->correct_discrete != 0) != (pr->subtract_shotnoise != 0));
   w.gw = wsd; w.scal = wsd + L.scal_offset; w.tscal = wsd + L.tscal_offset; w.lowmass = lowmass_dev;
   if (stages & 1) {
-    hm_gram_weights_kernel<<<dim3(L.nchunks, 1 + L.P, (unsigned)L.B), 256, 0, st>>>(w);
+    hm_gram_weights_kernel<<<dim3(L.nchunks, 1 + L.PTK, (unsigned)L.B), 256, 0, st>>>(w);
     HM_LAUNCH_CHECK();
     if (w.need_integrals) {      // shot noise / simple two-halo integrals: only non-default flags read them
       hm_gram_scalars_kernel<<<dim3(L.P, (unsigned)L.B), 256, 0, st>>>(w);
@@ -686,7 +695,7 @@ extern "C" int hm_gram_power_spectrum_stages(const hm_gram_problem* pr, double* 
   for (int p = 0; p < HM_GMAXP; ++p) g.grid[p] = (p < L.P) ? pr->tracers[p].grid_dev : nullptr;
   g.gw = wsd; g.partial = wsd + L.partial_offset;
   // the kernel is instantiated for block grids of 2, 4 and 8 (16, 32, 64 tracer rows); pad up to the next one
-  const int NBT = (L.NB <= 2) ? 2 : (L.NB <= 4) ? 4 : 8;
+  const int NBT = L.PTK / 8;
   const size_t smem = (size_t)HM_GNS * HM_GRK * (8 * NBT) * HM_GMCH * sizeof(double) + 64;
   static hm_once_per_device once;
   if (once.needed()) {
