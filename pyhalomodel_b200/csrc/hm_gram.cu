@@ -27,7 +27,9 @@
 #define HM_GMCH 32                 // masses per chunk = one stage of the ring (256-byte row segments)
 #endif
 #define HM_GRK 4                   // wavenumbers per group; two MMA warps share a wavenumber
-#ifdef HM_GRAM_SIXTEEN_WARPS       // (layout experiment) 8 DMMA-only warps + 4 diagonal-work warps + 4 producer warps
+#if defined(HM_GRAM_SIXTEEN_WARPS) || defined(HM_GRAM_THREE_WAY)
+// (layout experiments) SIXTEEN_WARPS: 8 DMMA-only warps + 4 diagonal-work warps + 4 producer warps; THREE_WAY: three MMA
+// warps per wavenumber, a third of its triangle (12 accumulator blocks) and of its diagonal work each, + 4 producer warps
 #define HM_GMMA_WARPS (3 * HM_GRK)
 #else
 #define HM_GMMA_WARPS (2 * HM_GRK)
@@ -43,6 +45,9 @@
 #define HM_GDIAG_REGS 152          // diagonal-work warps
 #define HM_G16_MMA_REGS 160        // sixteen-warp layout: launch at 128, DMMA warps 160, diagonal-work warps 112
 #define HM_G16_DIAG_REGS 112
+#ifndef HM_G3_MMA_REGS
+#define HM_G3_MMA_REGS 152         // three-way layout: launch at 128 (512 threads), producers 40, MMA warps 152
+#endif
 #define HM_GNSCAL 4
 #define HM_GNTS 3                  // per (model, tracer) scalars: shot noise, simple two-halo integral, c_p[M0]
 #define HM_GREC(PTK) (2 * (2 * (PTK) + 1))     // doubles per mass-pair record of the factor table: s [PTK], d [PTK], r2, x 2 masses
@@ -252,8 +257,16 @@ struct hm_gram_own {       // what MMA-group warp role H does: H = 0, 1: half of
                            // paired (I, NBT - 1 - I), pairs dealt alternately); H = 2: the whole triangle, no diagonal work;
                            // H = 3: the diagonal work of every block row, no DMMA
   __host__ __device__ static constexpr bool half(int I) { return (((I < NBT - 1 - I) ? I : NBT - 1 - I) & 1) == (H & 1); }
-  __host__ __device__ static constexpr bool mma(int I) { return H == 2 || ((H < 2 || H >= 4) && half(I)); }    // H = 4, 5: half
-  __host__ __device__ static constexpr bool diag(int I) { return H == 3 || (H < 2 && half(I)); }               // triangle, no diagonal work
+  // H = 6, 7, 8: a third of the triangle and its diagonal work -- block rows {0, 4}, {1, 3}, {2, 5, 6, 7} of eight (12 blocks
+  // each), {0}, {1}, {2, 3} of four, {0}, {1}, {} of two
+  __host__ __device__ static constexpr bool third(int I) {
+    return NBT == 8 ? (H == 6 ? (I == 0 || I == 4) : H == 7 ? (I == 1 || I == 3) : (I == 2 || I >= 5))
+                    : (H == 6 ? I == 0 : H == 7 ? I == 1 : I >= 2);
+  }
+  __host__ __device__ static constexpr bool mma(int I) {                                                       // H = 4, 5: half
+    return H >= 6 ? third(I) : (H == 2 || ((H < 2 || H >= 4) && half(I)));
+  }
+  __host__ __device__ static constexpr bool diag(int I) { return H >= 6 ? third(I) : (H == 3 || (H < 2 && half(I))); }   // triangle, no diagonal work
   __host__ __device__ static constexpr int nblocks() {
     int n = 0;
     for (int I = 0; I < NBT; ++I)
@@ -312,7 +325,12 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
       if (Own::diag(I)) Dn[i++] = rec[PT + 8 * I];
     }
   };
-  load_factors(gwb, ch, 0);
+#ifdef HM_GRAM_THREE_WAY           // no room for a block of factors in flight at 152 registers: load them with the fragments
+  constexpr bool PREFETCH = false;
+#else
+  constexpr bool PREFETCH = true;
+#endif
+  if (PREFETCH) load_factors(gwb, ch, 0);
   for (int n = 0; n < nunits; ++n) {
     // the unit after this one (for the factor prefetch and the end-of-group test)
     int chN = ch + 1, ginN = gin;
@@ -331,6 +349,7 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
 #pragma unroll BLKU
     for (int blk = 0; blk < HM_GMCH / 8; ++blk) {
       double2 X[NBT], Y[NBT];
+      if (!PREFETCH) load_factors(gwb, ch, blk);
 #pragma unroll
       for (int I = 0; I < NBT; ++I)
         X[I] = *reinterpret_cast<const double2*>(tile + (size_t)I * 8 * (HM_GMCH * 8) + ((((uint32_t)(4 * blk + fk)) ^ swz) << 4));
@@ -348,8 +367,10 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
       }
       // the factors have been used: fetch those of the next block (or of the first block of the next chunk) behind the
       // DMMAs below
-      if (blk < HM_GMCH / 8 - 1) load_factors(gwb, ch, blk + 1);
-      else if (!last_unit) load_factors(gwN, chN, 0);
+      if (PREFETCH) {
+        if (blk < HM_GMCH / 8 - 1) load_factors(gwb, ch, blk + 1);
+        else if (!last_unit) load_factors(gwN, chN, 0);
+      }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         int t = 0;
@@ -487,6 +508,15 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
   } else {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HM_G16_DIAG_REGS));
     hm_gram_mma_role<NBT, 3>(a, gsm, bar_full, bar_empty, u0, u1, warp - 2 * HM_GRK, lane);
+  }
+#elif defined(HM_GRAM_THREE_WAY)
+  // (experiment) warps 3r, 3r + 1, 3r + 2 share wavenumber r: three DMMA-issuing warps per scheduler instead of two
+  {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(HM_G3_MMA_REGS));
+    const int r = warp / 3, h = warp - 3 * r;
+    if (h == 0) hm_gram_mma_role<NBT, 6>(a, gsm, bar_full, bar_empty, u0, u1, r, lane);
+    else if (h == 1) hm_gram_mma_role<NBT, 7>(a, gsm, bar_full, bar_empty, u0, u1, r, lane);
+    else hm_gram_mma_role<NBT, 8>(a, gsm, bar_full, bar_empty, u0, u1, r, lane);
   }
 #elif !defined(HM_GRAM_WHOLE_TRIANGLE)
   // warps 2r and 2r + 1 share wavenumber r: half of the triangle and of the diagonal work each
