@@ -459,6 +459,36 @@ def test_three_tracer_sweep_vs_oracle_and_per_family_plans(halo, families, G, nk
             np.testing.assert_array_equal(A[:, f], A1.cpu().numpy())
 
 
+def test_sweep_kernel_random_shapes_vs_per_family_plans(halo):
+    """Seeded random draws over everything the row-per-lane sweep kernel is instantiated for -- one to three tracers, two to
+    five mass functions, item counts from one to several per SM, wavenumber tiles and mass stages of every raggedness down
+    to nk = 1 and nM = 2 -- against single-family plans (per-model streaming kernel), under default flags (fused epilogue)
+    and with k_trunc (separate epilogue)."""
+    from pyhalomodel_b200 import engine, workloads
+    rng = np.random.default_rng(2024)
+    shapes = [(1, 1, 2), (2, 31, 30), (3, 32, 32), (1, 33, 34), (7, 64, 66), (2, 65, 2)]
+    shapes += [(int(rng.integers(1, 40)), int(rng.integers(1, 200)), 2*int(rng.integers(1, 150))) for _ in range(8)]
+    for i, (G, nk, nM) in enumerate(shapes):
+        tracers = [('m',), ('m', 'g'), ('m', 'g', 'p'), ('g', 'p'), ('p', 'm', 'g')][i % 5]
+        F = 2+(i*3) % 4
+        fams = tuple(syn.FAMILY_NAMES[(i+j) % 5] for j in range(F))
+        batch = workloads.build(G, nk, nM, tracers, fams, seed=100+i, fiducial_first=False)
+        for kw in ({}, dict(k_trunc=0.5)):
+            fused, A = batch.plan(**kw).run()
+            S = fused.shape[1]
+            fused, A = fused.cpu().numpy().reshape(G, F, S, 3, nk), A.cpu().numpy().reshape(G, F)
+            assert np.isfinite(fused).all(), (G, nk, nM, tracers, fams, kw)
+            for f in range(F):
+                trs = [engine.Tracer(t.grid, t.amplitude, engine.to_dev(t.normalisation)[f::F].contiguous(),
+                                     variance=t.variance, mode=t.mode, mass_tracer=t.mass_tracer,
+                                     discrete_tracer=t.discrete_tracer) for t in batch.tracers]
+                single, A1 = engine.PowerSpectrumPlan(batch.k, batch.Pk_lin, batch.M, batch.sigma, trs,
+                                                      [m.descriptor() for m in batch.models[f::F]], **kw).run()
+                np.testing.assert_allclose(fused[:, f], single.cpu().numpy(), rtol=1e-12, atol=0.,
+                                           err_msg=str((G, nk, nM, tracers, fams[f], kw)))
+                np.testing.assert_array_equal(A[:, f], A1.cpu().numpy())
+
+
 @pytest.mark.parametrize('names,nk,nM', [([orc.PS74, orc.DESPALI16], 70, 200), ([orc.ST99, orc.SMT01, orc.TINKER10, orc.PS74], 129, 94)])
 def test_sweep_kernel_wk_grid_tracer_and_ragged_shapes_vs_oracle(halo, names, nk, nM):
     """The row-per-lane sweep kernel with its factored weights on what the config-3 workload does not exercise: a tracer
