@@ -54,15 +54,20 @@ __device__ __forceinline__ int hm_sici_interval(double x) {
 // Clenshaw sum, half its operations); one Horner loop serves every interval, so mixed warps do not diverge.  Max error vs mpmath on [1e-9,1e3]:
 // Si 4.4e-16 relative, Ci 3.6e-15 absolute -- the same class as scipy's routine (tools/gen_tables.py, tests/).
 // WANT_CI = false skips what only Ci needs (the logarithm of the small-argument branch); HAVE_SC = true takes sin x and
-// cos x from the caller (sx, cx: of |x|) instead of calling sincos; rx returns 1/|x| (large-argument branch only).
-template <bool WANT_CI, bool HAVE_SC>
+// cos x from the caller (sx, cx: of |x|) instead of calling sincos; rx returns 1/|x| (always with NEED_RX, otherwise only
+// where the large-argument branch needs it: the division is skipped for x <= 4).
+template <bool WANT_CI, bool HAVE_SC, bool NEED_RX>
 __device__ __forceinline__ void hm_sici_core(double xin, const hm_sici_tables& T, double sx, double cx, double& si, double& ci,
                                              double& rx) {
   const double x = fabs(xin);
   const int iv = hm_sici_interval(x);
   const double x2 = x * x;
-  rx = 1. / x;                                       // one division serves 1/x, 1/x^2 and the caller
-  const double r2 = rx * rx;
+  double r2 = 0.;
+  rx = 0.;
+  if (NEED_RX || iv != 0) {
+    rx = 1. / x;                                     // one division serves 1/x, 1/x^2 and the caller
+    r2 = rx * rx;
+  }
   const double u = (iv == 0) ? x2 : r2;
   const double t = T.map[0][iv] * u + T.map[1][iv];
   double Av = T.A[HM_SICI_NT - 1][iv], Bv = T.B[HM_SICI_NT - 1][iv];
@@ -89,7 +94,7 @@ __device__ __forceinline__ void hm_sici_core(double xin, const hm_sici_tables& T
 
 __device__ __forceinline__ void hm_sici_eval(double xin, const hm_sici_tables& T, double& si, double& ci) {
   double rx;
-  hm_sici_core<true, false>(xin, T, 0., 0., si, ci, rx);
+  hm_sici_core<true, false, false>(xin, T, 0., 0., si, ci, rx);
 }
 
 __global__ void __launch_bounds__(256) hm_sici_kernel(const double* __restrict__ x, long long n,
@@ -129,11 +134,12 @@ __global__ void __launch_bounds__(256) hm_window_nfw_kernel(const double* __rest
     const double kk = k[ik];
     const double kv = kk * r_v, ks = kk * r_s;        // :1046-1047
     const double ksv = ks + kv;
-    double s1, c1, s12, c12, Si_sv, Ci_sv, Si_s, Ci_s, r12, r1;
+    double s1, c1, s12 = 0., c12 = 0., Si_sv, Ci_sv, Si_s, Ci_s, r12, r1;
     sincos(ks, &s1, &c1);
-    sincos(ksv, &s12, &c12);
-    hm_sici_core<true, true>(ksv, T, s12, c12, Si_sv, Ci_sv, r12);      // :1048
-    hm_sici_core<true, true>(ks, T, s1, c1, Si_s, Ci_s, r1);            // :1049
+    if (ksv > 4.) sincos(ksv, &s12, &c12);            // only the large-argument branch of Si/Ci uses them (a warp holds
+                                                      // neighbouring masses of one wavenumber: the branch is mostly uniform)
+    hm_sici_core<true, true, true>(ksv, T, s12, c12, Si_sv, Ci_sv, r12);      // :1048
+    hm_sici_core<true, true, false>(ks, T, s1, c1, Si_s, Ci_s, r1);            // :1049
     const double f1 = c1 * (Ci_sv - Ci_s);
     const double f2 = s1 * (Si_sv - Si_s);
     const double f3 = sin(kv) * r12;                  // sin(kv)/(ks+kv) with the reciprocal of the Si/Ci evaluation (an
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(256) hm_window_iso_kernel(const double* __rest
   for (int ik = k0; ik < k1; ++ik) {
     const double kv = k[ik] * r_v;
     double si, ci, rx;
-    hm_sici_core<false, false>(kv, T, 0., 0., si, ci, rx);
+    hm_sici_core<false, false, true>(kv, T, 0., 0., si, ci, rx);
     o[(size_t)ik * nM] = si * rx;                     // Si(kv) / kv (:1036) with the reciprocal the evaluation already has
   }
 }

@@ -843,6 +843,13 @@ __device__ __forceinline__ void hm_tma_2d(uint32_t dst, const CUtensorMap* tm, i
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
+// the same copy with an L2 eviction-priority hint (the grids are read once: evict_first keeps them from displacing the
+// sample's weight vectors, which the other row tiles of the sample re-read from L2)
+__device__ __forceinline__ void hm_tma_2d_hint(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar), "l"(pol) : "memory");
+}
+
 template <int P, int FM>
 struct hm_rows_cfg {
   static constexpr int S = P * (P + 1) / 2;
@@ -936,6 +943,10 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(HM_ROWS_PRODUCER_REGS));
     if (warp == HM_CONSUMER_WARPS && lane == 0) {
       int it = blockIdx.x;
+#ifdef HM_ROWS_EVICT_FIRST
+      uint64_t pol;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
       for (uint32_t seq = 0;; ++seq) {
         const bool done = it >= nitems;
         hm_mbar_wait(bar_empty + 8 * s, parity ^ 1u);       // slot drained by all consumer warps (first stage of the item)
@@ -956,9 +967,13 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
           for (int p = 0; p < P; ++p)
 #pragma unroll
             for (int cb = 0; cb < C::NBOX; ++cb)
-              hm_tma_2d(dst + (uint32_t)((p * C::NBOX + cb) * C::BOX_BYTES), p == 0 ? &tmG0 : (p == 1 ? &tmG1 : &tmG2), m0 + cb * C::BOXC,
-                        row,
-                        bar_full + 8 * s);
+#ifdef HM_ROWS_EVICT_FIRST
+              hm_tma_2d_hint(dst + (uint32_t)((p * C::NBOX + cb) * C::BOX_BYTES), p == 0 ? &tmG0 : (p == 1 ? &tmG1 : &tmG2),
+                             m0 + cb * C::BOXC, row, bar_full + 8 * s, pol);
+#else
+              hm_tma_2d(dst + (uint32_t)((p * C::NBOX + cb) * C::BOX_BYTES), p == 0 ? &tmG0 : (p == 1 ? &tmG1 : &tmG2),
+                        m0 + cb * C::BOXC, row, bar_full + 8 * s);
+#endif
           hm_tma_2d(dst + (uint32_t)C::DATA_BYTES, &tmW, m0, wrow, bar_full + 8 * s);
           if (++s == NS) { s = 0; parity ^= 1u; }
         }
