@@ -53,12 +53,16 @@ __device__ __forceinline__ int hm_sici_interval(double x) {
 // A(t), B(t) are short power series in t (Chebyshev fits converted exactly, tools/gen_tables.py: as accurate as the
 // Clenshaw sum, half its operations); one Horner loop serves every interval, so mixed warps do not diverge.  Max error vs mpmath on [1e-9,1e3]:
 // Si 4.4e-16 relative, Ci 3.6e-15 absolute -- the same class as scipy's routine (tools/gen_tables.py, tests/).
-// WANT_CI = false skips what only Ci needs (the logarithm of the small-argument branch); HAVE_SC = true takes sin x and
+// CI = 0 skips what only Ci needs (the logarithm of the small-argument branch); CI = 2 returns, for x <= 4, only the series
+// part x^2 B(t) of Ci and sets `small`, so that a caller who needs a DIFFERENCE of two small-argument Ci values can add
+// ln(x1 / x2) once instead of two logarithms (hm_window_nfw_kernel: the ratio is 1 + c); CI = 3 returns Si(x) / x = A(t) in
+// `ci` for x <= 4 (no Ci at all); HAVE_SC = true takes sin x and
 // cos x from the caller (sx, cx: of |x|) instead of calling sincos; rx returns 1/|x| (always with NEED_RX, otherwise only
 // where the large-argument branch needs it: the division is skipped for x <= 4).
-template <bool WANT_CI, bool HAVE_SC, bool NEED_RX>
+template <int CI, bool HAVE_SC, bool NEED_RX>
 __device__ __forceinline__ void hm_sici_core(double xin, const hm_sici_tables& T, double sx, double cx, double& si, double& ci,
-                                             double& rx) {
+                                             double& rx, bool& small) {
+  constexpr bool WANT_CI = CI == 1 || CI == 2;
   const double x = fabs(xin);
   const int iv = hm_sici_interval(x);
   const double x2 = x * x;
@@ -77,9 +81,12 @@ __device__ __forceinline__ void hm_sici_core(double xin, const hm_sici_tables& T
     Bv = fma(Bv, t, T.B[n][iv]);
   }
   ci = 0.;
+  small = iv == 0;
   if (iv == 0) {
     si = x * Av;
-    if (WANT_CI) ci = 0.57721566490153286061 + log(x) + x2 * Bv;   // -inf at x = 0
+    if (CI == 1) ci = 0.57721566490153286061 + log(x) + x2 * Bv;   // -inf at x = 0
+    if (CI == 2) ci = x2 * Bv;
+    if (CI == 3) ci = Av;                              // Si(x) / x itself (hm_window_iso_kernel)
   } else {
     double s = sx, c = cx;
     if (!HAVE_SC) sincos(x, &s, &c);
@@ -94,7 +101,8 @@ __device__ __forceinline__ void hm_sici_core(double xin, const hm_sici_tables& T
 
 __device__ __forceinline__ void hm_sici_eval(double xin, const hm_sici_tables& T, double& si, double& ci) {
   double rx;
-  hm_sici_core<true, false, false>(xin, T, 0., 0., si, ci, rx);
+  bool small;
+  hm_sici_core<1, false, false>(xin, T, 0., 0., si, ci, rx, small);
 }
 
 __global__ void __launch_bounds__(256) hm_sici_kernel(const double* __restrict__ x, long long n,
@@ -124,7 +132,8 @@ __global__ void __launch_bounds__(256) hm_window_nfw_kernel(const double* __rest
   if (m >= nM || gs * (long long)nk * nM >= total) return;
   const double r_v = rv[gs * nM + m], c = conc[gs * nM + m];
   const double r_s = r_v / c;                         // :1045
-  const double f4 = log(1. + c) - c / (1. + c);       // :1062
+  const double l1pc = log(1. + c);
+  const double f4 = l1pc - c / (1. + c);              // :1062
   const double rf4 = 1. / f4;
   double* o = out + gs * (long long)nk * nM + m;
   const int kper = (nk + (int)gridDim.y - 1) / (int)gridDim.y;        // wavenumbers per CTA row (small batches split k too)
@@ -138,9 +147,18 @@ __global__ void __launch_bounds__(256) hm_window_nfw_kernel(const double* __rest
     sincos(ks, &s1, &c1);
     if (ksv > 4.) sincos(ksv, &s12, &c12);            // only the large-argument branch of Si/Ci uses them (a warp holds
                                                       // neighbouring masses of one wavenumber: the branch is mostly uniform)
-    hm_sici_core<true, true, true>(ksv, T, s12, c12, Si_sv, Ci_sv, r12);      // :1048
-    hm_sici_core<true, true, false>(ks, T, s1, c1, Si_s, Ci_s, r1);            // :1049
-    const double f1 = c1 * (Ci_sv - Ci_s);
+    bool small_sv, small_s;
+    hm_sici_core<2, true, true>(ksv, T, s12, c12, Si_sv, Ci_sv, r12, small_sv);      // :1048
+    hm_sici_core<2, true, false>(ks, T, s1, c1, Si_s, Ci_s, r1, small_s);            // :1049
+    // Ci(ks + kv) - Ci(ks): with both arguments on the small branch the logarithms combine to ln((ks + kv) / ks) = ln(1 + c),
+    // a per-mass constant; otherwise (ks <= 4 < ks + kv) the small one gets its gamma + ln x back
+    double dCi;
+    if (small_sv) dCi = l1pc + (Ci_sv - Ci_s);          // (ks < ks + kv: both small)
+    else {
+      if (small_s) Ci_s = 0.57721566490153286061 + log(ks) + Ci_s;
+      dCi = Ci_sv - Ci_s;
+    }
+    const double f1 = c1 * dCi;
     const double f2 = s1 * (Si_sv - Si_s);
     const double f3 = sin(kv) * r12;                  // sin(kv)/(ks+kv) with the reciprocal of the Si/Ci evaluation (an
                                                       // angle-subtraction sin(kv) costs 1e-11 where U cancels to 3e-5)
@@ -164,8 +182,10 @@ __global__ void __launch_bounds__(256) hm_window_iso_kernel(const double* __rest
   for (int ik = k0; ik < k1; ++ik) {
     const double kv = k[ik] * r_v;
     double si, ci, rx;
-    hm_sici_core<false, false, true>(kv, T, 0., 0., si, ci, rx);
-    o[(size_t)ik * nM] = si * rx;                     // Si(kv) / kv (:1036) with the reciprocal the evaluation already has
+    bool small;
+    hm_sici_core<3, false, false>(kv, T, 0., 0., si, ci, rx, small);
+    // Si(kv) / kv (:1036): the series itself for kv <= 4, else with the reciprocal the evaluation already has
+    o[(size_t)ik * nM] = small ? ci : si * rx;
   }
 }
 
