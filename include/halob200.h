@@ -217,6 +217,10 @@ int hm_window_nfw(const double* k_dev, const double* rv_dev, const double* c_dev
                   int32_t G, double* out_dev, void* stream);
 int hm_window_isothermal(const double* k_dev, const double* rv_dev, int32_t nk, int32_t nM, int32_t G,
                          double* out_dev, void* stream);
+/* Both windows of the same radii in one pass (window_function(k, rv, c, 'NFW') and window_function(k, rv,
+ * profile='isothermal'), pyhalomodel.py:1006-1062): the matter + galaxy pair of a sweep. */
+int hm_window_nfw_isothermal(const double* k_dev, const double* rv_dev, const double* c_dev, int32_t nk, int32_t nM,
+                             int32_t G, double* nfw_out_dev, double* iso_out_dev, void* stream);
 
 /* W(k,M) = int_0^rv j0(k r) P(r;M) dr on R = linspace(0, rv, nr) by a sample rule (profile.configuration with
  * win_integration in {trapezoid, simps, romb}; _halo_window, pyhalomodel.py:930-961).  profile_samples_dev:

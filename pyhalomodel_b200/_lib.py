@@ -86,6 +86,8 @@ _SIGNATURES = {
                                 C.c_void_p]),
     'hm_window_isothermal': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_void_p]),
+    'hm_window_nfw_isothermal': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]),
     'hm_window_configuration': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_void_p]),
     'hm_measure_fp64_peaks': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]),

@@ -121,9 +121,13 @@ __global__ void __launch_bounds__(256) hm_sici_kernel(const double* __restrict__
 // CTA = (sample, 256 masses); a thread keeps its mass and walks the wavenumbers, so r_s, the NFW factor and its
 // reciprocal are computed once per thread instead of once per element, and the stores stay coalesced along M.  Two
 // sincos per element serve both Si/Ci evaluations (round 1 called sincos up to three times and sin once).
+// WITH_ISO: the isothermal window Si(kv) / kv of the same radii as well (matter NFW + isothermal galaxies is the sweep's
+// pair of tracers): it shares the loop, the wavenumber loads and the sine of kv with the NFW element.
+template <bool WITH_ISO>
 __global__ void __launch_bounds__(256) hm_window_nfw_kernel(const double* __restrict__ k, const double* __restrict__ rv,
                                                             const double* __restrict__ conc, int nk, int nM,
-                                                            long long total, double* __restrict__ out) {
+                                                            long long total, double* __restrict__ out,
+                                                            double* __restrict__ out_iso) {
   __shared__ hm_sici_tables T;
   hm_sici_load_tables(T);
   const int mblocks = (nM + 255) / 256;
@@ -136,6 +140,7 @@ __global__ void __launch_bounds__(256) hm_window_nfw_kernel(const double* __rest
   const double f4 = l1pc - c / (1. + c);              // :1062
   const double rf4 = 1. / f4;
   double* o = out + gs * (long long)nk * nM + m;
+  double* oi = WITH_ISO ? out_iso + gs * (long long)nk * nM + m : nullptr;
   const int kper = (nk + (int)gridDim.y - 1) / (int)gridDim.y;        // wavenumbers per CTA row (small batches split k too)
   const int k0 = (int)blockIdx.y * kper, k1 = (k0 + kper < nk) ? k0 + kper : nk;
 #pragma unroll 2
@@ -160,9 +165,18 @@ __global__ void __launch_bounds__(256) hm_window_nfw_kernel(const double* __rest
     }
     const double f1 = c1 * dCi;
     const double f2 = s1 * (Si_sv - Si_s);
-    const double f3 = sin(kv) * r12;                  // sin(kv)/(ks+kv) with the reciprocal of the Si/Ci evaluation (an
+    double sv, cv = 0.;
+    if (WITH_ISO && kv > 4.) sincos(kv, &sv, &cv);
+    else sv = sin(kv);
+    const double f3 = sv * r12;                       // sin(kv)/(ks+kv) with the reciprocal of the Si/Ci evaluation (an
                                                       // angle-subtraction sin(kv) costs 1e-11 where U cancels to 3e-5)
     o[(size_t)ik * nM] = (f1 + f2 - f3) * rf4;
+    if (WITH_ISO) {                                   // Si(kv) / kv (:1036), as in hm_window_iso_kernel
+      double si, ci, rx;
+      bool small;
+      hm_sici_core<3, true, false>(kv, T, sv, cv, si, ci, rx, small);
+      oi[(size_t)ik * nM] = small ? ci : si * rx;
+    }
   }
 }
 
@@ -222,7 +236,21 @@ extern "C" int hm_window_nfw(const double* k_dev, const double* rv_dev, const do
   HM_REQUIRE(k_dev && rv_dev && c_dev && out_dev, "NULL pointer");
   HM_REQUIRE(nk > 0 && nM > 0 && G > 0, "empty grid");
   const long long total = (long long)G * nk * nM;
-  hm_window_nfw_kernel<<<hm_window_grid(nk, nM, G), 256, 0, (cudaStream_t)stream>>>(k_dev, rv_dev, c_dev, nk, nM, total, out_dev);
+  hm_window_nfw_kernel<false><<<hm_window_grid(nk, nM, G), 256, 0, (cudaStream_t)stream>>>(k_dev, rv_dev, c_dev, nk, nM, total,
+                                                                                          out_dev, nullptr);
+  HM_LAUNCH_CHECK();
+  return HM_OK;
+}
+
+extern "C" int hm_window_nfw_isothermal(const double* k_dev, const double* rv_dev, const double* c_dev, int32_t nk, int32_t nM,
+                                        int32_t G, double* nfw_out_dev, double* iso_out_dev, void* stream) {
+  int rc = hm_check_device();
+  if (rc) return rc;
+  HM_REQUIRE(k_dev && rv_dev && c_dev && nfw_out_dev && iso_out_dev, "NULL pointer");
+  HM_REQUIRE(nk > 0 && nM > 0 && G > 0, "empty grid");
+  const long long total = (long long)G * nk * nM;
+  hm_window_nfw_kernel<true><<<hm_window_grid(nk, nM, G), 256, 0, (cudaStream_t)stream>>>(k_dev, rv_dev, c_dev, nk, nM, total,
+                                                                                         nfw_out_dev, iso_out_dev);
   HM_LAUNCH_CHECK();
   return HM_OK;
 }

@@ -104,7 +104,13 @@ def to_host(t):
     return t.detach().cpu().numpy()
 
 
+_RAW_STREAM = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def _stream():
+    # (torch.cuda.current_stream() builds a Stream object through several Python layers: 20 us per kernel launch)
+    if _RAW_STREAM is not None:
+        return C.c_void_p(_RAW_STREAM(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -242,6 +248,20 @@ def window_nfw(k, rv, c, out=None):
         out = torch.empty((G, k.shape[0], nM), dtype=F64, device=k.device)
     check(lib().hm_window_nfw(_ptr(k), _ptr(rv), _ptr(c), k.shape[0], nM, G, _ptr(out), _stream()))
     return out if batched else out[0]
+
+
+def window_nfw_isothermal(k, rv, c, out_nfw=None, out_iso=None):
+    """Both windows of the same radii in one launch: (window_nfw(k, rv, c), window_isothermal(k, rv)), the matter + galaxy
+    pair of a sweep (the isothermal element shares the loop and the sine of k rv with the NFW one)."""
+    k, rv, c = to_dev(k), to_dev(rv), to_dev(c)
+    batched = rv.dim() == 2
+    G, nM = (rv.shape if batched else (1, rv.shape[0]))
+    if out_nfw is None:
+        out_nfw = torch.empty((G, k.shape[0], nM), dtype=F64, device=k.device)
+    if out_iso is None:
+        out_iso = torch.empty((G, k.shape[0], nM), dtype=F64, device=k.device)
+    check(lib().hm_window_nfw_isothermal(_ptr(k), _ptr(rv), _ptr(c), k.shape[0], nM, G, _ptr(out_nfw), _ptr(out_iso), _stream()))
+    return (out_nfw, out_iso) if batched else (out_nfw[0], out_iso[0])
 
 
 def window_isothermal(k, rv, out=None):

@@ -5,7 +5,7 @@ End-to-end evaluation from a linear spectrum (BASELINE config 5): for every samp
 entirely on the device, in chunks sized for HBM.  Only a handful of scalars per sample cross PCIe (cosmology and HOD
 parameters in; spectra out), or nothing at all when the caller keeps the results on the device.
 
-Every stage is a libhalob200 kernel (hm_sigma_tophat, hm_window_nfw, hm_window_isothermal, hm_average_batch,
+Every stage is a libhalob200 kernel (hm_sigma_tophat, hm_window_nfw_isothermal, hm_average_batch,
 hm_power_spectrum) except the element-wise vector preparations (radii, Duffy concentrations, Zheng05 occupation
 numbers, BBKS transfer function), which are a few torch ops on [chunk, nM] / [chunk, nkg] tensors.
 
@@ -85,8 +85,9 @@ class EndToEnd:
         rho_m = torch.as_tensor(np.ascontiguousarray(desc['rhom']), device=dev)
         # 6. Fourier profiles and spectra
         Mamp = self.M[None, :].expand(G, -1).contiguous()
-        tracers = [engine.Tracer(engine.window_nfw(self.k, rv, conc), Mamp, rho_m, mode=_lib.GRID_UK, mass_tracer=True),
-                   engine.Tracer(engine.window_isothermal(self.k, rv), N, rho_g, variance=V, mode=_lib.GRID_UK,
+        Um, Ug = engine.window_nfw_isothermal(self.k, rv, conc)       # both windows of the sample's radii in one launch
+        tracers = [engine.Tracer(Um, Mamp, rho_m, mode=_lib.GRID_UK, mass_tracer=True),
+                   engine.Tracer(Ug, N, rho_g, variance=V, mode=_lib.GRID_UK,
                                  discrete_tracer=True)]
         plan = engine.PowerSpectrumPlan(self.k, Pk, self.M, sigma, tracers, mdev, models_per_sample=F)
         out, lowmass = plan.run()

@@ -207,11 +207,11 @@ class HostSweep:
             with torch.cuda.stream(self.s_run):
                 self.s_run.wait_event(sl['up'])
                 self.s_run.wait_event(sl['down'])        # the previous download of this slot's spectra has finished
-                engine.window_nfw(self.k, sl['rv'], sl['c'], out=sl['Um'])
                 if self.galaxy_window == 'NFW':
+                    engine.window_nfw(self.k, sl['rv'], sl['c'], out=sl['Um'])
                     sl['Ug'].copy_(sl['Um'])
                 else:
-                    engine.window_isothermal(self.k, sl['rv'], out=sl['Ug'])
+                    engine.window_nfw_isothermal(self.k, sl['rv'], sl['c'], out_nfw=sl['Um'], out_iso=sl['Ug'])
                 rec = sl['models'].view(torch.float64).view(-1, 15)       # hm_model_desc = 15 doubles; [2] is rhom
                 sl['norm_m'].copy_(rec[:, 2])
                 engine.average_batch(sl['models'], self.M, sl['sigma'], sl['N'], models_per_sample=self.F, out=sl['norm_g'])

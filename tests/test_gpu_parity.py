@@ -78,6 +78,21 @@ def test_sici_and_windows(halo):
         halo.window_function(k, rv, profile='bogus')
 
 
+def test_fused_nfw_isothermal_windows_equal_the_separate_kernels():
+    """hm_window_nfw_isothermal (both windows of the same radii in one launch, as sweep.HostSweep and pipeline.EndToEnd use
+    them) reproduces hm_window_nfw and hm_window_isothermal bit for bit, batched and single, ragged shapes."""
+    from pyhalomodel_b200 import engine
+    rng = np.random.default_rng(8)
+    for G, nk, nM in [(3, 50, 300), (1, 256, 1024), (5, 7, 33)]:
+        k = syn.k_grid(nk, 1e-4, 1e2)
+        rv = 10**rng.uniform(-2.5, 1., size=(G, nM))
+        c = rng.uniform(1.5, 25., size=(G, nM))
+        Um, Ug = engine.window_nfw_isothermal(k, rv, c)
+        assert torch.equal(Um, engine.window_nfw(k, rv, c)) and torch.equal(Ug, engine.window_isothermal(k, rv))
+        Um1, Ug1 = engine.window_nfw_isothermal(k, rv[0], c[0])
+        assert torch.equal(Um1, Um[0]) and torch.equal(Ug1, Ug[0])
+
+
 def test_sici_interval_edges_and_dense_points():
     """The device Si/Ci picks one of 24 Chebyshev intervals from the bits of x (hm_sici_interval): both sides of every
     interval edge and a dense random set up to x = 300 against scipy.special.sici, at the tolerances of the golden test."""

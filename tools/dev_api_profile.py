@@ -29,4 +29,4 @@ torch.cuda.synchronize(); print('per call %.3f ms' % ((time.perf_counter()-t0)/5
 pr = cProfile.Profile(); pr.enable()
 for _ in range(50): call()
 pr.disable()
-pstats.Stats(pr).sort_stats('tottime').print_stats(22)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(45)

@@ -14,4 +14,6 @@ def t(fn, reps=10):
     return e0.elapsed_time(e1)/reps
 n = G*256*1024
 tn, ti = t(lambda: engine.window_nfw(b.k, b.rv, b.c)), t(lambda: engine.window_isothermal(b.k, b.rv))
-print('windows G=%d: NFW %.3f ms (%.1f G elements/s), isothermal %.3f ms (%.1f G elements/s)' % (G, tn, n/tn/1e6, ti, n/ti/1e6))
+tf = t(lambda: engine.window_nfw_isothermal(b.k, b.rv, b.c))
+print('windows G=%d: NFW %.3f ms (%.1f G elements/s), isothermal %.3f ms (%.1f G elements/s), both in one launch %.3f ms'
+      % (G, tn, n/tn/1e6, ti, n/ti/1e6, tf))
