@@ -77,7 +77,8 @@ struct hm_layout {
   int P, S, NW, nMp, nchunks, nslices, nparts, MC;
   int NVEC;                  // row-per-lane sweeps: factored weight vectors per SAMPLE (2 F + 2 P)
   bool stream, rows;
-  size_t B, scal_offset, cpart_offset, partial_offset, inl_offset, counter_offset, total_bytes;
+  size_t B, scal_offset, cpart_offset, partial_offset, inl_offset, bpart_offset, bcount_offset, counter_offset, total_bytes;
+  int bsplit;                // beta_NL: row chunks per (model, wavenumber) matrix, one CTA each
 };
 
 static bool hm_can_stream(const hm_problem* pr) {
@@ -120,7 +121,20 @@ static hm_layout hm_make_layout(const hm_problem* pr) {
   L.cpart_offset = align(L.scal_offset + L.B * HM_NSCAL);
   L.partial_offset = align(L.cpart_offset + L.B * (size_t)(L.nchunks + 1) * 2 * HM_MAXP);
   L.inl_offset = align(L.partial_offset + L.B * (size_t)L.nparts * L.NW * (size_t)pr->nk);
-  L.counter_offset = align(L.inl_offset + (pr->beta_dev ? L.B * (size_t)L.S * pr->nk : 0));      // sweep kernel: item queue
+  // beta_NL: a (model, k) matrix is one CTA's worth of streaming (8 MB at 1024 masses), and B nk CTAs seldom divide evenly
+  // over the SMs (256 over 148: the SMs with two take twice as long, 0.81 of the HBM peak); cut every matrix into row chunks
+  // so that there are at least six CTAs per SM, each with its own partial sums, finished by the last chunk to arrive
+  L.bsplit = 1;
+  if (pr->beta_dev) {
+    const long long mats = (long long)L.B * pr->nk;
+    long long sp = (6LL * hm_num_sms() + mats - 1) / mats;
+    const long long most = (pr->nM + 63) / 64;                     // at least 64 rows per chunk
+    sp = sp > most ? most : sp;
+    L.bsplit = (int)(sp < 1 ? 1 : (sp > 16 ? 16 : sp));
+  }
+  L.bpart_offset = align(L.inl_offset + (pr->beta_dev ? L.B * (size_t)L.S * pr->nk : 0));
+  L.bcount_offset = align(L.bpart_offset + (pr->beta_dev ? L.B * (size_t)pr->nk * L.bsplit * (L.S + 2 * L.P) : 0));
+  L.counter_offset = align(L.bcount_offset + (pr->beta_dev ? (L.B * (size_t)pr->nk + 1) / 2 : 0));      // sweep kernel: item queue
   L.total_bytes = (L.counter_offset + 32) * sizeof(double);
   return L;
 }
@@ -1209,6 +1223,9 @@ struct hm_beta_args {
   const double* weights;
   const double* scal;
   double* inl;                       // [B][S][nk]
+  int split;                         // row chunks per (model, k) matrix
+  double* part;                      // [B nk][split][S + 2 P] partial sums of the chunks
+  int* count;                        // [B nk] chunks finished (zeroed per launch)
 };
 
 template <int P>
@@ -1218,7 +1235,10 @@ __global__ void __launch_bounds__(256) hm_beta2h_kernel(const hm_beta_args a) {
   double* av = bsm;                                     // [P][nMp]  a_p[m] = w2[m] W_p(k,m) (no low-mass term)
   double* red = av + (size_t)P * a.nMp;                 // [8 warps][S + P]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ik = blockIdx.x % a.nk, b = blockIdx.x / a.nk, smp = b / a.F;
+  const int mat = blockIdx.x / a.split, chunk = blockIdx.x - mat * a.split;    // (model, wavenumber) matrix and my row chunk
+  const int ik = mat % a.nk, b = mat / a.nk, smp = b / a.F;
+  const int rows_per = (a.nM + a.split - 1) / a.split;
+  const int r0 = chunk * rows_per, r1 = (r0 + rows_per < a.nM) ? r0 + rows_per : a.nM;
   const double* sc = a.scal + (size_t)b * HM_NSCAL;
   const double A = sc[0], rhom = sc[1], w20 = sc[2], M0 = a.M[0];
   const double* w = a.weights + (size_t)b * NW * a.nMp;
@@ -1250,7 +1270,7 @@ __global__ void __launch_bounds__(256) hm_beta2h_kernel(const hm_beta_args a) {
       }
     if (lane >= S && lane < S + P) pu = lane - S;
   }
-  for (int m1 = warp; m1 < a.nM; m1 += 8) {
+  for (int m1 = r0 + warp; m1 < r1; m1 += 8) {
     const double* row = bk + (size_t)m1 * a.nM;
     double y[P];
 #pragma unroll
@@ -1297,11 +1317,26 @@ __global__ void __launch_bounds__(256) hm_beta2h_kernel(const hm_beta_args a) {
   }
   if (lane < S + P) red[warp * (S + P) + lane] = pair_acc;
   __shared__ double y0s[HM_MAXP];
-  if (warp == 0 && lane < P) y0s[lane] = y0;
+  __shared__ int s_last;
+  if (warp == 0 && lane < P) y0s[lane] = y0;          // (row 0 is warp 0's first row of chunk 0)
   __syncthreads();
+  // my chunk's sums: the eight warps in order; then the chunk that finds the others done adds the chunks in order
+  double* mypart = a.part + ((size_t)mat * a.split + chunk) * (S + 2 * P);
+  if (tid < S + P) {
+    double t = 0.;
+    for (int wi = 0; wi < 8; ++wi) t += red[wi * (S + P) + tid];
+    mypart[tid] = t;
+  } else if (tid < S + 2 * P) mypart[tid] = (chunk == 0) ? y0s[tid - S - P] : 0.;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(a.count + mat, 1) == a.split - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   if (tid < S) {
+    const double* pp = a.part + (size_t)mat * a.split * (S + 2 * P);
     double tot = 0.;
-    for (int wi = 0; wi < 8; ++wi) tot += red[wi * (S + P) + tid];
+    for (int c = 0; c < a.split; ++c) tot += __ldcg(pp + (size_t)c * (S + 2 * P) + tid);
     int u = 0, v = 0, cnt = 0;
 #pragma unroll
     for (int uu = 0; uu < P; ++uu)
@@ -1311,12 +1346,13 @@ __global__ void __launch_bounds__(256) hm_beta2h_kernel(const hm_beta_args a) {
         ++cnt;
       }
     double col_u = 0.;
-    for (int wi = 0; wi < 8; ++wi) col_u += red[wi * (S + P) + S + u];
+    for (int c = 0; c < a.split; ++c) col_u += __ldcg(pp + (size_t)c * (S + 2 * P) + S + u);
+    const double y0v = __ldcg(pp + S + P + v);
     // L_p = A W_p(k, M0)/M0 for mass tracers (:560-570); W_p(k, M0) = c_p[0] grid_p[k, 0]
     const double Lu = a.mass[u] ? A * (sc[4 + u] * a.gridW[u][goff]) / M0 : 0.;
     const double Lv = a.mass[v] ? A * (sc[4 + v] * a.gridW[v][goff]) / M0 : 0.;
     if (a.do_I11 && a.mass[u] && a.mass[v]) tot += bk[0] * Lu * Lv;                    // :559-560
-    if (a.do_I12_I21 && a.mass[u]) tot += Lu * y0s[v];                                 // :561-565  beta[0,:] with W_v
+    if (a.do_I12_I21 && a.mass[u]) tot += Lu * y0v;                                    // :561-565  beta[0,:] with W_v
     if (a.do_I12_I21 && a.mass[v]) tot += Lv * col_u;                                  // :566-570  beta[:,0] with W_u
     a.inl[((size_t)b * S + tid) * a.nk + ik] = tot * rhom * rhom;                      // :571
   }
@@ -1333,7 +1369,8 @@ static int hm_launch_beta(const hm_beta_args& a, int B, cudaStream_t st) {
     hm_set_error("beta_NL: %d tracers x %d masses do not fit in shared memory", P, a.nM);
     return HM_ERR_INVALID;
   }
-  hm_beta2h_kernel<P><<<B * a.nk, 256, smem, st>>>(a);
+  HM_CUDA_TRY(cudaMemsetAsync(a.count, 0, (size_t)B * a.nk * sizeof(int), st));
+  hm_beta2h_kernel<P><<<B * a.nk * a.split, 256, smem, st>>>(a);
   HM_LAUNCH_CHECK();
   return HM_OK;
 }
@@ -1714,6 +1751,7 @@ extern "C" int hm_mass_quadrature_stages(const hm_problem* pr, double* out_dev, 
   bt.vec2 = (pr->nM % 2 == 0) && !((uintptr_t)pr->beta_dev & 15);
   for (int p = 0; p < HM_MAXP; ++p) { bt.gridW[p] = a.gridW[p]; bt.mass[p] = (p < L.P) ? pr->tracers[p].mass_tracer : 0; }
   bt.weights = a.weights; bt.scal = e.scal; bt.inl = (double*)ws + L.inl_offset;
+  bt.split = L.bsplit; bt.part = (double*)ws + L.bpart_offset; bt.count = (int*)((double*)ws + L.bcount_offset);
   for (int p = 0; p < HM_MAXP; ++p) e.discrete[p] = (p < L.P) ? pr->tracers[p].discrete_tracer : 0;
   e.out = out_dev;
   cudaStream_t st = (cudaStream_t)stream;
