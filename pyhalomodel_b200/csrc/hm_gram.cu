@@ -39,8 +39,13 @@
 #endif
 #define HM_GPROD_WARPS 4
 #define HM_GTHREADS (32 * (HM_GMMA_WARPS + HM_GPROD_WARPS))
+#ifdef HM_GRAM_PRESCALE            // the producer warps also scale the staged tile in place and keep the diagonal work
+#define HM_GPROD_REGS 112
+#define HM_GMMA_REGS 192
+#else
 #define HM_GPROD_REGS 40
 #define HM_GMMA_REGS 232           // (split-triangle layout)
+#endif
 #define HM_GMMA_ALL_REGS 248       // whole-triangle MMA warps: 144 accumulator registers
 #define HM_GDIAG_REGS 152          // diagonal-work warps
 #define HM_G16_MMA_REGS 160        // sixteen-warp layout: launch at 128, DMMA warps 160, diagonal-work warps 112
@@ -325,10 +330,15 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
       if (Own::diag(I)) Dn[i++] = rec[PT + 8 * I];
     }
   };
+#ifdef HM_GRAM_PRESCALE            // the staged tile already holds Y = s_p * grid, and the producers keep the diagonal sums
+  constexpr bool PRE = true;
+#else
+  constexpr bool PRE = false;
+#endif
 #ifdef HM_GRAM_THREE_WAY           // no room for a block of factors in flight at 152 registers: load them with the fragments
   constexpr bool PREFETCH = false;
 #else
-  constexpr bool PREFETCH = true;
+  constexpr bool PREFETCH = !PRE;
 #endif
   if (PREFETCH) load_factors(gwb, ch, 0);
   for (int n = 0; n < nunits; ++n) {
@@ -349,7 +359,7 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
 #pragma unroll BLKU
     for (int blk = 0; blk < HM_GMCH / 8; ++blk) {
       double2 X[NBT], Y[NBT];
-      if (!PREFETCH) load_factors(gwb, ch, blk);
+      if (!PREFETCH && !PRE) load_factors(gwb, ch, blk);
 #pragma unroll
       for (int I = 0; I < NBT; ++I)
         X[I] = *reinterpret_cast<const double2*>(tile + (size_t)I * 8 * (HM_GMCH * 8) + ((((uint32_t)(4 * blk + fk)) ^ swz) << 4));
@@ -357,8 +367,16 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
         int i = 0;
 #pragma unroll
         for (int I = 0; I < NBT; ++I) {
-          Y[I] = make_double2(Sn[I].x * X[I].x, Sn[I].y * X[I].y);                               // Y = s_p * grid
-          if (Own::diag(I)) {
+#ifdef HM_GRAM_DEBUG_NO_SCALE      // (timing experiment, wrong results: the fragments go to the DMMAs unscaled)
+          Y[I] = X[I];
+#else
+          Y[I] = PRE ? X[I] : make_double2(Sn[I].x * X[I].x, Sn[I].y * X[I].y);                  // Y = s_p * grid
+#endif
+#ifdef HM_GRAM_DEBUG_NO_DIAG       // (timing experiment, wrong results: no two-halo / auto one-halo sums)
+          if (false) {
+#else
+          if (!PRE && Own::diag(I)) {
+#endif
             a2h[i] = fma(r2n.x, Y[I].x, fma(r2n.y, Y[I].y, a2h[i]));                             // sum_m r2 Y_p = sum_m w2 W_p  (:539)
             a1h[i] = fma(Dn[i].x * X[I].x, X[I].x, fma(Dn[i].y * X[I].y, X[I].y, a1h[i]));       // sum_m d_p U^2  (:475-477)
             ++i;
@@ -412,7 +430,7 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
             ++t;
           }
         }
-        if (Own::diag(I)) {
+        if (!PRE && Own::diag(I)) {
           // the four lanes of a tracer row hold its masses 2 fk, 2 fk + 1 (mod 8)
           double v2 = a2h[i], v1 = a1h[i];
           v2 += __shfl_xor_sync(0xffffffffu, v2, 1); v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
@@ -439,13 +457,21 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
   constexpr int STAGE_BYTES = HM_GRK * PT * HM_GMCH * 8;
   uint64_t* bars = reinterpret_cast<uint64_t*>(gsm + (size_t)HM_GNS * STAGE_BYTES);
   const uint32_t ring = hm_smem_addr(gsm), bar_full = hm_smem_addr(bars), bar_empty = hm_smem_addr(bars + HM_GNS);
+#ifdef HM_GRAM_PRESCALE
+  const uint32_t bar_raw = hm_smem_addr(bars + 2 * HM_GNS);   // the raw tile has landed (cp.async); bar_full: it has been scaled
+#else
+  const uint32_t bar_raw = bar_full;
+#endif
   const int P = a.P;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform: role dispatch does not diverge
   if (tid == 0) {
     for (int s = 0; s < HM_GNS; ++s) {
-      hm_mbar_init(bar_full + 8 * s, 32 * HM_GPROD_WARPS);    // one cp.async-driven arrival per producer thread
+      hm_mbar_init(bar_full + 8 * s, 32 * HM_GPROD_WARPS);    // one (cp.async-driven) arrival per producer thread
       hm_mbar_init(bar_empty + 8 * s, HM_GMMA_WARPS);
+#ifdef HM_GRAM_PRESCALE
+      hm_mbar_init(bar_raw + 8 * s, 32 * HM_GPROD_WARPS);
+#endif
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -468,6 +494,78 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
     const int nunits = (int)(u1 - u0);
     // my 16-byte slots of a stage: (wavenumber r, tracer pg * 8 + pq), slot c XOR-swizzled by the tracer's parity
     const uint32_t dst_thread = (uint32_t)((pq * SLOTS + (c ^ ((pq & 1) << 2))) * 16);
+#ifdef HM_GRAM_PRESCALE
+    // ---- second duty of the role: once a raw tile has landed, scale it IN PLACE (Y = s_p * grid, what the DMMAs contract) and
+    // keep the diagonal work -- the two-halo sums sum_m r2 Y_p and the auto one-halo sums sum_m d_p grid^2 -- so that the MMA
+    // warps issue nothing on the FP64 pipe but DMMAs (scaling and diagonal work on them cost 33 of 117 us).  A thread owns
+    // SPT 16-byte slots of one tracer row for the four wavenumbers (slot order rotated by the tracer: no bank conflicts);
+    // it reads and writes only its own slots, so the pass needs no synchronisation beyond the two barriers.
+    constexpr int TPT = 32 * HM_GPROD_WARPS / PT, SPT = SLOTS / TPT;   // threads per tracer row; slots per thread
+    const int sp = pt / TPT, part = pt - sp * TPT;
+    const uint32_t swz_s = (uint32_t)(sp & 1) << 2;
+    double a2h[HM_GRK], a1h[HM_GRK];
+#pragma unroll
+    for (int r = 0; r < HM_GRK; ++r) a2h[r] = a1h[r] = 0.;
+    long long Gq = G;                                   // cursor of the unit being scaled (one behind the copies)
+    int chq = ch;
+    const double* __restrict__ gwq = a.gw + (size_t)b * a.gw_stride;
+    int ginq = g, sq = 0;
+    uint32_t parq = 0;
+    auto scale_unit = [&](bool last) {
+      constexpr int JB = SPT < 4 ? SPT : 4;             // slots per pass: the factors of a pass stay in registers (36 at JB = 4)
+      unsigned char* st = gsm + (size_t)sq * STAGE_BYTES;
+#pragma unroll
+      for (int j0 = 0; j0 < SPT; j0 += JB) {
+        double2 fS[JB], fD[JB], fR[JB];
+        uint32_t off[JB];
+#pragma unroll
+        for (int j = 0; j < JB; ++j) {                  // (first pass: the factors fly while the tile lands)
+          const int cs = part * SPT + ((j0 + j + sp) & (SPT - 1));
+          const int mm = chq * HM_GMCH + 2 * cs;
+          const int mc = (mm < a.nMp - 2) ? mm : a.nMp - 2;
+          const double2* rec = reinterpret_cast<const double2*>(gwq + (2 * a.nMp + (mc >> 1) * HM_GREC(PT)));
+          fS[j] = rec[sp]; fD[j] = rec[PT + sp]; fR[j] = rec[2 * PT];
+          off[j] = (uint32_t)((sp * SLOTS + (cs ^ swz_s)) * 16);
+        }
+        if (j0 == 0) hm_mbar_wait(bar_raw + 8 * sq, parq);
+#pragma unroll
+        for (int r = 0; r < HM_GRK; ++r)
+#pragma unroll
+          for (int j = 0; j < JB; ++j) {
+            double2* q = reinterpret_cast<double2*>(st + (size_t)r * PT * SLOTS * 16 + off[j]);
+            const double2 X = *q;
+            const double2 Y = make_double2(fS[j].x * X.x, fS[j].y * X.y);
+            a2h[r] = fma(fR[j].x, Y.x, fma(fR[j].y, Y.y, a2h[r]));                             // sum_m w2 W_p  (:539)
+            a1h[r] = fma(fD[j].x * X.x, X.x, fma(fD[j].y * X.y, X.y, a1h[r]));                 // sum_m d_p U^2  (:475-477)
+            *q = Y;
+          }
+      }
+      hm_mbar_arrive(bar_full + 8 * sq);                // (release: the MMA warps' wait sees my stores)
+      if (++sq == HM_GNS) { sq = 0; parq ^= 1u; }
+      if (chq == a.CH - 1 || last) {                    // the group ends here for this CTA: my rows' diagonal sums
+        const int jslot = (int)blockIdx.x - hm_gram_cta_of(Gq * a.CH, a.total, a.ncta);
+        double* dstp = a.partial + ((size_t)Gq * a.J + jslot) * (size_t)a.NW * HM_GRK;
+#pragma unroll
+        for (int r = 0; r < HM_GRK; ++r) {
+          double v2 = a2h[r], v1 = a1h[r];
+#pragma unroll
+          for (int o = TPT / 2; o >= 1; o >>= 1) {
+            v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+          }
+          if (part == 0 && sp < P) {
+            dstp[(size_t)sp * HM_GRK + r] = v2;
+            dstp[(size_t)(P + sp) * HM_GRK + r] = v1;
+          }
+          a2h[r] = a1h[r] = 0.;
+        }
+      }
+      if (++chq == a.CH) {
+        chq = 0; ++Gq;
+        if (++ginq == a.ngroups) { ginq = 0; gwq += a.gw_stride; }
+      }
+    };
+#endif
     for (int n = 0; n < nunits; ++n) {
       const int smp = b / a.F, row0 = g * HM_GRK;
       const int m = ch * HM_GMCH + 2 * c;
@@ -487,13 +585,19 @@ __global__ void __launch_bounds__(HM_GTHREADS, 1) hm_gram_kernel(const hm_gram_a
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(on ? 16 : 0) : "memory");
         }
       }
-      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_full + 8 * s) : "memory");
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_raw + 8 * s) : "memory");
       if (++s == HM_GNS) { s = 0; parity ^= 1u; }
       if (++ch == a.CH) {
         ch = 0;
         if (++g == a.ngroups) { g = 0; ++b; }
       }
+#ifdef HM_GRAM_PRESCALE
+      if (n >= 1) scale_unit(false);                    // the unit before this one: its copies were issued an iteration ago
+#endif
     }
+#ifdef HM_GRAM_PRESCALE
+    if (nunits >= 1) scale_unit(true);
+#endif
     return;
   }
 
@@ -726,7 +830,7 @@ extern "C" int hm_gram_power_spectrum_stages(const hm_gram_problem* pr, double* 
   g.gw = wsd; g.partial = wsd + L.partial_offset;
   // the kernel is instantiated for block grids of 2, 4 and 8 (16, 32, 64 tracer rows); pad up to the next one
   const int NBT = L.PTK / 8;
-  const size_t smem = (size_t)HM_GNS * HM_GRK * (8 * NBT) * HM_GMCH * sizeof(double) + 64;
+  const size_t smem = (size_t)HM_GNS * HM_GRK * (8 * NBT) * HM_GMCH * sizeof(double) + 128;
   static hm_once_per_device once;
   if (once.needed()) {
     HM_CUDA_TRY(cudaFuncSetAttribute(hm_gram_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
