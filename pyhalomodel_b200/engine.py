@@ -150,7 +150,7 @@ def low_mass_correction(descs, nu0):
 
 def average(desc: ModelDesc, M, sigma, funcs):
     """funcs: [nf, nM] -> [nf] halo averages (model.average, pyhalomodel.py:335-359)."""
-    M, sigma, funcs = to_dev(M), to_dev(sigma), to_dev(funcs)
+    M, sigma, funcs = to_dev_many([M, sigma, funcs])      # (host arrays go up in one copy)
     if funcs.dim() == 1:
         funcs = funcs[None, :]
     nf, nM = funcs.shape
