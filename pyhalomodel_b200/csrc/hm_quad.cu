@@ -852,6 +852,11 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
 // round-robin (CTA c takes c, c + grid, ...), so the row tiles of one sample run at the same time on neighbouring
 // SMs and its weight vectors come from DRAM once and from L2 for the other tiles.
 // ---------------------------------------------------------------------------------------------------------------
+// 16-byte shared-memory load from a 32-bit shared-window address
+__device__ __forceinline__ double2 hm_lds2(uint32_t addr) {
+  return *reinterpret_cast<const double2*>(__cvta_shared_to_generic(addr));
+}
+
 __device__ __forceinline__ void hm_tma_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar) : "memory");
@@ -1020,8 +1025,10 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
       for (int j = 0; j < NV; ++j) acc[r][j] = 0.;
 #pragma unroll 1
     for (int st = 0; st < nstages; ++st) {
-      const unsigned char* stage = smem_raw + (size_t)s * C::STAGE_BYTES;
-      const unsigned char* wsm = stage + C::DATA_BYTES + wcol;
+      // (32-bit shared-window addresses, turned into pointers only at the load: a generic stage pointer made the compiler
+      // rebuild the shared window's base -- S2UR, ULEA and a scoreboard wait -- at the top of every stage)
+      const uint32_t stage = ring + (uint32_t)s * C::STAGE_BYTES;
+      const uint32_t wsm = stage + C::DATA_BYTES + wcol;
       if (!landed) hm_mbar_wait(bar_full + 8 * s, parity);    // the stage's boxes have landed
       const int sn = (s + 1 == NS) ? 0 : s + 1;
       const uint32_t pn = (s + 1 == NS) ? parity ^ 1u : parity;
@@ -1035,15 +1042,14 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
         for (int r = 0; r < NR; ++r)
 #pragma unroll
           for (int p = 0; p < P; ++p)
-            x[r][p] = *reinterpret_cast<const double2*>(stage + (size_t)(p * C::NBOX) * C::BOX_BYTES + r * (32 * 128) +
-                                                        (cp == 0 ? xo0 : xo1));
+            x[r][p] = hm_lds2(stage + (uint32_t)((p * C::NBOX) * C::BOX_BYTES + r * (32 * 128)) + (cp == 0 ? xo0 : xo1));
         // basis values of my two rows and two columns, in the order of the sums: A_p G_p, T_p G_p^2, (A_u G_u)(A_v G_v).
         // The tracer factors are lane-uniform: broadcast 16-byte loads, like the mass-function weights below.
         double2 v[NR][NW];
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-          const double2 Av = *reinterpret_cast<const double2*>(wsm + ((2 * FM + p) * CS + 2 * cp) * 8);
-          const double2 Tv = *reinterpret_cast<const double2*>(wsm + ((2 * FM + P + p) * CS + 2 * cp) * 8);
+          const double2 Av = hm_lds2(wsm + (uint32_t)(((2 * FM + p) * CS + 2 * cp) * 8));
+          const double2 Tv = hm_lds2(wsm + (uint32_t)(((2 * FM + P + p) * CS + 2 * cp) * 8));
 #pragma unroll
           for (int r = 0; r < NR; ++r) {
             v[r][p] = make_double2(Av.x * x[r][p].x, Av.y * x[r][p].y);
@@ -1065,8 +1071,8 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
         }
 #pragma unroll
         for (int f = 0; f < FM; ++f) {
-          const double2 w2 = *reinterpret_cast<const double2*>(wsm + (f * CS + 2 * cp) * 8);            // two-halo weight
-          const double2 w1 = *reinterpret_cast<const double2*>(wsm + ((FM + f) * CS + 2 * cp) * 8);     // one-halo weight
+          const double2 w2 = hm_lds2(wsm + (uint32_t)((f * CS + 2 * cp) * 8));                          // two-halo weight
+          const double2 w1 = hm_lds2(wsm + (uint32_t)(((FM + f) * CS + 2 * cp) * 8));                   // one-halo weight
 #pragma unroll
           for (int i = 0; i < NW; ++i) {
             const double2 w = (i < P) ? w2 : w1;
