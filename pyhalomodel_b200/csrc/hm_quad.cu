@@ -14,9 +14,9 @@
 //                          grid; 8 independent consumer warps keep the weights of their 2*H mass columns in
 //                          registers, accumulate R*(P+S) sums, reduce them over the warp with a transposing
 //                          shuffle network and store the warp's partial row sums (no CTA-wide synchronisation).
-//   hm_quad_rows_kernel    sweeps with five models per sample (one or two tracers): a lane owns two wavenumber
-//                          rows for the whole mass axis, the weights are broadcast from shared memory, and
-//                          nothing is reduced across lanes (see the comment above the kernel).
+//   hm_quad_rows_kernel    sweeps with two to five models per sample on one to three tracers: a lane owns two
+//                          wavenumber rows (one at three tracers) for the whole mass axis, the weights are broadcast
+//                          from shared memory, and nothing is reduced across lanes (see the comment above the kernel).
 //   hm_quad_kernel         fallback of the same arithmetic with plain (scalar or 16-byte) loads for odd nM,
 //                          unaligned grids or profiles with separate Uk/Wk grids.
 //   hm_beta2h_kernel       optional non-linear halo bias: I_NL = rhom^2 a_u^T beta_k a_v + edge terms (:546-571)
@@ -833,9 +833,9 @@ __global__ void __launch_bounds__(HM_STREAM_THREADS, 1) hm_quad_stream_kernel(co
 //
 // With FM*(P+S) = 25 sums per grid row and only 16 bytes of grid per (k, M) point, the column-per-lane kernel above
 // drowns in its warp reductions (one 32-value shuffle network per 50 FMAs; ncu: 423 instructions per warp tile,
-// FP64 pipe 29 %).  Here a lane owns two wavenumber rows (lane and lane + 32 of a 64-row tile) for the whole mass
-// axis, so its FM*(P+S) sums per row stay in registers from the first mass to the last and nothing is ever
-// reduced across lanes.  The weights of a mass column are the same for every lane: they ride in the ring next to
+// FP64 pipe 29 %).  Here a lane owns two wavenumber rows (lane and lane + 32 of a 64-row tile; ONE row of a 32-row tile
+// at three tracers, whose 9 FM sums per row would not fit twice) for the whole mass axis, so its FM*(P+S) sums per row
+// stay in registers from the first mass to the last and nothing is ever reduced across lanes.  The weights of a mass column are the same for every lane: they ride in the ring next to
 // the grid tile and are read with broadcast 16-byte shared-memory loads, one load feeding four FMAs (two rows x two
 // columns).
 //
@@ -1043,7 +1043,7 @@ __global__ void __launch_bounds__(HM_ROWS_LAUNCH_THREADS, 1) hm_quad_rows_kernel
 #pragma unroll
           for (int p = 0; p < P; ++p)
             x[r][p] = hm_lds2(stage + (uint32_t)((p * C::NBOX) * C::BOX_BYTES + r * (32 * 128)) + (cp == 0 ? xo0 : xo1));
-        // basis values of my two rows and two columns, in the order of the sums: A_p G_p, T_p G_p^2, (A_u G_u)(A_v G_v).
+        // basis values of my rows and two columns, in the order of the sums: A_p G_p, T_p G_p^2, (A_u G_u)(A_v G_v).
         // The tracer factors are lane-uniform: broadcast 16-byte loads, like the mass-function weights below.
         double2 v[NR][NW];
 #pragma unroll
