@@ -24,7 +24,8 @@ for g in range(G):          # cheap synthetic variation around one cosmology (th
     c[g] = concentration(M, zz, halo_definition='Mvir')
     Nc, Ns = HOD_mean(M, method='Zheng et al. (2005)', **syn.draw_hod(rng)); Vc, Vs, _ = HOD_variance(Nc, Ns)
     N[g], V[g] = Nc+Ns, Vc+Vs
-hs = sweep.HostSweep(k, M, syn.FAMILY_NAMES, chunk=512)
+CH = int(sys.argv[2]) if len(sys.argv) > 2 else 512
+hs = sweep.HostSweep(k, M, syn.FAMILY_NAMES, chunk=CH)
 out = hs.run(z, Om, Dv, dc, Pk, sig, rv, c, N, V)
 assert np.isfinite(out).all()
 torch.cuda.synchronize(); t0 = time.perf_counter()
