@@ -352,6 +352,65 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
     const bool last_unit = n == nunits - 1;
     hm_mbar_wait(bar_full + 8 * s, parity);             // the chunk has landed
     const unsigned char* tile = gsm + (size_t)s * STAGE_BYTES + (size_t)krow * PT * (HM_GMCH * 8) + (size_t)fr * (HM_GMCH * 8);
+#ifdef HM_GRAM_SWPIPE
+    // (experiment) software pipeline inside a chunk: the fragments of block b + 1 are loaded before the DMMAs of block b and
+    // scaled BETWEEN them (one fragment every 36 / 8 DMMAs), so that the scaling and diagonal instructions queue behind
+    // this warp's own DMMAs -- which it would have to wait for anyway -- instead of forming a phase of their own
+    {
+      constexpr int NBLK = HM_GMCH / 8, NDM = 2 * NB;
+      double2 Y[NBT];
+      auto load_x = [&](int blk, double2 (&X)[NBT]) {
+#pragma unroll
+        for (int I = 0; I < NBT; ++I)
+          X[I] = *reinterpret_cast<const double2*>(tile + (size_t)I * 8 * (HM_GMCH * 8) + ((((uint32_t)(4 * blk + fk)) ^ swz) << 4));
+      };
+      auto scale_frag = [&](int I, double2 (&X)[NBT]) {      // X[I] -> Y = s_p * grid in place, after the diagonal work on it
+        int i = 0;
+#pragma unroll
+        for (int J = 0; J < NBT; ++J)
+          if (J < I && Own::diag(J)) ++i;
+        const double2 x = X[I];
+        const double2 y = make_double2(Sn[I].x * x.x, Sn[I].y * x.y);
+        if (Own::diag(I)) {
+          a2h[i] = fma(r2n.x, y.x, fma(r2n.y, y.y, a2h[i]));
+          a1h[i] = fma(Dn[i].x * x.x, x.x, fma(Dn[i].y * x.y, x.y, a1h[i]));
+        }
+        X[I] = y;
+      };
+      {
+        double2 X0[NBT];
+        load_x(0, X0);
+#pragma unroll
+        for (int I = 0; I < NBT; ++I) { scale_frag(I, X0); Y[I] = X0[I]; }
+      }
+#pragma unroll
+      for (int blk = 0; blk < NBLK; ++blk) {
+        const bool more = blk < NBLK - 1;
+        double2 Xn[NBT];
+        if (more) { load_factors(gwb, ch, blk + 1); load_x(blk + 1, Xn); }
+        else if (!last_unit) load_factors(gwN, chN, 0);
+        int cnt = 0, kf = 0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          int t = 0;
+#pragma unroll
+          for (int I = 0; I < NBT; ++I)
+            if (Own::mma(I)) {
+#pragma unroll
+              for (int Jb = I; Jb < NBT; ++Jb) {
+                hm_dmma884(acc[t][0], acc[t][1], half ? Y[I].y : Y[I].x, half ? Y[Jb].y : Y[Jb].x);
+                ++t; ++cnt;
+                if (more && kf < NBT && cnt == ((kf + 1) * NDM) / NBT) { scale_frag(kf, Xn); ++kf; }
+              }
+            }
+        }
+        if (more) {
+#pragma unroll
+          for (int I = 0; I < NBT; ++I) Y[I] = Xn[I];
+        }
+      }
+    }
+#else
 #ifndef HM_GRAM_BLK_UNROLL
 #define HM_GRAM_BLK_UNROLL 1
 #endif
@@ -403,6 +462,7 @@ __device__ __forceinline__ void hm_gram_mma_role(const hm_gram_args& a, const un
           }
       }
     }
+#endif
     __syncwarp();
     if (lane == 0) hm_mbar_arrive(bar_empty + 8 * s);   // my reads of the stage have been consumed
     if (++s == HM_GNS) { s = 0; parity ^= 1u; }
