@@ -203,11 +203,14 @@ __global__ void __launch_bounds__(256) hm_window_iso_kernel(const double* __rest
   }
 }
 
-// (sample, 256-mass block) CTAs along x; the wavenumber axis is split along y only as far as needed to fill the GPU, so
-// that big batches keep a thread's per-mass constants for all wavenumbers
+// (sample, 256-mass block) CTAs along x; the wavenumber axis is split along y as far as needed for a launch of many waves of
+// CTAs (a thread's per-mass constants are cheap next to the wavenumbers it still walks)
 static dim3 hm_window_grid(int nk, int nM, int G) {
   const long long bx = (long long)G * ((nM + 255) / 256);
-  long long by = ((long long)hm_num_sms() * 4 + bx - 1) / bx;
+#ifndef HM_WINDOW_WAVES
+#define HM_WINDOW_WAVES 16       // CTAs per resident CTA slot (4 per SM): enough of them that the last wave is a small part --
+#endif                           // 2048 equal CTAs on 592 slots are 3.46 waves, i.e. four, 14 % of them empty
+  long long by = ((long long)hm_num_sms() * 4 * HM_WINDOW_WAVES + bx - 1) / bx;
   if (by > nk) by = nk;
   if (by < 1) by = 1;
   return dim3((unsigned)bx, (unsigned)by);
