@@ -123,11 +123,14 @@ static hm_layout hm_make_layout(const hm_problem* pr) {
   L.inl_offset = align(L.partial_offset + L.B * (size_t)L.nparts * L.NW * (size_t)pr->nk);
   // beta_NL: a (model, k) matrix is one CTA's worth of streaming (8 MB at 1024 masses), and B nk CTAs seldom divide evenly
   // over the SMs (256 over 148: the SMs with two take twice as long, 0.81 of the HBM peak); cut every matrix into row chunks
-  // so that there are at least six CTAs per SM, each with its own partial sums, finished by the last chunk to arrive
+  // so that there are at least sixteen CTAs per SM (measured: 449 / 377 / 354 / 337 / 356 us at 3 / 6 / 9 / 16 / 24 for
+  // 256 x 1024^2), each with its own partial sums, finished by the last chunk to arrive
   L.bsplit = 1;
   if (pr->beta_dev) {
     const long long mats = (long long)L.B * pr->nk;
-    long long sp = (6LL * hm_num_sms() + mats - 1) / mats;
+    static const char* env = getenv("HALOB200_BETA_CTAS_PER_SM");      // (A/B switch for timing runs)
+    const long long per_sm = env ? atoll(env) : 16;
+    long long sp = (per_sm * hm_num_sms() + mats - 1) / mats;
     const long long most = (pr->nM + 63) / 64;                     // at least 64 rows per chunk
     sp = sp > most ? most : sp;
     L.bsplit = (int)(sp < 1 ? 1 : (sp > 16 ? 16 : sp));
